@@ -1,0 +1,371 @@
+"""ORACLE (test infrastructure): verifier-side replay of a Boojum proof, used to pin the oracle's
+Poseidon2 / sponge / Merkle / transcript / DEEP / FRI-fold restatements against the reference's own
+golden fixture (proof.json + vk.json).
+
+Follows, step by step:
+  * AlgebraicSpongeBasedTranscript        src/cs/implementations/transcript.rs:62-129
+  * BoolsBuffer::get_bits                 src/cs/implementations/transcript.rs:369-417
+  * compute_fri_schedule                  src/cs/implementations/prover.rs:2281-2372
+  * materialize_ext_challenge_powers      src/cs/implementations/prover.rs:2374-2395
+  * Verifier::verify (transcript order, query loop, DEEP regrouping, FRI chain)
+                                          src/cs/implementations/verifier.rs:888-1145, 1817-2510
+Pure Python ints for the (tiny) field work; Poseidon2 goes through the C oracle so that the C code is
+what gets pinned.
+"""
+import numpy as np
+
+from . import oracle as O
+
+P = O.P
+
+
+# ------------------------------------------------------------------ Fp / Fp2 on Python ints -------
+def fadd(a, b):
+    return (a + b) % P
+
+
+def fsub(a, b):
+    return (a - b) % P
+
+
+def fmul(a, b):
+    return (a * b) % P
+
+
+def finv(a):
+    return pow(a, P - 2, P)
+
+
+def e_add(a, b):
+    return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+
+
+def e_sub(a, b):
+    return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+
+
+def e_mul(a, b):
+    return ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def e_mul_base(a, b):
+    return ((a[0] * b) % P, (a[1] * b) % P)
+
+
+def e_inv(a):
+    n = (a[0] * a[0] - 7 * a[1] * a[1]) % P
+    ni = finv(n)
+    return ((a[0] * ni) % P, ((P - a[1]) * ni) % P)
+
+
+def omega(log_n):
+    w = 0x185629DCDA58878C
+    for _ in range(log_n, 32):
+        w = w * w % P
+    return w
+
+
+# ------------------------------------------------------------------------------ transcript --------
+class Poseidon2Transcript:
+    """GoldilocksPoisedon2Transcript = AlgebraicSpongeBasedTranscript<_, 8, 12, 4, Poseidon2, Overwrite>."""
+
+    def __init__(self):
+        self.buffer = []
+        self.available = []
+        self.state = np.zeros(12, np.uint64)
+
+    def witness_field_elements(self, els):
+        self.buffer.extend(int(e) % P for e in els)
+
+    def witness_merkle_tree_cap(self, cap):
+        for digest in cap:
+            self.witness_field_elements(digest)
+
+    def get_challenge(self):
+        if not self.buffer:
+            if self.available:
+                return self.available.pop(0)
+            self.state = O.poseidon2_permutation(self.state)
+            self.available = [int(x) for x in self.state[:8]]
+            return self.get_challenge()
+        to_absorb = self.buffer + [1]
+        self.buffer = []
+        while len(to_absorb) % 8:
+            to_absorb.append(0)
+        for i in range(0, len(to_absorb), 8):
+            self.state[:8] = np.array(to_absorb[i:i + 8], dtype=np.uint64)
+            self.state = O.poseidon2_permutation(self.state)
+        self.available = [int(x) for x in self.state[:8]]
+        return self.get_challenge()
+
+    def get_ext_challenge(self):
+        c0 = self.get_challenge()
+        c1 = self.get_challenge()
+        return (c0, c1)
+
+
+class BoolsBuffer:
+    def __init__(self, max_needed):
+        self.available = []
+        self.max_needed = max_needed
+
+    def get_bits(self, transcript, num_bits):
+        while len(self.available) < num_bits:
+            el = transcript.get_challenge()
+            for b in range(64 - self.max_needed):
+                self.available.append((el >> b) & 1)
+        out, self.available = self.available[:num_bits], self.available[num_bits:]
+        return out
+
+
+def compute_fri_schedule(security_bits, cap_size, pow_bits, rate_log2, initial_degree_log2):
+    raw = security_bits - pow_bits
+    new_pow = pow_bits
+    if raw % rate_log2 != 0:
+        if new_pow >= rate_log2 - (raw % rate_log2):
+            new_pow -= rate_log2 - (raw % rate_log2)
+    raw = security_bits - new_pow
+    num_queries = raw // rate_log2 + (1 if raw % rate_log2 else 0)
+    stop = max(1, cap_size >> rate_log2)
+    stop_log2 = stop.bit_length() - 1
+    deg = initial_degree_log2
+    cap_log2 = cap_size.bit_length() - 1
+    schedule = []
+    while deg > stop_log2:
+        if deg + rate_log2 <= cap_log2:
+            break
+        if deg - stop_log2 >= 3:
+            deg -= 3
+            schedule.append(3)
+        elif deg - stop_log2 == 2:
+            deg -= 2
+            schedule.append(2)
+        else:
+            deg -= 1
+            schedule.append(1)
+            break
+        if deg + rate_log2 <= cap_log2:
+            break
+    return new_pow, num_queries, schedule, 1 << deg
+
+
+def ext_powers(c, count):
+    out = [(1, 0), c]
+    cur = c
+    for _ in range(2, count):
+        cur = e_mul(cur, c)
+        out.append(cur)
+    return out[:count]
+
+
+def _ext(d):
+    return (d["coeffs"][0], d["coeffs"][1])
+
+
+# ----------------------------------------------------------------------------- replay -------------
+def replay_proof(fixture, num_variable_polys=None):
+    """Replays transcript + queries of the fixture; returns a dict of per-check counters.
+
+    Raises AssertionError at the first mismatch.
+    """
+    vk, proof = fixture["vk"], fixture["proof"]
+    fp = vk["fixed_parameters"]
+    n = fp["domain_size"]
+    log_n = n.bit_length() - 1
+    L = proof["proof_config"]["fri_lde_factor"]
+    log_L = L.bit_length() - 1
+    cap_size = proof["proof_config"]["merkle_tree_cap_size"]
+    Q = fp["quotient_degree"]
+    lk = fp["lookup_parameters"]["UseSpecializedColumnsWithTableIdAsConstant"]
+    lookup_width, num_sub = lk["width"], lk["num_repetitions"]
+    num_mult = 1
+
+    tr = Poseidon2Transcript()
+    tr.witness_merkle_tree_cap(vk["setup_merkle_tree_cap"])
+    for v in proof["public_inputs"]:
+        tr.witness_field_elements([v])
+    tr.witness_merkle_tree_cap(proof["witness_oracle_cap"])
+    beta = tr.get_ext_challenge()
+    gamma = tr.get_ext_challenge()
+    lookup_beta = tr.get_ext_challenge()
+    lookup_gamma = tr.get_ext_challenge()
+    tr.witness_merkle_tree_cap(proof["stage_2_oracle_cap"])
+    alpha = tr.get_ext_challenge()
+    tr.witness_merkle_tree_cap(proof["quotient_oracle_cap"])
+    z = tr.get_ext_challenge()
+    for group in ("values_at_z", "values_at_z_omega", "values_at_0"):
+        for v in proof[group]:
+            tr.witness_field_elements(_ext(v))
+
+    # public inputs grouped by opening point (verifier.rs:1074-1108)
+    w_n = omega(log_n)
+    pi_groups = []
+    for (col, row), val in zip(fp["public_inputs_locations"], proof["public_inputs"]):
+        at = pow(w_n, row, P)
+        for g in pi_groups:
+            if g[0] == at:
+                g[1].append((col, val))
+                break
+        else:
+            pi_groups.append((at, [(col, val)]))
+
+    c = tr.get_ext_challenge()
+    total_ch = len(proof["values_at_z"]) + len(proof["values_at_z_omega"]) + len(proof["values_at_0"])
+    total_ch += sum(len(g[1]) for g in pi_groups)
+    ch = ext_powers(c, total_ch)
+
+    new_pow, num_queries, schedule, final_degree = compute_fri_schedule(
+        proof["proof_config"]["security_level"], cap_size, proof["proof_config"]["pow_bits"], log_L, log_n)
+    assert new_pow == 0
+    assert num_queries == fixture["num_queries_total"]
+    assert len(schedule) - 1 == len(proof["fri_intermediate_oracles_caps"])
+
+    fri_challenges = []
+    caps = [proof["fri_base_oracle_cap"]] + list(proof["fri_intermediate_oracles_caps"])
+    for cap, k in zip(caps, schedule):
+        tr.witness_merkle_tree_cap(cap)
+        a = tr.get_ext_challenge()
+        pw = [a]
+        for _ in range(1, k):
+            pw.append(e_mul(pw[-1], pw[-1]))
+        fri_challenges.append(pw)
+    assert len(proof["final_fri_monomials"][0]) == final_degree
+    tr.witness_field_elements(proof["final_fri_monomials"][0])
+    tr.witness_field_elements(proof["final_fri_monomials"][1])
+
+    max_bits = log_n + log_L
+    bools = BoolsBuffer(max_bits)
+    powers = [omega(i) for i in range(max_bits + 1)]
+    powers_inv = [finv(x) for x in powers]
+    steps = [1, powers_inv[2], powers_inv[3], fmul(powers_inv[2], powers_inv[3])]
+
+    # layout (verifier.rs:2200-2214)
+    q0 = proof["queries_per_fri_repetition"][0]
+    num_partial = len(q0["stage_2_query"]["leaf_elements"]) // 2 - 1 - num_sub - num_mult
+    setup_len = len(q0["setup_query"]["leaf_elements"])
+    vw = len(q0["witness_query"]["leaf_elements"]) - num_mult  # variables + witness
+    V = num_variable_polys
+    if V is None:
+        # V + W = vw ; partial = ceil(V/Q) - 1 ; the geometry has num_witness_columns = 0
+        V = vw - fp["parameters"]["num_witness_columns"]
+    C = setup_len - V - (lookup_width + 1)
+
+    counters = dict(merkle_paths=0, deep=0, fri_levels=0, final=0)
+    z_omega = e_mul_base(z, w_n)
+    base_depth = max_bits - (cap_size.bit_length() - 1)
+
+    for q in proof["queries_per_fri_repetition"]:
+        bits = bools.get_bits(tr, max_bits)
+        inner = sum(b << i for i, b in enumerate(bits[:log_n]))
+        coset = sum(b << i for i, b in enumerate(bits[log_n:]))
+        idx = (coset << log_n) + inner
+
+        for name, cap in (("witness_query", proof["witness_oracle_cap"]),
+                          ("stage_2_query", proof["stage_2_oracle_cap"]),
+                          ("quotient_query", proof["quotient_oracle_cap"]),
+                          ("setup_query", vk["setup_merkle_tree_cap"])):
+            leaf = O.poseidon2_hash_leaf(np.array(q[name]["leaf_elements"], dtype=np.uint64))
+            path = np.array(q[name]["proof"], dtype=np.uint64).reshape(-1, 4)
+            assert path.shape[0] == base_depth
+            assert O.merkle_verify(leaf, path, np.array(cap, dtype=np.uint64), idx), (name, idx)
+            counters["merkle_paths"] += 1
+
+        x = 1
+        for b, pw in zip(bits, powers[1:]):
+            if b:
+                x = fmul(x, pw)
+        power_chunks, skip = [], 0
+        for k in schedule:
+            d = 1
+            for b, pw in list(zip(bits[skip:], powers_inv[1:]))[k:]:
+                if b:
+                    d = fmul(d, pw)
+            skip += k
+            power_chunks.append(d)
+        x_q = fmul(x, 7)
+
+        wq, sq = q["witness_query"]["leaf_elements"], q["stage_2_query"]["leaf_elements"]
+        qq, uq = q["quotient_query"]["leaf_elements"], q["setup_query"]["leaf_elements"]
+        base = lambda els: [(e, 0) for e in els]
+        ext = lambda els: [(els[i], els[i + 1]) for i in range(0, len(els), 2)]
+        off_partial = 2
+        off_lookup_a = off_partial + 2 * num_partial
+        off_lookup_b = off_lookup_a + 2 * num_sub
+        src = []
+        src += base(wq[:vw])                       # variables, witness
+        src += base(uq[V:V + C])                   # constants
+        src += base(uq[:V])                        # sigmas
+        src += ext(sq[0:2])                        # z
+        src += ext(sq[off_partial:off_lookup_a])   # partial products
+        src += base(wq[vw:vw + num_mult])          # multiplicities
+        src += ext(sq[off_lookup_a:off_lookup_b])  # lookup A
+        src += ext(sq[off_lookup_b:])              # lookup B
+        src += base(uq[V + C:V + C + lookup_width + 1])
+        src += ext(qq)
+        vals = [_ext(v) for v in proof["values_at_z"]]
+        assert len(src) == len(vals), (len(src), len(vals))
+
+        acc = (0, 0)
+        off = 0
+
+        def quot(acc, srcs, values, at, off):
+            a = O.deep_point(acc, srcs, values, ch[off:off + len(srcs)], x_q, at)
+            # cross-check the C restatement against Python ints
+            den = e_inv(e_sub((x_q, 0), at))
+            s = (0, 0)
+            for f, v, cc in zip(srcs, values, ch[off:off + len(srcs)]):
+                s = e_add(s, e_mul(cc, e_sub(f, v)))
+            assert a == e_add(acc, e_mul(s, den))
+            return a, off + len(srcs)
+
+        acc, off = quot(acc, src, vals, z, off)
+        acc, off = quot(acc, ext(sq[0:2]), [_ext(v) for v in proof["values_at_z_omega"]], z_omega, off)
+        acc, off = quot(acc, ext(sq[off_lookup_a:off_lookup_b]) + ext(sq[off_lookup_b:]),
+                        [_ext(v) for v in proof["values_at_0"]], (0, 0), off)
+        for at, items in pi_groups:
+            acc, off = quot(acc, [(wq[col], 0) for col, _ in items], [(val, 0) for _, val in items], (at, 0), off)
+        assert off == len(ch)
+
+        cur, subidx, coset_inv = acc, idx, finv(7)
+        x_interp = x_q
+        expected_len = base_depth
+        for lvl, (k, fq) in enumerate(zip(schedule, q["fri_queries"])):
+            expected_len -= k
+            deg = 1 << k
+            sub_in_leaf, tree_idx = subidx % deg, subidx >> k
+            le = fq["leaf_elements"]
+            assert len(le) == 2 * deg
+            assert (le[sub_in_leaf], le[deg + sub_in_leaf]) == cur, ("DEEP/FRI value mismatch at level", lvl)
+            if lvl == 0:
+                counters["deep"] += 1
+            leaf = O.poseidon2_hash_leaf(np.array(le, dtype=np.uint64))
+            path = np.array(fq["proof"], dtype=np.uint64).reshape(-1, 4)
+            assert path.shape[0] == expected_len
+            assert O.merkle_verify(leaf, path, np.array(caps[lvl], dtype=np.uint64), tree_idx)
+            counters["merkle_paths"] += 1
+            els = [(le[i], le[deg + i]) for i in range(deg)]
+            base_pow = power_chunks[lvl]
+            for a in fri_challenges[lvl]:
+                nxt = []
+                for i in range(0, len(els), 2):
+                    u, v = els[i], els[i + 1]
+                    pw = fmul(fmul(base_pow, steps[i // 2]), coset_inv)
+                    nxt.append(e_add(e_add(u, v), e_mul_base(e_mul(e_sub(u, v), a), pw)))
+                els = nxt
+                base_pow = fmul(base_pow, base_pow)
+                coset_inv = fmul(coset_inv, coset_inv)
+            for _ in range(k):
+                x_interp = fmul(x_interp, x_interp)
+            subidx, cur = tree_idx, els[0]
+            counters["fri_levels"] += 1
+
+        res = (0, 0)
+        for c0, c1 in reversed(list(zip(*proof["final_fri_monomials"]))):
+            res = e_add(e_mul_base(res, x_interp), (c0, c1))
+        assert res == cur, "final monomial evaluation mismatch"
+        counters["final"] += 1
+
+    counters["challenges"] = dict(beta=beta, gamma=gamma, lookup_beta=lookup_beta, lookup_gamma=lookup_gamma,
+                                  alpha=alpha, z=z, deep=c, fri=fri_challenges)
+    counters["schedule"] = schedule
+    return counters
