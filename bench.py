@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py - headline measurement for the Boojum polynomial-commitment hot path on B200.
+
+metric  : Goldilocks NTT G-elements/s (BASELINE.json metric, first half; the SHA-256 full-prove seconds need the
+          complete prover and are not produced by this round's bench).
+workload: BASELINE.json configs[1] "2^20-2^24 Goldilocks NTT/LDE sweep on 1xB200": one step = forward
+          natural->bit-reversed NTT on coset 7 (benches/benchmarks.rs:541 uses coset 7) of five resident batches,
+          n = 2^20..2^24 with 128/64/32/16/8 columns (1 GiB each, SURVEY.md 8(d) cfg 2), in place, through the
+          C-ABI (bj_ntt_natural_to_bitreversed).  5 GiB of inputs >> 126 MB L2, so no L2 flush is needed.
+value   : elements transformed per second, all ranks (columns shard across GPUs with no collective -> weak scaling).
+e2e     : the same sweep through bj_ntt_natural_to_bitreversed_host: pinned HOST buffers, H2D + NTT + D2H per step.
+roofline: dominant kernel ntt_pass_kernel; algorithmic bytes = 16 B per element per transform (read once, write
+          once) / measured HBM copy peak (MEASURED_PEAKS.json, burst figure).
+cpu_baseline / --impl reference: the oracle's restatement of the reference CPU algorithm (one serial NTT per column,
+          columns spread over all host threads, src/cs/implementations/utils.rs:295-304) on a bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZES = [20, 21, 22, 23, 24]
+BATCH_ELEMS_LOG = 27  # 1 GiB of u64 per size
+COSET = 7
+METRIC = "goldilocks_ntt_gelements_per_s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], 0, None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.reasons |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in names.items() if self.reasons & b], "samples": len(s)}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the oracle's restatement of the reference CPU path, all host threads, bounded sample."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle as O
+    threads = O.num_threads()
+    rng = np.random.default_rng(0)
+    cols = {m: max(1, min(threads, 1 << (BATCH_ELEMS_LOG - m))) for m in SIZES}
+    data = {m: O.random_field(rng, (cols[m], 1 << m)) for m in SIZES}
+    elems = sum(cols[m] << m for m in SIZES)
+
+    def step():
+        for m in SIZES:
+            a = data[m]
+            O.lib().orc_ntt_n2b(a.ctypes.data_as(ctypes.c_void_p), m, cols[m], 1 << m, COSET)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = elems / dt / 1e9
+    sample = "per step: forward NTT coset 7, sizes 2^20..2^24, %d column(s) each (one serial NTT per column, %d threads)" % (
+        cols[SIZES[0]], threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Gelem/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "ntt_forward_sweep_2^20..2^24_coset7 (bounded sample of the GPU arm's batches)"},
+        "cpu_baseline": {"value": val, "unit": "Gelem/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_sample():
+    import numpy as np
+    from oracle import oracle as O
+    threads = O.num_threads()
+    m = 22
+    cols = max(8, threads)
+    a = O.random_field(np.random.default_rng(1), (cols, 1 << m))
+    O.lib().orc_ntt_n2b(a.ctypes.data_as(ctypes.c_void_p), m, min(cols, threads), 1 << m, COSET)  # warm-up
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        O.lib().orc_ntt_n2b(a.ctypes.data_as(ctypes.c_void_p), m, cols, 1 << m, COSET)
+        reps += 1
+        if time.perf_counter() - t0 > 10.0 or reps >= 20:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": reps * cols * (1 << m) / dt / 1e9, "unit": "Gelem/s", "cores": threads, "kind": "port",
+            "sample": "%d x (%d columns of 2^22, forward NTT coset 7), one serial NTT per column over %d threads, %.1f s"
+                      % (reps, cols, threads, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import era_boojum_b200 as bj
+    from era_boojum_b200 import native
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = bj.Context.on_current_stream(local_rank)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    cols = {m: 1 << (BATCH_ELEMS_LOG - m) for m in SIZES}
+    # synthetic resident inputs: uniform 63-bit values (valid lazy field elements), created before the timed region
+    data = {m: torch.randint(0, 2**63 - 1, (cols[m], 1 << m), dtype=torch.int64, device=dev, generator=gen) for m in SIZES}
+    elems_per_step = sum(cols[m] << m for m in SIZES)
+
+    def step():
+        for m in SIZES:
+            ctx.fft_natural_to_bitreversed(data[m], COSET)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * elems_per_step / (ms * 1e-3) / 1e9
+
+    # per-size breakdown (device time, CUDA events, same stream), after the headline region
+    sweep = {}
+    for m in SIZES:
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(3):
+            ctx.fft_natural_to_bitreversed(data[m], COSET)
+        a1.record()
+        torch.cuda.synchronize()
+        t_ms = a0.elapsed_time(a1) / 3
+        el = cols[m] << m
+        sweep["2^%d" % m] = {"cols": cols[m], "ms": round(t_ms, 4), "gelem_s": round(el / t_ms / 1e6, 3),
+                             "algo_gbs": round(16 * el / t_ms / 1e6, 1)}
+
+    peak, peak_kind = load_peaks()
+    launches_per_step = launches / max(1, args.steps)
+    algo_bytes_step = 16.0 * elems_per_step
+    achieved = algo_bytes_step / (ms * 1e-3) / 1e9  # the step is ntt_pass_kernel launches only
+    roofline = {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": round(achieved, 1), "peak": peak,
+                "peak_source": peak_kind + " hbm copy", "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "algo_bytes_per_launch": algo_bytes_step / max(1.0, launches_per_step),
+                "avg_launch_ms": ms / max(1.0, launches_per_step), "traffic": None}
+
+    # end to end: pinned host buffers -> H2D -> NTT -> D2H through the host-buffer C-ABI entry point
+    e2e = None
+    if not args.no_e2e:
+        host = {m: torch.empty((cols[m], 1 << m), dtype=torch.int64).pin_memory() for m in SIZES}
+        for m in SIZES:
+            host[m].copy_(data[m])
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            for m in SIZES:
+                st = native.lib.bj_ntt_natural_to_bitreversed_host(ctx._h, ctypes.c_void_p(host[m].data_ptr()), m, cols[m], COSET)
+                if st != 0:
+                    raise bj.BoojumError(st, "host NTT failed")
+
+        e2e_step()
+        barrier()
+        k = max(1, min(args.steps, 3))
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(k):
+            e2e_step()
+        b1.record()
+        barrier()
+        e_ms = b0.elapsed_time(b1) / k
+        if world > 1:
+            t = torch.tensor([e_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": round(world * elems_per_step / (e_ms * 1e-3) / 1e9, 4), "unit": "Gelem/s",
+               "h2d_bytes_per_step": 8 * elems_per_step, "d2h_bytes_per_step": 8 * elems_per_step,
+               "ms_per_step": round(e_ms, 3), "steps": k}
+        del host
+
+    out = {
+        "metric": METRIC, "value": round(value, 4), "unit": "Gelem/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "ntt_forward_sweep_2^20..2^24_coset7", "sizes_log2": SIZES,
+                   "columns_per_size": [cols[m] for m in SIZES], "resident_bytes_per_gpu": 8 * elems_per_step,
+                   "l2": "inputs (5 GiB) larger than L2, no flush", "parallelism": "columns sharded x%d, no collective" % world},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "sweep": sweep, "e2e": e2e,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline_sample()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,197 @@
+"""era_boojum_b200 - B200-native backend for Boojum's polynomial-commitment hot path.
+
+Python host mirror of the reference plug points, over the C-ABI (libboojum_b200.so):
+
+    reference (Rust, /root/reference/src)                        here
+    --------------------------------------------------------     -------------------------------------------
+    Worker (worker/mod.rs:5-87)                                   Context (device + stream + cached tables)
+    P::fft_natural_to_bitreversed (field/traits/field_like.rs)    Context.fft_natural_to_bitreversed
+    P::ifft_natural_to_natural                                    Context.ifft_natural_to_natural
+    precompute_twiddles_for_fft (cs/implementations/utils.rs)     Context.precompute_twiddles_for_fft
+    transform_raw_storages_to_lde (utils.rs:270-309)              Context.transform_raw_storages_to_lde
+    MerkleTreeWithCap::construct* (cs/oracle/merkle_tree.rs)      Context.merkle_tree_construct -> MerkleTreeWithCap
+    fold step of do_fri (cs/implementations/fri/mod.rs)           Context.fri_fold
+
+Tensors are torch int64 CUDA tensors holding the u64 bit patterns (torch is plumbing: memory + streams).
+No CPU fallback exists: importing this package without the built library raises, and creating a Context
+without a CUDA device raises BoojumError(BJ_ERR_NO_DEVICE).
+"""
+import ctypes
+
+import numpy as np
+
+from . import native
+from .native import BoojumError, P, lib
+
+__all__ = ["Context", "MerkleTreeWithCap", "BoojumError", "P", "to_device", "to_numpy"]
+
+
+def to_device(a, device="cuda:0"):
+    """numpy uint64 array -> torch int64 CUDA tensor (same bits)."""
+    import torch
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return torch.from_numpy(a.view(np.int64)).to(device)
+
+
+def to_numpy(t):
+    """torch int64 tensor -> numpy uint64 array (same bits)."""
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+class MerkleTreeWithCap:
+    """cap_size / leaf_hashes / node_hashes_enumerated_from_leafs (cs/oracle/merkle_tree.rs:23-33)."""
+
+    def __init__(self, cap_size, leaf_hashes, nodes):
+        self.cap_size = cap_size
+        self.leaf_hashes = leaf_hashes  # [n_leaves, 4] int64 cuda
+        self.nodes = nodes              # [n_leaves - cap_size, 4]
+
+    def levels(self):
+        out, off, cnt = [], 0, self.leaf_hashes.shape[0]
+        while cnt > self.cap_size:
+            cnt //= 2
+            out.append(self.nodes[off:off + cnt])
+            off += cnt
+        return out
+
+    def get_cap(self):
+        """get_cap (merkle_tree.rs:451-460): canonical digests of the level with cap_size nodes."""
+        lv = self.levels()
+        return to_numpy(lv[-1] if lv else self.leaf_hashes)
+
+    def get_proof(self, idx):
+        """get_proof (merkle_tree.rs:462-480): (leaf hash, siblings bottom-up, cap level excluded)."""
+        lv = self.levels()
+        layers = ([self.leaf_hashes] + lv[:-1]) if lv else []
+        leaf = to_numpy(self.leaf_hashes[idx])
+        path = []
+        for layer in layers:
+            path.append(to_numpy(layer[idx ^ 1]))
+            idx >>= 1
+        return leaf, np.array(path, dtype=np.uint64).reshape(-1, 4)
+
+
+class Context:
+    """One device + one stream (the reference's Worker role)."""
+
+    def __init__(self, device=0, stream=None):
+        import torch
+        self._torch = torch
+        self.device = device
+        handle = ctypes.c_void_p()
+        st = lib.bj_ctx_create(device, ctypes.c_void_p(stream) if stream else None, ctypes.byref(handle))
+        if st != native.BJ_OK:
+            raise BoojumError(st, lib.bj_status_string(st).decode())
+        self._h = handle
+        self._stream = stream
+
+    @classmethod
+    def on_current_stream(cls, device=0):
+        import torch
+        with torch.cuda.device(device):
+            return cls(device, torch.cuda.current_stream().cuda_stream)
+
+    def close(self):
+        if self._h:
+            lib.bj_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != native.BJ_OK:
+            raise BoojumError(st, "%s: %s" % (lib.bj_status_string(st).decode(), lib.bj_last_error(self._h).decode()))
+
+    def synchronize(self):
+        self._check(lib.bj_ctx_synchronize(self._h))
+
+    def launch_count(self):
+        return int(lib.bj_launch_count(self._h))
+
+    @staticmethod
+    def _ptr(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def _cols(self, t):
+        assert t.is_cuda and t.dtype == self._torch.int64 and t.is_contiguous()
+        n = t.shape[-1]
+        assert n & (n - 1) == 0
+        return n.bit_length() - 1, t.numel() // n, n
+
+    # ---- NTT family ----
+    def precompute_twiddles_for_fft(self, fft_size, inverse=False):
+        log_n = fft_size.bit_length() - 1
+        out = self._torch.empty(max(1, fft_size // 2), dtype=self._torch.int64, device="cuda:%d" % self.device)
+        self._check(lib.bj_twiddles(self._h, log_n, int(inverse), self._ptr(out)))
+        return out
+
+    def fft_natural_to_bitreversed(self, cols, coset=1):
+        """In place on a [n_cols, n] (or [n]) tensor."""
+        log_n, n_cols, n = self._cols(cols)
+        self._check(lib.bj_ntt_natural_to_bitreversed(self._h, self._ptr(cols), log_n, n_cols, n, coset))
+        return cols
+
+    def ifft_natural_to_natural(self, cols, coset=1):
+        log_n, n_cols, n = self._cols(cols)
+        self._check(lib.bj_intt_natural_to_natural(self._h, self._ptr(cols), log_n, n_cols, n, coset))
+        return cols
+
+    def bitreverse_enumeration_inplace(self, cols):
+        log_n, n_cols, n = self._cols(cols)
+        self._check(lib.bj_bitreverse(self._h, self._ptr(cols), log_n, n_cols, n))
+        return cols
+
+    def transform_raw_storages_to_lde(self, cols, lde_degree, from_monomials=False, out=None):
+        """[n_cols, n] Lagrange values -> [n_cols, lde_degree, n] (coset-major, bit-reversed in coset)."""
+        log_n, n_cols, n = self._cols(cols)
+        log_l = lde_degree.bit_length() - 1
+        if out is None:
+            out = self._torch.empty((n_cols, lde_degree, n), dtype=self._torch.int64, device=cols.device)
+        self._check(lib.bj_lde(self._h, self._ptr(cols), n, self._ptr(out), log_n, log_l, n_cols, int(from_monomials)))
+        return out
+
+    # ---- Merkle ----
+    def merkle_tree_construct(self, sources, cap_size, elems_per_leaf=1):
+        """sources: list of flat int64 CUDA tensors in leaf-preimage order (MerkleTreeWithCap::construct for
+        elems_per_leaf == 1, construct_by_chunking[_from_flat_sources] otherwise)."""
+        torch = self._torch
+        n_leaves = sources[0].numel() // elems_per_leaf
+        for s in sources:
+            assert s.is_cuda and s.dtype == torch.int64 and s.is_contiguous() and s.numel() == n_leaves * elems_per_leaf
+        ptrs = (ctypes.c_void_p * len(sources))(*[s.data_ptr() for s in sources])
+        dev = sources[0].device
+        leaf_hashes = torch.empty((n_leaves, 4), dtype=torch.int64, device=dev)
+        nodes = torch.empty((max(n_leaves - cap_size, 1), 4), dtype=torch.int64, device=dev)
+        self._check(lib.bj_merkle_build_poseidon2(self._h, ptrs, len(sources), n_leaves, elems_per_leaf, cap_size,
+                                                  self._ptr(leaf_hashes), self._ptr(nodes)))
+        return MerkleTreeWithCap(cap_size, leaf_hashes, nodes[:max(n_leaves - cap_size, 0)])
+
+    def poseidon2_hash_rows(self, rows):
+        torch = self._torch
+        assert rows.is_cuda and rows.dtype == torch.int64 and rows.is_contiguous() and rows.dim() == 2
+        out = torch.empty((rows.shape[0], 4), dtype=torch.int64, device=rows.device)
+        self._check(lib.bj_poseidon2_hash_rows(self._h, self._ptr(rows), rows.shape[0], rows.shape[1], self._ptr(out)))
+        return out
+
+    def poseidon2_permute(self, states):
+        assert states.is_cuda and states.is_contiguous() and states.shape[-1] == 12
+        self._check(lib.bj_poseidon2_permute(self._h, self._ptr(states), states.numel() // 12))
+        return states
+
+    # ---- FRI ----
+    def fri_fold(self, c0, c1, log_fold, alpha, coset_inv):
+        """One oracle step (log_fold folds).  Returns (out_c0, out_c1, new_coset_inv)."""
+        torch = self._torch
+        m = c0.numel()
+        log_m = m.bit_length() - 1
+        o0 = torch.empty(m >> log_fold, dtype=torch.int64, device=c0.device)
+        o1 = torch.empty(m >> log_fold, dtype=torch.int64, device=c0.device)
+        al = (ctypes.c_uint64 * 2)(alpha[0], alpha[1])
+        ci = ctypes.c_uint64(coset_inv)
+        self._check(lib.bj_fri_fold(self._h, self._ptr(c0), self._ptr(c1), log_m, log_fold, al, ctypes.byref(ci),
+                                    self._ptr(o0), self._ptr(o1)))
+        return o0, o1, int(ci.value)

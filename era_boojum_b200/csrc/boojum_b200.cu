@@ -1,0 +1,5 @@
+// Single translation unit of libboojum_b200.so (keeps __constant__ tables and inlining in one module).
+#include "capi.cu"
+#include "ntt.cu"
+#include "poseidon2.cu"
+#include "fri.cu"

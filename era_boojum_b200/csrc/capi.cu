@@ -1,0 +1,168 @@
+// Context management, device memory and host self-test hooks of the C-ABI (include/boojum_b200.h).
+#include <cstdlib>
+#include <cstring>
+#include "ctx.hpp"
+
+namespace bj {
+int32_t poseidon2_init_constants(bj_ctx* ctx);
+}
+
+using namespace bj;
+
+extern "C" {
+
+const char* bj_version(void) { return "boojum_b200 0.1.0 (sm_100a)"; }
+
+const char* bj_status_string(int32_t s) {
+  switch (s) {
+    case BJ_OK: return "ok";
+    case BJ_ERR_INVALID_ARG: return "invalid argument";
+    case BJ_ERR_CUDA: return "CUDA error";
+    case BJ_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case BJ_ERR_OOM: return "out of device memory";
+    case BJ_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+  }
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
+  if (!out_ctx) return BJ_ERR_INVALID_ARG;
+  *out_ctx = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return BJ_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) return BJ_ERR_INVALID_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return BJ_ERR_CUDA;
+  bj_ctx* ctx = new bj_ctx();
+  ctx->device = device;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete ctx;
+      return BJ_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  ctx->ntt_max_tile_log = env_int("BJ_NTT_MAX_TILE_LOG", 14);
+  if (ctx->ntt_max_tile_log < 8) ctx->ntt_max_tile_log = 8;
+  if (ctx->ntt_max_tile_log > 14) ctx->ntt_max_tile_log = 14;
+  ctx->ntt_pass1_w = env_int("BJ_NTT_PASS1_W", -1);
+  int32_t st = poseidon2_init_constants(ctx);
+  if (st != BJ_OK) {
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return st;
+  }
+  *out_ctx = ctx;
+  return BJ_OK;
+}
+
+int32_t bj_ctx_destroy(bj_ctx* ctx) {
+  if (!ctx) return BJ_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->tw_fwd) cudaFree(ctx->tw_fwd);
+  if (ctx->tw_inv) cudaFree(ctx->tw_inv);
+  for (auto& e : ctx->pow_cache) {
+    cudaFree(e.lo);
+    cudaFree(e.hi);
+  }
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->ptr_table) cudaFree(ctx->ptr_table);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return BJ_OK;
+}
+
+int32_t bj_ctx_set_stream(bj_ctx* ctx, void* stream) {
+  if (!ctx) return BJ_ERR_INVALID_ARG;
+  BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->own_stream = false;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    BJ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return BJ_OK;
+}
+
+int32_t bj_ctx_synchronize(bj_ctx* ctx) {
+  if (!ctx) return BJ_ERR_INVALID_ARG;
+  BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BJ_OK;
+}
+
+const char* bj_last_error(const bj_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
+uint64_t bj_launch_count(const bj_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t bj_alloc(bj_ctx* ctx, size_t bytes, void** d_ptr) {
+  if (!ctx || !d_ptr) return BJ_ERR_INVALID_ARG;
+  cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *d_ptr = nullptr;
+    BJ_FAIL(ctx, e == cudaErrorMemoryAllocation ? BJ_ERR_OOM : BJ_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  return BJ_OK;
+}
+int32_t bj_free(bj_ctx* ctx, void* d_ptr) {
+  if (!ctx) return BJ_ERR_INVALID_ARG;
+  if (!d_ptr) return BJ_OK;
+  BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  BJ_CUDA(ctx, cudaFree(d_ptr));
+  return BJ_OK;
+}
+int32_t bj_upload(bj_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (!ctx || (!d_dst && bytes) || (!h_src && bytes)) return BJ_ERR_INVALID_ARG;
+  BJ_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return BJ_OK;
+}
+int32_t bj_download(bj_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  if (!ctx || (!h_dst && bytes) || (!d_src && bytes)) return BJ_ERR_INVALID_ARG;
+  BJ_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return BJ_OK;
+}
+int32_t bj_alloc_host_pinned(size_t bytes, void** h_ptr) {
+  if (!h_ptr) return BJ_ERR_INVALID_ARG;
+  if (cudaMallocHost(h_ptr, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    *h_ptr = nullptr;
+    return BJ_ERR_OOM;
+  }
+  return BJ_OK;
+}
+int32_t bj_free_host_pinned(void* h_ptr) {
+  if (h_ptr && cudaFreeHost(h_ptr) != cudaSuccess) return BJ_ERR_CUDA;
+  return BJ_OK;
+}
+
+// ---- host self-test hooks (same gl64 / poseidon2 source, host compilation) ----
+uint64_t bj_host_gl_mul(uint64_t a, uint64_t b) { return gl::mul(a, b); }
+uint64_t bj_host_gl_add(uint64_t a, uint64_t b) { return gl::canon(gl::add_lazy(a, b)); }
+uint64_t bj_host_gl_sub(uint64_t a, uint64_t b) { return gl::canon(gl::sub_lazy(a, b)); }
+uint64_t bj_host_gl_inv(uint64_t a) { return gl::inv(a); }
+uint64_t bj_host_gl_mul_pow2(uint64_t a, uint32_t s) { return gl::mul_pow2(a, s); }
+void bj_host_e2_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]) {
+  gl::e2 r = gl::e2_mul({a[0], a[1]}, {b[0], b[1]});
+  out[0] = r.c0;
+  out[1] = r.c1;
+}
+void bj_host_e2_inv(const uint64_t a[2], uint64_t out[2]) {
+  gl::e2 r = gl::e2_inv({gl::canon(a[0]), gl::canon(a[1])});
+  out[0] = r.c0;
+  out[1] = r.c1;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Library context: one device + one stream, cached twiddle / coset-power tables, scratch arena.
+// Replaces the reference's Worker (src/worker/mod.rs:5-87) as the "data-parallel executor" handle and caches
+// what the reference recomputes on every stage (precompute_twiddles_for_fft, utils.rs:88-125).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "../../include/boojum_b200.h"
+#include "gl64.cuh"
+
+namespace bj {
+using gl::u64;
+
+struct PowTab {
+  u64 coset;
+  int log_n;
+  u64 scale;
+  int split;
+  u64* lo;
+  u64* hi;
+};
+
+}  // namespace bj
+
+struct bj_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string last_error;
+  // bit-reversed twiddle tables tab[k] = w^bitrev(k); prefix property makes one table serve all sizes
+  bj::u64* tw_fwd = nullptr;
+  bj::u64* tw_inv = nullptr;
+  int tw_log = 0;  // tables hold 2^(tw_log-1) entries
+  std::vector<bj::PowTab> pow_cache;
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void* ptr_table = nullptr;  // device copy of host pointer arrays (Merkle sources)
+  size_t ptr_table_bytes = 0;
+  uint64_t launches = 0;  // kernels launched by this library through this context
+  int sm_count = 148;
+  bool ntt_attr_set = false;
+  int ntt_max_tile_log = 14;  // tunables (env BJ_NTT_*)
+  int ntt_pass1_w = -1;
+  int ntt_chunk_mb = 0;
+};
+
+#define BJ_FAIL(ctx, code, msg)          \
+  do {                                   \
+    if (ctx) (ctx)->last_error = (msg);  \
+    return (code);                       \
+  } while (0)
+
+#define BJ_CUDA(ctx, expr)                                                                      \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      if (ctx) (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);          \
+      return BJ_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+#define BJ_TRY(expr)                 \
+  do {                               \
+    int32_t _s = (expr);             \
+    if (_s != BJ_OK) return _s;      \
+  } while (0)
+
+#define BJ_LAUNCH_CHECK(ctx)                                                              \
+  do {                                                                                    \
+    (ctx)->launches++;                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      (ctx)->last_error = std::string("kernel launch: ") + cudaGetErrorString(_e);        \
+      return BJ_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+namespace bj {
+int32_t ensure_scratch(bj_ctx* ctx, size_t bytes);
+int32_t ensure_twiddles(bj_ctx* ctx, int log_n);
+}  // namespace bj

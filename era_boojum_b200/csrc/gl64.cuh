@@ -1,0 +1,129 @@
+// Goldilocks field (p = 2^64 - 2^32 + 1) arithmetic for sm_100a device code.
+//
+// Semantics follow the reference's scalar field (src/field/goldilocks/mod.rs:188-201 reduce,
+// :215-233 add, :309-327 sub) and Fp2 = Fp[u]/(u^2-7) (src/field/goldilocks/extension.rs:15,
+// src/field/traits/field.rs:407-447).  Representation contract used by every kernel in this library:
+//
+//   * "canonical"  : value < p
+//   * "lazy"       : any 64-bit value congruent to the element (the reference tolerates the same, mod.rs:147-171)
+//   * gl::mul / gl::sqr / gl::mul_pow2   : lazy inputs  -> CANONICAL output
+//   * gl::add(a, b) / gl::sub(a, b)      : a lazy, b CANONICAL -> lazy output (single wrap correction is exact)
+//   * gl::add_lazy / gl::sub_lazy        : both lazy (canonicalises b first)
+//   * gl::canon                          : lazy -> canonical; applied on every store that leaves the library
+//
+// All arithmetic is exact mod p, so the lazy/canonical choice can never change a result that is
+// observed through gl::canon (which is how the reference observes them: serde, hashing, transcript).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace gl {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+static constexpr u64 P = 0xFFFFFFFF00000001ull;
+static constexpr u64 EPS = 0xFFFFFFFFull;  // 2^64 mod p
+static constexpr u64 MULT_GEN = 7ull;
+static constexpr u64 RADIX2_GEN = 0x185629dcda58878cull;  // order 2^32 (mod.rs:111)
+static constexpr u64 INV7 = 0x249249246db6db6eull;         // 7^-1 mod p (checked in tests)
+
+__host__ __device__ __forceinline__ u64 canon(u64 a) { return a >= P ? a - P : a; }
+
+// a lazy, b canonical -> lazy
+__host__ __device__ __forceinline__ u64 add(u64 a, u64 b) {
+  u64 s = a + b;
+  // wrapped by 2^64 = EPS (mod p); s_wrapped < b <= p-1 so s + EPS cannot wrap again
+  return s < a ? s + EPS : s;
+}
+// a lazy, b canonical -> lazy
+__host__ __device__ __forceinline__ u64 sub(u64 a, u64 b) {
+  u64 d = a - b;
+  // borrowed 2^64 = EPS (mod p); d_wrapped >= 2^64 - p + 1 > EPS so d - EPS cannot wrap again
+  return a < b ? d - EPS : d;
+}
+__host__ __device__ __forceinline__ u64 add_lazy(u64 a, u64 b) { return add(a, canon(b)); }
+__host__ __device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) { return sub(a, canon(b)); }
+__host__ __device__ __forceinline__ u64 neg(u64 a) {
+  a = canon(a);
+  return a ? P - a : 0;
+}
+__host__ __device__ __forceinline__ u64 dbl(u64 a) { return add(a, canon(a)); }
+
+// 128-bit (hi:lo) -> canonical, using 2^64 = 2^32 - 1 and 2^96 = -1 (mod p)
+__host__ __device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) {
+  u64 hh = hi >> 32, hl = hi & EPS;
+  u64 t0 = lo - hh;
+  if (lo < hh) t0 -= EPS;
+  u64 t1 = hl * EPS;  // (hl << 32) - hl, < 2^64
+  u64 r = t0 + t1;
+  if (r < t1) r += EPS;
+  return canon(r);
+}
+
+__host__ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+  u64 lo = a * b;
+  u64 hi = __umul64hi(a, b);
+#else
+  unsigned __int128 x = (unsigned __int128)a * b;
+  u64 lo = (u64)x, hi = (u64)(x >> 64);
+#endif
+  return reduce128(lo, hi);
+}
+__host__ __device__ __forceinline__ u64 sqr(u64 a) { return mul(a, a); }
+
+// a * 2^s for 0 <= s < 64 (s compile-time or uniform): 128-bit shift then reduce
+__host__ __device__ __forceinline__ u64 mul_pow2(u64 a, unsigned s) {
+  if (s == 0) return canon(a);
+  u64 lo = a << s, hi = a >> (64 - s);
+  return reduce128(lo, hi);
+}
+
+__host__ __device__ inline u64 pow(u64 b, u64 e) {
+  u64 r = 1;
+  while (e) {
+    if (e & 1) r = mul(r, b);
+    b = sqr(b);
+    e >>= 1;
+  }
+  return r;
+}
+__host__ __device__ inline u64 inv(u64 a) { return pow(a, P - 2); }
+
+// omega_{2^k} = G^(2^(32-k))           (src/cs/implementations/utils.rs:13-28)
+__host__ __device__ inline u64 omega(unsigned log_n) {
+  u64 w = RADIX2_GEN;
+  for (unsigned i = log_n; i < 32; i++) w = sqr(w);
+  return w;
+}
+
+// ---- Fp2 = Fp[u]/(u^2 - 7); components canonical on output of mul/inv, lazy after add/sub ----
+struct e2 {
+  u64 c0, c1;
+};
+__host__ __device__ __forceinline__ e2 e2_canon(e2 a) { return {canon(a.c0), canon(a.c1)}; }
+// b canonical
+__host__ __device__ __forceinline__ e2 e2_add(e2 a, e2 b) { return {add(a.c0, b.c0), add(a.c1, b.c1)}; }
+__host__ __device__ __forceinline__ e2 e2_sub(e2 a, e2 b) { return {sub(a.c0, b.c0), sub(a.c1, b.c1)}; }
+__host__ __device__ __forceinline__ u64 mul7(u64 a) {  // a canonical or lazy -> canonical
+  // 7a = 8a - a
+  return canon(sub(mul_pow2(a, 3), canon(a)));
+}
+__host__ __device__ __forceinline__ e2 e2_mul(e2 a, e2 b) {
+  // Karatsuba as in field.rs:407-426: v0 = a0 b0, v1 = a1 b1, c1 = (a0+a1)(b0+b1) - v0 - v1, c0 = v0 + 7 v1
+  u64 v0 = mul(a.c0, b.c0), v1 = mul(a.c1, b.c1);
+  u64 s = mul(add_lazy(a.c0, a.c1), add_lazy(b.c0, b.c1));
+  u64 c1 = canon(sub(sub(s, v0), v1));
+  u64 c0 = canon(add(v0, mul7(v1)));
+  return {c0, c1};
+}
+__host__ __device__ __forceinline__ e2 e2_mul_base(e2 a, u64 b) { return {mul(a.c0, b), mul(a.c1, b)}; }
+__host__ __device__ __forceinline__ e2 e2_sqr(e2 a) { return e2_mul(a, a); }
+__host__ __device__ inline e2 e2_inv(e2 a) {
+  u64 n = canon(sub(sqr(a.c0), mul7(sqr(a.c1))));
+  u64 ni = inv(n);
+  return {mul(a.c0, ni), mul(neg(a.c1), ni)};
+}
+
+}  // namespace gl

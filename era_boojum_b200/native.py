@@ -1,0 +1,83 @@
+"""ctypes binding of libboojum_b200.so (the C-ABI in include/boojum_b200.h).
+
+This is the only way Python reaches the kernels: there is no Python or CPU fallback.  If the shared library
+has not been built (`python -c "import __graft_entry__ as g; g.build()"` or `make -C era_boojum_b200`) the import
+of this module raises.  PyTorch is used by callers for device memory and streams only; this module
+itself only needs ctypes.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libboojum_b200.so")
+
+P = 0xFFFFFFFF00000001
+
+BJ_OK = 0
+BJ_ERR_INVALID_ARG = -1
+BJ_ERR_CUDA = -2
+BJ_ERR_NO_DEVICE = -3
+BJ_ERR_OOM = -4
+BJ_ERR_UNSUPPORTED = -5
+
+
+class BoojumError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("boojum_b200 status %d: %s" % (status, message))
+        self.status = status
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "era_boojum_b200: %s is missing - build it with `make -C era_boojum_b200` (nvcc, sm_100a). "
+        "There is no CPU fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_u64, _u32, _i32, _sz, _vp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32, ctypes.c_size_t, ctypes.c_void_p
+_pp = ctypes.POINTER(ctypes.c_void_p)
+
+SIGNATURES = {
+    "bj_version": (ctypes.c_char_p, []),
+    "bj_status_string": (ctypes.c_char_p, [_i32]),
+    "bj_ctx_create": (_i32, [_i32, _vp, _pp]),
+    "bj_ctx_destroy": (_i32, [_vp]),
+    "bj_ctx_set_stream": (_i32, [_vp, _vp]),
+    "bj_ctx_synchronize": (_i32, [_vp]),
+    "bj_last_error": (ctypes.c_char_p, [_vp]),
+    "bj_launch_count": (_u64, [_vp]),
+    "bj_alloc": (_i32, [_vp, _sz, _pp]),
+    "bj_free": (_i32, [_vp, _vp]),
+    "bj_upload": (_i32, [_vp, _vp, _vp, _sz]),
+    "bj_download": (_i32, [_vp, _vp, _vp, _sz]),
+    "bj_alloc_host_pinned": (_i32, [_sz, _pp]),
+    "bj_free_host_pinned": (_i32, [_vp]),
+    "bj_twiddles": (_i32, [_vp, _u32, _i32, _vp]),
+    "bj_ntt_natural_to_bitreversed": (_i32, [_vp, _vp, _u32, _u32, _u64, _u64]),
+    "bj_intt_natural_to_natural": (_i32, [_vp, _vp, _u32, _u32, _u64, _u64]),
+    "bj_bitreverse": (_i32, [_vp, _vp, _u32, _u32, _u64]),
+    "bj_lde": (_i32, [_vp, _vp, _u64, _vp, _u32, _u32, _u32, _i32]),
+    "bj_merkle_build_poseidon2": (_i32, [_vp, _vp, _u32, _u64, _u32, _u32, _vp, _vp]),
+    "bj_poseidon2_hash_rows": (_i32, [_vp, _vp, _u64, _u32, _vp]),
+    "bj_poseidon2_permute": (_i32, [_vp, _vp, _u64]),
+    "bj_fri_fold": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "bj_ntt_natural_to_bitreversed_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
+    "bj_intt_natural_to_natural_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
+    "bj_host_gl_mul": (_u64, [_u64, _u64]),
+    "bj_host_gl_add": (_u64, [_u64, _u64]),
+    "bj_host_gl_sub": (_u64, [_u64, _u64]),
+    "bj_host_gl_inv": (_u64, [_u64]),
+    "bj_host_gl_mul_pow2": (_u64, [_u64, _u32]),
+    "bj_host_e2_mul": (None, [_vp, _vp, _vp]),
+    "bj_host_e2_inv": (None, [_vp, _vp]),
+    "bj_host_poseidon2_permutation": (None, [_vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here == header/library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def version():
+    return lib.bj_version().decode()
