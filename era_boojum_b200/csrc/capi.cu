@@ -7,9 +7,55 @@ namespace bj {
 int32_t poseidon2_init_constants(bj_ctx* ctx);
 }
 
+namespace bj {
+// device self-test of the PTX field arithmetic against the portable C versions (same inputs, same thread)
+__global__ void field_selftest_kernel(u64 n, u64 seed, unsigned long long* mismatches) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // splitmix64 stream + edge values
+  auto next = [](u64& s) {
+    s += 0x9E3779B97F4A7C15ull;
+    u64 z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  u64 st = seed + i * 0x632BE59BD9B4E019ull;
+  const u64 edges[12] = {0, 1, gl::P - 1, gl::P, gl::P + 1, ~0ull, gl::EPS, gl::EPS + 1, 1ull << 63, gl::P - gl::EPS, 2, gl::P - 2};
+  u64 a = next(st), b = next(st);
+  if ((i & 7) == 0) a = edges[(i >> 3) % 12];
+  if ((i & 15) < 2) b = edges[(i >> 4) % 12];
+  unsigned bad = 0;
+  if (gl::mul(a, b) != gl::mul_c(a, b)) bad++;
+  const u64 bc = gl::canon(b);
+  if (gl::canon(gl::add(a, bc)) != gl::canon(gl::add_c(a, bc))) bad++;
+  if (gl::canon(gl::sub(a, bc)) != gl::canon(gl::sub_c(a, bc))) bad++;
+  // b == p is allowed by the contract
+  if (gl::canon(gl::add(a, gl::P)) != gl::canon(a)) bad++;
+  if (gl::canon(gl::sub(a, gl::P)) != gl::canon(a)) bad++;
+  if (gl::mul(a, b) >= gl::P) bad++;
+  if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+}  // namespace bj
+
 using namespace bj;
 
 extern "C" {
+
+int32_t bj_selftest_field(bj_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* h_mismatches) {
+  if (!ctx || !h_mismatches) return BJ_ERR_INVALID_ARG;
+  unsigned long long* d = nullptr;
+  BJ_CUDA(ctx, cudaMalloc(&d, sizeof(unsigned long long)));
+  BJ_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+  field_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, seed, d);
+  BJ_LAUNCH_CHECK(ctx);
+  unsigned long long h = 0;
+  BJ_CUDA(ctx, cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  *h_mismatches = h;
+  return BJ_OK;
+}
 
 const char* bj_version(void) { return "boojum_b200 0.1.0 (sm_100a)"; }
 
@@ -42,15 +88,7 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
   if (cudaSetDevice(device) != cudaSuccess) return BJ_ERR_CUDA;
   bj_ctx* ctx = new bj_ctx();
   ctx->device = device;
-  if (stream) {
-    ctx->stream = (cudaStream_t)stream;
-  } else {
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-      delete ctx;
-      return BJ_ERR_CUDA;
-    }
-    ctx->own_stream = true;
-  }
+  ctx->stream = (cudaStream_t)stream;  // NULL == the CUDA legacy default stream (what torch uses by default)
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   ctx->ntt_max_tile_log = env_int("BJ_NTT_MAX_TILE_LOG", 14);
@@ -59,7 +97,6 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
   ctx->ntt_pass1_w = env_int("BJ_NTT_PASS1_W", -1);
   int32_t st = poseidon2_init_constants(ctx);
   if (st != BJ_OK) {
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return st;
   }
@@ -79,7 +116,6 @@ int32_t bj_ctx_destroy(bj_ctx* ctx) {
   }
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->ptr_table) cudaFree(ctx->ptr_table);
-  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return BJ_OK;
 }
@@ -87,14 +123,7 @@ int32_t bj_ctx_destroy(bj_ctx* ctx) {
 int32_t bj_ctx_set_stream(bj_ctx* ctx, void* stream) {
   if (!ctx) return BJ_ERR_INVALID_ARG;
   BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-  ctx->own_stream = false;
-  if (stream) {
-    ctx->stream = (cudaStream_t)stream;
-  } else {
-    BJ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    ctx->own_stream = true;
-  }
+  ctx->stream = (cudaStream_t)stream;
   return BJ_OK;
 }
 

@@ -7,7 +7,8 @@
 //   * "canonical"  : value < p
 //   * "lazy"       : any 64-bit value congruent to the element (the reference tolerates the same, mod.rs:147-171)
 //   * gl::mul / gl::sqr / gl::mul_pow2   : lazy inputs  -> CANONICAL output
-//   * gl::add(a, b) / gl::sub(a, b)      : a lazy, b CANONICAL -> lazy output (single wrap correction is exact)
+//   * gl::add(a, b) / gl::sub(a, b)      : a lazy, b CANONICAL (b <= p suffices) -> lazy output (single wrap
+//                                          correction is exact)
 //   * gl::add_lazy / gl::sub_lazy        : both lazy (canonicalises b first)
 //   * gl::canon                          : lazy -> canonical; applied on every store that leaves the library
 //
@@ -30,17 +31,67 @@ static constexpr u64 INV7 = 0x249249246db6db6eull;         // 7^-1 mod p (checke
 
 __host__ __device__ __forceinline__ u64 canon(u64 a) { return a >= P ? a - P : a; }
 
-// a lazy, b canonical -> lazy
-__host__ __device__ __forceinline__ u64 add(u64 a, u64 b) {
+// portable C versions (host path; also the in-kernel reference of the PTX self-test)
+__host__ __device__ __forceinline__ u64 add_c(u64 a, u64 b) {
   u64 s = a + b;
-  // wrapped by 2^64 = EPS (mod p); s_wrapped < b <= p-1 so s + EPS cannot wrap again
   return s < a ? s + EPS : s;
 }
-// a lazy, b canonical -> lazy
-__host__ __device__ __forceinline__ u64 sub(u64 a, u64 b) {
+__host__ __device__ __forceinline__ u64 sub_c(u64 a, u64 b) {
   u64 d = a - b;
-  // borrowed 2^64 = EPS (mod p); d_wrapped >= 2^64 - p + 1 > EPS so d - EPS cannot wrap again
   return a < b ? d - EPS : d;
+}
+
+#if defined(__CUDA_ARCH__) && !defined(BJ_GL_PORTABLE)
+#define BJ_GL_PTX 1
+__device__ __forceinline__ u64 pack2(u32 lo, u32 hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 a, u32& lo, u32& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(a)); }
+#endif
+
+// a lazy, b <= p -> lazy.  (2^64 = EPS mod p: one wrap correction; it cannot wrap twice because the wrapped sum is < b)
+__host__ __device__ __forceinline__ u64 add(u64 a, u64 b) {
+#ifdef BJ_GL_PTX
+  u32 a0, a1, b0, b1, lo, hi;
+  unpack2(a, a0, a1);
+  unpack2(b, b0, b1);
+  // carry chains only mix add.cc/addc or sub.cc/subc (never add.cc -> subc)
+  asm("{\n\t.reg .u32 c;\n\t"
+      "add.cc.u32 %0, %2, %4;\n\t"
+      "addc.cc.u32 %1, %3, %5;\n\t"
+      "addc.u32 c, 0, 0;\n\t"        // c = carry (0/1);  s + c*EPS = s - c + (c << 32)
+      "sub.cc.u32 %0, %0, c;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "add.u32 %1, %1, c;\n\t"
+      "}"
+      : "=&r"(lo), "=&r"(hi)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return pack2(lo, hi);
+#else
+  return add_c(a, b);
+#endif
+}
+// a lazy, b <= p -> lazy
+__host__ __device__ __forceinline__ u64 sub(u64 a, u64 b) {
+#ifdef BJ_GL_PTX
+  u32 a0, a1, b0, b1, lo, hi;
+  unpack2(a, a0, a1);
+  unpack2(b, b0, b1);
+  asm("{\n\t.reg .u32 m;\n\t"
+      "sub.cc.u32 %0, %2, %4;\n\t"
+      "subc.cc.u32 %1, %3, %5;\n\t"
+      "subc.u32 m, 0, 0;\n\t"        // m = borrow ? 0xffffffff : 0
+      "sub.cc.u32 %0, %0, m;\n\t"    // -= EPS on borrow
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(lo), "=&r"(hi)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return pack2(lo, hi);
+#else
+  return sub_c(a, b);
+#endif
 }
 __host__ __device__ __forceinline__ u64 add_lazy(u64 a, u64 b) { return add(a, canon(b)); }
 __host__ __device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) { return sub(a, canon(b)); }
@@ -61,7 +112,7 @@ __host__ __device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) {
   return canon(r);
 }
 
-__host__ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
+__host__ __device__ __forceinline__ u64 mul_c(u64 a, u64 b) {
 #ifdef __CUDA_ARCH__
   u64 lo = a * b;
   u64 hi = __umul64hi(a, b);
@@ -70,6 +121,53 @@ __host__ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
   u64 lo = (u64)x, hi = (u64)(x >> 64);
 #endif
   return reduce128(lo, hi);
+}
+
+__host__ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
+#ifdef BJ_GL_PTX
+  // 4-limb product with 32-bit carry chains, then x = (r1:r0) + r2 (2^32 - 1) - r3 with the wrap corrections merged
+  // into the final canonicalising "+EPS" (taken when the sum wrapped once or when it is >= p).
+  u32 a0, a1, b0, b1, v0, v1;
+  unpack2(a, a0, a1);
+  unpack2(b, b0, b1);
+  asm("{\n\t"
+      ".reg .u32 r0, r1, r2, r3, m, c, t0, t1;\n\t"
+      ".reg .pred p;\n\t"
+      "mul.lo.u32 r0, %2, %4;\n\t"
+      "mul.hi.u32 r1, %2, %4;\n\t"
+      "mad.lo.cc.u32 r1, %2, %5, r1;\n\t"
+      "madc.hi.u32 r2, %2, %5, 0;\n\t"
+      "mad.lo.cc.u32 r1, %3, %4, r1;\n\t"
+      "madc.hi.cc.u32 r2, %3, %4, r2;\n\t"
+      "addc.u32 r3, 0, 0;\n\t"
+      "mad.lo.cc.u32 r2, %3, %5, r2;\n\t"
+      "madc.hi.u32 r3, %3, %5, r3;\n\t"
+      // A = (r1:r0) - r3 ; on borrow A -= EPS (cannot borrow twice)
+      "sub.cc.u32 r0, r0, r3;\n\t"
+      "subc.cc.u32 r1, r1, 0;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 r0, r0, m;\n\t"
+      "subc.u32 r1, r1, 0;\n\t"
+      // A += r2 << 32 (carry C1) ; A -= r2 (borrow B2) ; c = C1 - B2 in {0, 1}
+      "add.cc.u32 r1, r1, r2;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.cc.u32 r0, r0, r2;\n\t"
+      "subc.cc.u32 r1, r1, 0;\n\t"
+      "subc.u32 c, c, 0;\n\t"
+      // t = A + EPS ; result = t if (wrapped once) or (A >= p, i.e. A + EPS carries) else A
+      "add.cc.u32 t0, r0, 0xffffffff;\n\t"
+      "addc.cc.u32 t1, r1, 0;\n\t"
+      "addc.u32 c, c, 0;\n\t"
+      "setp.ne.u32 p, c, 0;\n\t"
+      "selp.u32 %0, t0, r0, p;\n\t"
+      "selp.u32 %1, t1, r1, p;\n\t"
+      "}"
+      : "=r"(v0), "=r"(v1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return pack2(v0, v1);
+#else
+  return mul_c(a, b);
+#endif
 }
 __host__ __device__ __forceinline__ u64 sqr(u64 a) { return mul(a, a); }
 

@@ -357,6 +357,8 @@ static int32_t launch_pass(bj_ctx* ctx, const NttPass& p, u32 n_cols) {
   const size_t smem = sizeof(u64) * ((size_t)(1 << LOG_E) + ((size_t)(1 << LOG_E) >> 4) + 1);
   if (!ctx->ntt_attr_set) {
     BJ_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BJ_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
     ctx->ntt_attr_set = true;
   }
   if (tiles > 0x7fffffffull || n_cols > 65535) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "grid too large");

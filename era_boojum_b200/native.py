@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libboojum_b200.so")
+LIB_PATH = os.path.join(_HERE, "libboojum_b200_portable.so" if os.environ.get("BJ_LIB_VARIANT") == "portable"
+                        else "libboojum_b200.so")
 
 P = 0xFFFFFFFF00000001
 
@@ -63,6 +64,7 @@ SIGNATURES = {
     "bj_fri_fold": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),
     "bj_ntt_natural_to_bitreversed_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
     "bj_intt_natural_to_natural_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
+    "bj_selftest_field": (_i32, [_vp, _u64, _u64, _vp]),
     "bj_host_gl_mul": (_u64, [_u64, _u64]),
     "bj_host_gl_add": (_u64, [_u64, _u64]),
     "bj_host_gl_sub": (_u64, [_u64, _u64]),

@@ -45,7 +45,8 @@ typedef struct bj_ctx bj_ctx;
 /* ---- context (replaces Worker, src/worker/mod.rs:5-87, as the executor handle) ---- */
 BJ_API const char* bj_version(void);
 BJ_API const char* bj_status_string(int32_t status);
-/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL to create an owned stream */
+/* stream: a cudaStream_t owned by the caller (e.g. torch.cuda.current_stream().cuda_stream); NULL is the CUDA
+ * legacy default stream.  The library never creates streams of its own. */
 BJ_API int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx);
 BJ_API int32_t bj_ctx_destroy(bj_ctx* ctx);
 BJ_API int32_t bj_ctx_set_stream(bj_ctx* ctx, void* stream);
@@ -121,6 +122,9 @@ BJ_API int32_t bj_ntt_natural_to_bitreversed_host(bj_ctx* ctx, uint64_t* h_data,
                                            uint64_t coset);
 BJ_API int32_t bj_intt_natural_to_natural_host(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint32_t n_cols,
                                         uint64_t coset);
+
+/* device self-test: PTX field arithmetic vs the portable C versions on n pseudo-random + edge inputs */
+BJ_API int32_t bj_selftest_field(bj_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* h_mismatches);
 
 /* ---- host self-test hooks: the same gl64 source compiled for the host (CPU tests, no device needed) ---- */
 BJ_API uint64_t bj_host_gl_mul(uint64_t a, uint64_t b);

@@ -318,3 +318,12 @@ def test_fri_fold_golden_fixture(bj, ctx, golden_fixture):
             assert int(bj.to_numpy(o0[tree_idx:tree_idx + 1])[0]) == nxt[pos]
             assert int(bj.to_numpy(o1[tree_idx:tree_idx + 1])[0]) == nxt[ndeg + pos]
             sub, log_m = tree_idx, log_m - k
+
+
+def test_device_field_selftest(bj, ctx):
+    """Inline-PTX mul/add/sub vs the portable C versions inside one kernel (4M random + edge inputs)."""
+    import ctypes
+    from era_boojum_b200 import native
+    bad = ctypes.c_uint64(123)
+    st = native.lib.bj_selftest_field(ctx._h, 1 << 22, 20260924, ctypes.byref(bad))
+    assert st == 0 and bad.value == 0
