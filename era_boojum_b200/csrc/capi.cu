@@ -95,6 +95,7 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
   if (ctx->ntt_max_tile_log < 8) ctx->ntt_max_tile_log = 8;
   if (ctx->ntt_max_tile_log > 14) ctx->ntt_max_tile_log = 14;
   ctx->ntt_pass1_w = env_int("BJ_NTT_PASS1_W", -1);
+  ctx->ntt_use_v2 = env_int("BJ_NTT_V2", 1);
   int32_t st = poseidon2_init_constants(ctx);
   if (st != BJ_OK) {
     delete ctx;

@@ -41,6 +41,8 @@ struct bj_ctx {
   uint64_t launches = 0;  // kernels launched by this library through this context
   int sm_count = 148;
   bool ntt_attr_set = false;
+  std::vector<void*> attr_done;  // kernels whose smem attributes are set on this device
+  int ntt_use_v2 = 1;            // BJ_NTT_V2=0 forces the generic pass kernel
   int ntt_max_tile_log = 14;  // tunables (env BJ_NTT_*)
   int ntt_pass1_w = -1;
   int ntt_chunk_mb = 0;

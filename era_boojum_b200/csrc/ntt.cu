@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include "ctx.hpp"
 #include "ntt.cuh"
+#include "ntt_v2.cuh"
 
 namespace bj {
 
@@ -353,6 +354,24 @@ static Plan make_plan(const bj_ctx* ctx, int m, bool transpose_last) {
 static int32_t launch_pass(bj_ctx* ctx, const NttPass& p, u32 n_cols) {
   const int LOG_E = p.t + p.w;
   const u64 tiles = p.kind == PASS_TILE ? (1ull << (p.log_n - p.t - p.w)) : (1ull << (p.r0 - p.w));
+  if (tiles > 0x7fffffffull || n_cols > 65535) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "grid too large");
+  dim3 grid((unsigned)tiles, n_cols, 1);
+  // specialised kernel when one is instantiated for this tile shape and the buffers allow 128-bit accesses
+  V2Launch v2;
+  const bool aligned = ((((uintptr_t)p.src | (uintptr_t)p.dst) & 15) == 0) && ((p.src_col_stride | p.dst_col_stride) & 1) == 0;
+  if (ctx->ntt_use_v2 && aligned && v2_lookup(p.t, p.w, p.kind, &v2)) {
+    bool known = false;
+    for (void* f : ctx->attr_done) known |= (f == (void*)v2.fn);
+    if (!known) {
+      BJ_CUDA(ctx, cudaFuncSetAttribute((const void*)v2.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      BJ_CUDA(ctx, cudaFuncSetAttribute((const void*)v2.fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+      ctx->attr_done.push_back((void*)v2.fn);
+    }
+    v2.fn<<<grid, v2.threads, v2.smem, ctx->stream>>>(p);
+    BJ_LAUNCH_CHECK(ctx);
+    return BJ_OK;
+  }
   const int threads = std::max(32, std::min(512, (1 << LOG_E) >> 4));
   const size_t smem = sizeof(u64) * ((size_t)(1 << LOG_E) + ((size_t)(1 << LOG_E) >> 4) + 1);
   if (!ctx->ntt_attr_set) {
@@ -361,8 +380,6 @@ static int32_t launch_pass(bj_ctx* ctx, const NttPass& p, u32 n_cols) {
                                       cudaSharedmemCarveoutMaxShared));
     ctx->ntt_attr_set = true;
   }
-  if (tiles > 0x7fffffffull || n_cols > 65535) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "grid too large");
-  dim3 grid((unsigned)tiles, n_cols, 1);
   ntt_pass_kernel<<<grid, threads, smem, ctx->stream>>>(p);
   BJ_LAUNCH_CHECK(ctx);
   return BJ_OK;
