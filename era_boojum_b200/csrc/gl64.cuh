@@ -57,14 +57,14 @@ __host__ __device__ __forceinline__ u64 add(u64 a, u64 b) {
   u32 a0, a1, b0, b1, lo, hi;
   unpack2(a, a0, a1);
   unpack2(b, b0, b1);
-  // carry chains only mix add.cc/addc or sub.cc/subc (never add.cc -> subc)
+  // carry chains only mix add.cc/addc or sub.cc/subc (never add.cc -> subc, whose flag sense differs in SASS);
+  // "+ c*EPS" is written as a multiply-add so that ptxas places it on the (under-used) FMA pipe
   asm("{\n\t.reg .u32 c;\n\t"
       "add.cc.u32 %0, %2, %4;\n\t"
       "addc.cc.u32 %1, %3, %5;\n\t"
-      "addc.u32 c, 0, 0;\n\t"        // c = carry (0/1);  s + c*EPS = s - c + (c << 32)
-      "sub.cc.u32 %0, %0, c;\n\t"
-      "subc.u32 %1, %1, 0;\n\t"
-      "add.u32 %1, %1, c;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "mad.lo.cc.u32 %0, c, 0xffffffff, %0;\n\t"
+      "madc.hi.u32 %1, c, 0xffffffff, %1;\n\t"
       "}"
       : "=&r"(lo), "=&r"(hi)
       : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
@@ -125,44 +125,49 @@ __host__ __device__ __forceinline__ u64 mul_c(u64 a, u64 b) {
 
 __host__ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
 #ifdef BJ_GL_PTX
-  // 4-limb product with 32-bit carry chains, then x = (r1:r0) + r2 (2^32 - 1) - r3 with the wrap corrections merged
-  // into the final canonicalising "+EPS" (taken when the sum wrapped once or when it is >= p).
+  // 4-limb product from four 32x32->64 multiply-adds (no overflow in any partial sum), then
+  // x = (r1:r0) + r2*EPS - r3 (2^64 = EPS, 2^96 = -1 mod p).  The "*EPS" steps are multiply-adds (FMA pipe); every wrap
+  // is corrected at once (each can happen at most once, see the bounds in DESIGN.md 4.1); output canonical.
   u32 a0, a1, b0, b1, v0, v1;
   unpack2(a, a0, a1);
   unpack2(b, b0, b1);
   asm("{\n\t"
-      ".reg .u32 r0, r1, r2, r3, m, c, t0, t1;\n\t"
-      ".reg .pred p;\n\t"
-      "mul.lo.u32 r0, %2, %4;\n\t"
-      "mul.hi.u32 r1, %2, %4;\n\t"
-      "mad.lo.cc.u32 r1, %2, %5, r1;\n\t"
-      "madc.hi.u32 r2, %2, %5, 0;\n\t"
-      "mad.lo.cc.u32 r1, %3, %4, r1;\n\t"
-      "madc.hi.cc.u32 r2, %3, %4, r2;\n\t"
-      "addc.u32 r3, 0, 0;\n\t"
-      "mad.lo.cc.u32 r2, %3, %5, r2;\n\t"
-      "madc.hi.u32 r3, %3, %5, r3;\n\t"
-      // A = (r1:r0) - r3 ; on borrow A -= EPS (cannot borrow twice)
-      "sub.cc.u32 r0, r0, r3;\n\t"
-      "subc.cc.u32 r1, r1, 0;\n\t"
-      "subc.u32 m, 0, 0;\n\t"
-      "sub.cc.u32 r0, r0, m;\n\t"
-      "subc.u32 r1, r1, 0;\n\t"
-      // A += r2 << 32 (carry C1) ; A -= r2 (borrow B2) ; c = C1 - B2 in {0, 1}
-      "add.cc.u32 r1, r1, r2;\n\t"
+      ".reg .u64 p0, p1, p2, p3, z;\n\t"
+      ".reg .u32 r0, r1, r2, r3, x, y, w, c, bb, ge;\n\t"
+      ".reg .pred q;\n\t"
+      "mul.wide.u32 p0, %2, %4;\n\t"
+      "mov.b64 {r0, x}, p0;\n\t"
+      "cvt.u64.u32 z, x;\n\t"
+      "mad.wide.u32 p1, %2, %5, z;\n\t"
+      "mov.b64 {x, y}, p1;\n\t"
+      "cvt.u64.u32 z, x;\n\t"
+      "mad.wide.u32 p2, %3, %4, z;\n\t"
+      "mov.b64 {r1, w}, p2;\n\t"
+      "cvt.u64.u32 z, y;\n\t"
+      "mad.wide.u32 p3, %3, %5, z;\n\t"
+      "cvt.u64.u32 z, w;\n\t"
+      "add.u64 p3, p3, z;\n\t"
+      "mov.b64 {r2, r3}, p3;\n\t"
+      // t = (r1:r0) + r2*EPS with carry c ; t += c*EPS (cannot carry again)
+      "mad.lo.cc.u32 %0, r2, 0xffffffff, r0;\n\t"
+      "madc.hi.cc.u32 %1, r2, 0xffffffff, r1;\n\t"
       "addc.u32 c, 0, 0;\n\t"
-      "sub.cc.u32 r0, r0, r2;\n\t"
-      "subc.cc.u32 r1, r1, 0;\n\t"
-      "subc.u32 c, c, 0;\n\t"
-      // t = A + EPS ; result = t if (wrapped once) or (A >= p, i.e. A + EPS carries) else A
-      "add.cc.u32 t0, r0, 0xffffffff;\n\t"
-      "addc.cc.u32 t1, r1, 0;\n\t"
-      "addc.u32 c, c, 0;\n\t"
-      "setp.ne.u32 p, c, 0;\n\t"
-      "selp.u32 %0, t0, r0, p;\n\t"
-      "selp.u32 %1, t1, r1, p;\n\t"
+      "mad.lo.cc.u32 %0, c, 0xffffffff, %0;\n\t"
+      "madc.hi.u32 %1, c, 0xffffffff, %1;\n\t"
+      // t -= r3 ; on borrow t -= EPS (cannot borrow again)
+      "sub.cc.u32 %0, %0, r3;\n\t"
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 bb, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, bb;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      // canonicalise: t >= p  <=>  hi == 0xffffffff and lo != 0 ; then t += EPS (mod 2^64) == t - p
+      "setp.eq.u32 q, %1, 0xffffffff;\n\t"
+      "setp.ne.and.u32 q, %0, 0, q;\n\t"
+      "selp.u32 ge, 1, 0, q;\n\t"
+      "mad.lo.cc.u32 %0, ge, 0xffffffff, %0;\n\t"
+      "madc.hi.u32 %1, ge, 0xffffffff, %1;\n\t"
       "}"
-      : "=r"(v0), "=r"(v1)
+      : "=&r"(v0), "=&r"(v1)
       : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
   return pack2(v0, v1);
 #else

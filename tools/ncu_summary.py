@@ -1,0 +1,26 @@
+"""Print the metrics we track from an .ncu-rep (run here, no GPU needed): python tools/ncu_summary.py file.ncu-rep"""
+import csv, subprocess, sys
+KEYS = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_warps',
+        'smsp__inst_executed.sum', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'lts__t_bytes.sum', 'sm__cycles_elapsed.max']
+out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
+for r in rows[2:]:
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            print(k, '=', r[i], units[i])
+    stalls = []
+    for i, h in enumerate(hdr):
+        if 'issue_stalled' in h and h.endswith('per_warp_active.pct') and 'not_issued' not in h:
+            v = float(r[i])
+            if v >= 3:
+                stalls.append((v, h.replace('smsp__warp_issue_stalled_', '').replace('_per_warp_active.pct', '')))
+    print('stalls(% of warp-active cycles):', ', '.join('%s=%.0f' % (n, v) for v, n in sorted(stalls, reverse=True)))
+    print('---')
