@@ -182,6 +182,68 @@ class Context:
         self._check(lib.bj_poseidon2_permute(self._h, self._ptr(states), states.numel() // 12))
         return states
 
+    # ---- element-wise ----
+    def batch_inverse_inplace(self, a):
+        """batch_inverse_inplace (cs/implementations/utils.rs:439-472); zero -> zero."""
+        self._check(lib.bj_batch_inverse(self._h, self._ptr(a), a.numel()))
+        return a
+
+    def batch_inverse_inplace_in_extension(self, c0, c1):
+        self._check(lib.bj_batch_inverse_ext(self._h, self._ptr(c0), self._ptr(c1), c0.numel()))
+        return c0, c1
+
+    def quotening_operation_in_extension(self, acc_c0, acc_c1, sources, values_at, at, challenges):
+        """DEEP accumulation for one opening point (cs/implementations/prover.rs:2523-2706).
+        sources: list of (c0_tensor, c1_tensor_or_None), each the flat [L*n] LDE of a polynomial."""
+        n_src = len(sources)
+        p0 = (ctypes.c_void_p * n_src)(*[s[0].data_ptr() for s in sources])
+        p1 = (ctypes.c_void_p * n_src)(*[(s[1].data_ptr() if s[1] is not None else None) for s in sources])
+        vals = (ctypes.c_uint64 * (2 * n_src))(*[int(x) for v in values_at for x in v])
+        chs = (ctypes.c_uint64 * (2 * n_src))(*[int(x) for v in challenges for x in v])
+        at_ = (ctypes.c_uint64 * 2)(int(at[0]), int(at[1]))
+        log_rows = acc_c0.numel().bit_length() - 1
+        self._check(lib.bj_deep_quotient_group(self._h, p0, p1, n_src, vals, chs, at_, log_rows,
+                                               self._ptr(acc_c0), self._ptr(acc_c1)))
+        return acc_c0, acc_c1
+
+    # ---- gate / quotient evaluator ----
+    def evaluate_gates_over_general_purpose_columns(self, gates, variables, witnesses, constants, alpha_powers, q_c0, q_c1):
+        """Row loop of prove_cpu_basic over general-purpose columns (cs/implementations/prover.rs:1031-1080).
+        gates: list of dicts {relations: [(op, dst, (kind, value), (kind, value) | None)], writes: [(kind, value)],
+        num_repetitions, variables_offset, witnesses_offset, constants_offset, constants_placement_offset,
+        selector_path: [bool]} - the data of gpu_synthesizer::GPUDataCapture; columns: lists of flat CUDA tensors."""
+        N = native
+        keep, descs = [], (N.GateDesc * len(gates))()
+        for d, g in zip(descs, gates):
+            rels = (N.GateRelation * max(1, len(g["relations"])))()
+            for r, (op, dst, a, b) in zip(rels, g["relations"]):
+                r.op, r.dst_temporary = op, dst
+                r.a.kind, r.a.value = a[0], int(a[1])
+                if b is not None:
+                    r.b.kind, r.b.value = b[0], int(b[1])
+            wr = (N.GateIndex * max(1, len(g["writes"])))()
+            for w, (k, v) in zip(wr, g["writes"]):
+                w.kind, w.value = k, int(v)
+            path = (ctypes.c_uint8 * max(1, len(g["selector_path"])))(*[int(bool(x)) for x in g["selector_path"]])
+            keep += [rels, wr, path]
+            d.relations, d.n_relations = rels, len(g["relations"])
+            d.writes, d.n_writes = wr, len(g["writes"])
+            d.num_repetitions = g["num_repetitions"]
+            d.variables_offset, d.witnesses_offset = g.get("variables_offset", 0), g.get("witnesses_offset", 0)
+            d.constants_offset = g.get("constants_offset", 0)
+            d.constants_placement_offset = g["constants_placement_offset"]
+            d.selector_path_len, d.selector_path = len(g["selector_path"]), path
+
+        def ptrs(cols):
+            return (ctypes.c_void_p * max(1, len(cols)))(*[c.data_ptr() for c in cols])
+
+        n_terms = len(alpha_powers)
+        al = (ctypes.c_uint64 * max(2, 2 * n_terms))(*[int(x) for a in alpha_powers for x in a])
+        self._check(lib.bj_quotient_gates_general_purpose(
+            self._h, descs, len(gates), ptrs(variables), len(variables), ptrs(witnesses), len(witnesses),
+            ptrs(constants), len(constants), al, n_terms, q_c0.numel(), self._ptr(q_c0), self._ptr(q_c1)))
+        return q_c0, q_c1
+
     # ---- FRI ----
     def fri_fold(self, c0, c1, log_fold, alpha, coset_inv):
         """One oracle step (log_fold folds).  Returns (out_c0, out_c1, new_coset_inv)."""

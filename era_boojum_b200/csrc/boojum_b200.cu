@@ -3,3 +3,5 @@
 #include "ntt.cu"
 #include "poseidon2.cu"
 #include "fri.cu"
+#include "elementwise.cu"
+#include "gates.cu"

@@ -91,7 +91,7 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
   ctx->stream = (cudaStream_t)stream;  // NULL == the CUDA legacy default stream (what torch uses by default)
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-  ctx->ntt_max_tile_log = env_int("BJ_NTT_MAX_TILE_LOG", 14);
+  ctx->ntt_max_tile_log = env_int("BJ_NTT_MAX_TILE_LOG", 13);
   if (ctx->ntt_max_tile_log < 8) ctx->ntt_max_tile_log = 8;
   if (ctx->ntt_max_tile_log > 14) ctx->ntt_max_tile_log = 14;
   ctx->ntt_pass1_w = env_int("BJ_NTT_PASS1_W", -1);
@@ -117,6 +117,7 @@ int32_t bj_ctx_destroy(bj_ctx* ctx) {
   }
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->ptr_table) cudaFree(ctx->ptr_table);
+  if (ctx->param_arena) cudaFree(ctx->param_arena);
   delete ctx;
   return BJ_OK;
 }

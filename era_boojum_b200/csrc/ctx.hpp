@@ -38,12 +38,14 @@ struct bj_ctx {
   size_t scratch_bytes = 0;
   void* ptr_table = nullptr;  // device copy of host pointer arrays (Merkle sources)
   size_t ptr_table_bytes = 0;
+  void* param_arena = nullptr;  // bump arena for small per-call parameter blocks
+  size_t param_off = 0;
   uint64_t launches = 0;  // kernels launched by this library through this context
   int sm_count = 148;
   bool ntt_attr_set = false;
   std::vector<void*> attr_done;  // kernels whose smem attributes are set on this device
   int ntt_use_v2 = 1;            // BJ_NTT_V2=0 forces the generic pass kernel
-  int ntt_max_tile_log = 14;  // tunables (env BJ_NTT_*)
+  int ntt_max_tile_log = 13;  // tunables (env BJ_NTT_*)
   int ntt_pass1_w = -1;
   int ntt_chunk_mb = 0;
 };
@@ -82,4 +84,5 @@ struct bj_ctx {
 namespace bj {
 int32_t ensure_scratch(bj_ctx* ctx, size_t bytes);
 int32_t ensure_twiddles(bj_ctx* ctx, int log_n);
+int32_t param_upload(bj_ctx* ctx, const void* host, size_t bytes, void** d_out);
 }  // namespace bj

@@ -328,8 +328,10 @@ static Plan make_plan(const bj_ctx* ctx, int m, bool transpose_last) {
     pl.w[0] = 0;
     return pl;
   }
-  const int TL = transpose_last ? MAXE - 3 : MAXE;
-  const int TM = 11;
+  // tiles of at most 2^MAXE values (default 2^13 = 68 KB of shared memory -> 3 CTAs per SM); the transposing last pass
+  // keeps at least 4 columns so that its stores are 32-byte segments
+  const int TL = transpose_last ? MAXE - 2 : MAXE;
+  const int TM = MAXE - 2;
   int t_last = std::min(TL, std::max((m + 1) / 2, m - 10));
   int rest = m - t_last;
   int n_front = (rest + TM - 1) / TM;
@@ -338,7 +340,7 @@ static Plan make_plan(const bj_ctx* ctx, int m, bool transpose_last) {
   for (int i = 0; i < n_front; i++) {
     int ti = rest / (n_front - i);
     rest -= ti;
-    int wi = ctx->ntt_pass1_w >= 0 ? ctx->ntt_pass1_w : std::max(3, std::min(5, 13 - ti));
+    int wi = ctx->ntt_pass1_w >= 0 ? ctx->ntt_pass1_w : std::max(2, std::min(5, MAXE - ti));
     wi = std::min(wi, MAXE - ti);
     wi = std::min(wi, m - r0 - ti);
     if (ti + wi < 4) wi = 4 - ti;

@@ -239,6 +239,7 @@ struct V2Launch {
 static bool v2_lookup(int t, int w, int kind, V2Launch* out) {
   BJ_V2_CASE(4, 0) BJ_V2_CASE(5, 0) BJ_V2_CASE(6, 0) BJ_V2_CASE(7, 0) BJ_V2_CASE(8, 0) BJ_V2_CASE(9, 0)
   BJ_V2_CASE(10, 0) BJ_V2_CASE(11, 0) BJ_V2_CASE(12, 0) BJ_V2_CASE(13, 0) BJ_V2_CASE(14, 0)
+  BJ_V2_CASE(11, 2)
   BJ_V2_CASE(8, 3) BJ_V2_CASE(9, 3) BJ_V2_CASE(10, 3) BJ_V2_CASE(11, 3)
   BJ_V2_CASE(8, 4) BJ_V2_CASE(9, 4) BJ_V2_CASE(10, 4)
   BJ_V2_CASE(6, 5) BJ_V2_CASE(7, 5) BJ_V2_CASE(8, 5) BJ_V2_CASE(9, 5)

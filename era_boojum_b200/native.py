@@ -62,6 +62,10 @@ SIGNATURES = {
     "bj_poseidon2_hash_rows": (_i32, [_vp, _vp, _u64, _u32, _vp]),
     "bj_poseidon2_permute": (_i32, [_vp, _vp, _u64]),
     "bj_fri_fold": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "bj_batch_inverse": (_i32, [_vp, _vp, _u64]),
+    "bj_batch_inverse_ext": (_i32, [_vp, _vp, _vp, _u64]),
+    "bj_deep_quotient_group": (_i32, [_vp, _vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp]),
+    "bj_quotient_gates_general_purpose": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _u64, _vp, _vp]),
     "bj_ntt_natural_to_bitreversed_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
     "bj_intt_natural_to_natural_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
     "bj_selftest_field": (_i32, [_vp, _u64, _u64, _vp]),
@@ -83,3 +87,23 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 def version():
     return lib.bj_version().decode()
+
+
+class GateIndex(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("value", ctypes.c_uint64)]
+
+
+class GateRelation(ctypes.Structure):
+    _fields_ = [("op", ctypes.c_uint32), ("dst_temporary", ctypes.c_uint32), ("a", GateIndex), ("b", GateIndex)]
+
+
+class GateDesc(ctypes.Structure):
+    _fields_ = [("relations", ctypes.POINTER(GateRelation)), ("n_relations", ctypes.c_uint32), ("n_writes", ctypes.c_uint32),
+                ("writes", ctypes.POINTER(GateIndex)), ("num_repetitions", ctypes.c_uint32),
+                ("variables_offset", ctypes.c_uint32), ("witnesses_offset", ctypes.c_uint32),
+                ("constants_offset", ctypes.c_uint32), ("constants_placement_offset", ctypes.c_uint32),
+                ("selector_path_len", ctypes.c_uint32), ("selector_path", ctypes.POINTER(ctypes.c_uint8))]
+
+
+IDX_VARIABLE, IDX_WITNESS, IDX_CONSTANT_POLY, IDX_TEMPORARY, IDX_CONSTANT_VALUE, IDX_CONSTANT_POLY_SHARED = range(6)
+REL_ADD, REL_DOUBLE, REL_SUB, REL_NEGATE, REL_MUL, REL_SQUARE, REL_INVERSE = range(7)

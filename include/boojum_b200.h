@@ -116,6 +116,68 @@ BJ_API int32_t bj_poseidon2_permute(bj_ctx* ctx, uint64_t* d_states, uint64_t n_
 BJ_API int32_t bj_fri_fold(bj_ctx* ctx, const uint64_t* d_c0, const uint64_t* d_c1, uint32_t log_m, uint32_t log_fold,
                     const uint64_t h_alpha[2], uint64_t* h_coset_inv_io, uint64_t* d_out_c0, uint64_t* d_out_c1);
 
+/* ---- batch inverse: batch_inverse_inplace / batch_inverse_inplace_in_extension (src/cs/implementations/utils.rs:405-600)
+ * In place.  The reference panics on a zero element ("must be called on sets without zeroes", utils.rs:425-427); here a
+ * zero is mapped to zero and does not disturb the other elements. */
+BJ_API int32_t bj_batch_inverse(bj_ctx* ctx, uint64_t* d_data, uint64_t n);
+BJ_API int32_t bj_batch_inverse_ext(bj_ctx* ctx, uint64_t* d_c0, uint64_t* d_c1, uint64_t n);
+
+/* ---- DEEP: quotening_operation_in_extension (src/cs/implementations/prover.rs:2523-2706), one call per opening point
+ * For every point t of the LDE domain (2^log_rows = n*L points, coset-major, bit-reversed inside a coset; x(t) =
+ * 7 * w_{nL}^{bitrev(t)}):   acc[t] += ( sum_i ch_i * (f_i(t) - v_i) ) / (x(t) - at)      in Fp2.
+ * h_src_c0 / h_src_c1: HOST arrays of n_src DEVICE pointers to the c0 / c1 columns (each n*L u64, LDE layout);
+ *   h_src_c1[i] == NULL marks a base-field polynomial (prover.rs:2655-2677).
+ * h_values_at / h_challenges: n_src (c0, c1) pairs: f_i(at) and the challenge coefficient of term i.
+ * d_acc_c0 / d_acc_c1: the Fp2 codeword accumulated across calls (zero-initialised by the caller). */
+BJ_API int32_t bj_deep_quotient_group(bj_ctx* ctx, const uint64_t* const* h_src_c0, const uint64_t* const* h_src_c1,
+                               uint32_t n_src, const uint64_t* h_values_at, const uint64_t* h_challenges,
+                               const uint64_t h_at[2], uint32_t log_rows, uint64_t* d_acc_c0, uint64_t* d_acc_c1);
+
+/* ---- gate / quotient evaluator over general-purpose columns: the row loop of prove_cpu_basic
+ *      (src/cs/implementations/prover.rs:1031-1080) with GateConstraintEvaluator::evaluate_once (src/cs/traits/evaluator.rs:145-152)
+ *      supplied as DATA: the SSA program recorded by the reference's own GPU hook, gpu_synthesizer::GPUDataCapture
+ *      (src/gpu_synthesizer/mod.rs:115-133 Index / Relation, :354-443 capture). */
+enum { /* Index<F> (gpu_synthesizer/mod.rs:115-121); SHARED = a ConstantPoly listed in row_shared_constants_set */
+  BJ_IDX_VARIABLE = 0, BJ_IDX_WITNESS = 1, BJ_IDX_CONSTANT_POLY = 2, BJ_IDX_TEMPORARY = 3, BJ_IDX_CONSTANT_VALUE = 4,
+  BJ_IDX_CONSTANT_POLY_SHARED = 5
+};
+enum { /* Relation<F> (gpu_synthesizer/mod.rs:125-133) */
+  BJ_REL_ADD = 0, BJ_REL_DOUBLE = 1, BJ_REL_SUB = 2, BJ_REL_NEGATE = 3, BJ_REL_MUL = 4, BJ_REL_SQUARE = 5, BJ_REL_INVERSE = 6
+};
+typedef struct bj_gate_index {
+  uint32_t kind;   /* BJ_IDX_* */
+  uint32_t reserved;
+  uint64_t value;  /* column / temporary index, or the field element for BJ_IDX_CONSTANT_VALUE */
+} bj_gate_index;
+typedef struct bj_gate_relation {
+  uint32_t op;            /* BJ_REL_* */
+  uint32_t dst_temporary; /* TemporaryValue index this relation defines (< 96) */
+  bj_gate_index a, b;     /* b ignored by the unary relations */
+} bj_gate_relation;
+typedef struct bj_gate_desc {
+  const bj_gate_relation* relations; /* GPUDataCapture::relations, in recording order */
+  uint32_t n_relations;
+  uint32_t n_writes;
+  const bj_gate_index* writes;       /* GPUDataCapture::writes_per_repetition (one quotient term each) */
+  uint32_t num_repetitions;          /* num_repetitions_on_row */
+  uint32_t variables_offset;         /* PerChunkOffset (GatePlacementType::MultipleOnRow) */
+  uint32_t witnesses_offset;
+  uint32_t constants_offset;
+  uint32_t constants_placement_offset; /* first constant column of the gate = selector path length (prover.rs:1000-1013) */
+  uint32_t selector_path_len;          /* TreeNode path of the gate; 0 = no selector */
+  const uint8_t* selector_path;        /* path[i] != 0: factor const_i, else (1 - const_i) (prover.rs:2775-2916) */
+} bj_gate_desc;
+/* For every point t < n_points (= Q * n, the first Q cosets of the LDE, flat coset-major):
+ *   q[t] += sum_g selector_g(t) * sum_k alpha_pow[k] * term_k(t),  k running over the terms of all gates in order
+ * (gates with zero terms, e.g. NOP, are simply not passed).  Column pointer arrays are HOST arrays of DEVICE pointers,
+ * each column flat [coset][row] as produced by bj_lde.  h_alpha_powers: (c0, c1) pairs, one per term. */
+BJ_API int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_desc* h_gates, uint32_t n_gates,
+                                          const uint64_t* const* h_variable_cols, uint32_t n_variables,
+                                          const uint64_t* const* h_witness_cols, uint32_t n_witnesses,
+                                          const uint64_t* const* h_constant_cols, uint32_t n_constants,
+                                          const uint64_t* h_alpha_powers, uint32_t n_alpha_powers,
+                                          uint64_t n_points, uint64_t* d_q_c0, uint64_t* d_q_c1);
+
 /* ---- host-buffer convenience entry points (what the Rust shim calls when columns live in host Vecs).
  * They upload, run, download and synchronise; used for the end-to-end measurement. */
 BJ_API int32_t bj_ntt_natural_to_bitreversed_host(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint32_t n_cols,

@@ -447,3 +447,30 @@ API void orc_deep_point(uint64_t acc[2], const uint64_t *f_c0, const uint64_t *f
   acc[0] = r.c0;
   acc[1] = r.c1;
 }
+
+/* DEEP accumulation over the whole LDE domain for one opening point (prover-side driver of the sum above):
+ * quotening_operation_in_extension                              src/cs/implementations/prover.rs:2523-2706
+ * for t in 0..2^log_rows: x = 7 * w_{nL}^{bitrev(t)};  acc[t] += sum_i ch_i (f_i[t] - v_i) / (x - at)
+ * src_c1[i] == NULL marks a base-field polynomial. */
+API void orc_deep_group(uint64_t *acc0, uint64_t *acc1, const uint64_t *const *src_c0, const uint64_t *const *src_c1,
+                        size_t n_src, const uint64_t *values_at, const uint64_t *challenges, const uint64_t at[2],
+                        unsigned log_rows) {
+  size_t rows = (size_t)1 << log_rows;
+  uint64_t w = gl_omega(log_rows);
+  gl2_t a = {gl_canon(at[0]), gl_canon(at[1])};
+#pragma omp parallel for schedule(static)
+  for (long t = 0; t < (long)rows; t++) {
+    uint64_t x = gl_mul(GL_MULT_GEN, gl_pow(w, gl_bitrev((size_t)t, log_rows)));
+    gl2_t den = gl2_inv(gl2_sub((gl2_t){x, 0}, a));
+    gl2_t s = {0, 0};
+    for (size_t i = 0; i < n_src; i++) {
+      gl2_t f = {gl_canon(src_c0[i][t]), src_c1[i] ? gl_canon(src_c1[i][t]) : 0};
+      gl2_t v = {gl_canon(values_at[2 * i]), gl_canon(values_at[2 * i + 1])};
+      gl2_t c = {gl_canon(challenges[2 * i]), gl_canon(challenges[2 * i + 1])};
+      s = gl2_add(s, gl2_mul(c, gl2_sub(f, v)));
+    }
+    s = gl2_mul(s, den);
+    acc0[t] = gl_add(gl_canon(acc0[t]), s.c0);
+    acc1[t] = gl_add(gl_canon(acc1[t]), s.c1);
+  }
+}

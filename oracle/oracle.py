@@ -54,6 +54,7 @@ def lib():
             "orc_batch_inverse": (None, [vp, sz]),
             "orc_batch_inverse_ext": (None, [vp, vp, sz]),
             "orc_deep_point": (None, [vp, vp, vp, vp, vp, vp, vp, sz, u64, vp]),
+            "orc_deep_group": (None, [vp, vp, vp, vp, sz, vp, vp, vp, ctypes.c_uint]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -268,6 +269,22 @@ def deep_point(acc, f, v, ch, x, at):
     a, at_ = _u64(acc).copy(), _u64(at)
     lib().orc_deep_point(_p(a), *[_p(c) for c in cols], f.shape[0], x, _p(at_))
     return (int(a[0]), int(a[1]))
+
+
+def deep_group(acc0, acc1, sources, values_at, challenges, at):
+    """quotening_operation_in_extension over the whole LDE domain (prover.rs:2523-2706).
+    sources: list of (c0_array, c1_array_or_None); returns updated (acc0, acc1)."""
+    a0, a1 = _u64(acc0).copy(), _u64(acc1).copy()
+    c0s = [_u64(s[0]).reshape(-1) for s in sources]
+    c1s = [(_u64(s[1]).reshape(-1) if s[1] is not None else None) for s in sources]
+    n = len(sources)
+    p0 = (ctypes.c_void_p * n)(*[c.ctypes.data for c in c0s])
+    p1 = (ctypes.c_void_p * n)(*[(c.ctypes.data if c is not None else None) for c in c1s])
+    vals = _u64(np.array(values_at, dtype=np.uint64).reshape(-1))
+    chs = _u64(np.array(challenges, dtype=np.uint64).reshape(-1))
+    at_ = _u64(np.array(at, dtype=np.uint64))
+    lib().orc_deep_group(_p(a0), _p(a1), p0, p1, n, _p(vals), _p(chs), _p(at_), a0.shape[0].bit_length() - 1)
+    return a0, a1
 
 
 def random_field(rng, shape):

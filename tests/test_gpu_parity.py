@@ -327,3 +327,175 @@ def test_device_field_selftest(bj, ctx):
     bad = ctypes.c_uint64(123)
     st = native.lib.bj_selftest_field(ctx._h, 1 << 22, 20260924, ctypes.byref(bad))
     assert st == 0 and bad.value == 0
+
+
+# ----------------------------------------------------------------------------- batch inverse / DEEP ---------
+@pytest.mark.parametrize("n", [1, 7, 8, 1000, 1 << 16])
+def test_batch_inverse_matches_oracle(bj, ctx, n):
+    r = rng(n)
+    a = O.random_field(r, n)
+    a[a == 0] = 1
+    got = bj.to_numpy(ctx.batch_inverse_inplace(bj.to_device(a)))
+    assert np.array_equal(got, O.batch_inverse(a))
+    c0, c1 = O.random_field(r, n), O.random_field(r, n)
+    g0, g1 = ctx.batch_inverse_inplace_in_extension(bj.to_device(c0), bj.to_device(c1))
+    w0, w1 = O.batch_inverse_ext(c0, c1)
+    assert np.array_equal(bj.to_numpy(g0), w0) and np.array_equal(bj.to_numpy(g1), w1)
+
+
+def test_batch_inverse_zero_maps_to_zero(bj, ctx):
+    a = np.array([5, 0, 7, P, 11, 0, 13, 17, 19, 23], dtype=np.uint64)
+    got = bj.to_numpy(ctx.batch_inverse_inplace(bj.to_device(a)))
+    for x, y in zip(a, got):
+        assert int(y) == (pow(int(x) % P, P - 2, P) if int(x) % P else 0)
+
+
+@pytest.mark.parametrize("log_rows,n_base,n_ext", [(6, 3, 2), (12, 9, 4), (15, 20, 3)])
+def test_deep_group_matches_oracle(bj, ctx, log_rows, n_base, n_ext):
+    rows = 1 << log_rows
+    r = rng(log_rows)
+    srcs = [(O.random_field(r, rows), None) for _ in range(n_base)]
+    srcs += [(O.random_field(r, rows), O.random_field(r, rows)) for _ in range(n_ext)]
+    n = len(srcs)
+    vals = [tuple(int(x) for x in O.random_field(r, 2)) for _ in range(n)]
+    for i in range(n_base):
+        vals[i] = (vals[i][0], vals[i][1])  # the value at an Fp2 point is in Fp2 even for base-field polynomials
+    chs = [tuple(int(x) for x in O.random_field(r, 2)) for _ in range(n)]
+    acc0, acc1 = O.random_field(r, rows), O.random_field(r, rows)
+    for at in ([int(x) for x in O.random_field(r, 2)], [0, 0], [int(O.omega(4)), 0]):
+        d_srcs = [(bj.to_device(s0), bj.to_device(s1) if s1 is not None else None) for s0, s1 in srcs]
+        g0, g1 = ctx.quotening_operation_in_extension(bj.to_device(acc0), bj.to_device(acc1), d_srcs, vals, at, chs)
+        w0, w1 = O.deep_group(acc0, acc1, srcs, vals, chs, at)
+        assert np.array_equal(bj.to_numpy(g0), w0) and np.array_equal(bj.to_numpy(g1), w1)
+
+
+def test_deep_golden_fixture_point(bj, ctx, golden_fixture):
+    """One opened row of the reference proof embedded at its true LDE position: the GPU DEEP value over the four
+    opening groups equals the element in the first FRI leaf (verifier.rs:2154-2384)."""
+    fx = golden_fixture
+    c = replay.replay_proof(fx)
+    proof, vk = fx["proof"], fx["vk"]
+    fp = vk["fixed_parameters"]
+    log_n = fp["domain_size"].bit_length() - 1
+    log_rows = log_n + 1
+    idx = _query_indices(fx)[0]
+    q = proof["queries_per_fri_repetition"][0]
+    wq, sq = q["witness_query"]["leaf_elements"], q["stage_2_query"]["leaf_elements"]
+    qq, uq = q["quotient_query"]["leaf_elements"], q["setup_query"]["leaf_elements"]
+    V, C, vw = 155, 8, 155
+    base = lambda els: [(e, None) for e in els]
+    ext = lambda els: [(els[i], els[i + 1]) for i in range(0, len(els), 2)]
+    src_z = base(wq[:vw]) + base(uq[V:V + C]) + base(uq[:V]) + ext(sq[0:2]) + ext(sq[2:40]) + base(wq[vw:vw + 1]) \
+        + ext(sq[40:56]) + ext(sq[56:]) + base(uq[V + C:V + C + 4]) + ext(qq)
+    groups = [(src_z, [tuple(v["coeffs"]) for v in proof["values_at_z"]], c["challenges"]["z"])]
+    w_n = replay.omega(log_n)
+    z = c["challenges"]["z"]
+    groups.append((ext(sq[0:2]), [tuple(v["coeffs"]) for v in proof["values_at_z_omega"]], replay.e_mul_base(z, w_n)))
+    groups.append((ext(sq[40:56]) + ext(sq[56:]), [tuple(v["coeffs"]) for v in proof["values_at_0"]], (0, 0)))
+    pi_at = pow(w_n, fp["public_inputs_locations"][0][1], P)
+    groups.append(([(wq[col], None) for col, _ in fp["public_inputs_locations"]],
+                   [(v, 0) for v in proof["public_inputs"]], (pi_at, 0)))
+    ch = replay.ext_powers(c["challenges"]["deep"], 374)
+    import torch
+    acc0 = torch.zeros(1 << log_rows, dtype=torch.int64, device="cuda:0")
+    acc1 = torch.zeros(1 << log_rows, dtype=torch.int64, device="cuda:0")
+    off = 0
+    for srcs, vals, at in groups:
+        d_srcs = []
+        for s0, s1 in srcs:
+            t0 = torch.zeros(1 << log_rows, dtype=torch.int64, device="cuda:0")
+            t0[idx] = int(np.array([s0], dtype=np.uint64).view(np.int64)[0])
+            t1 = None
+            if s1 is not None:
+                t1 = torch.zeros(1 << log_rows, dtype=torch.int64, device="cuda:0")
+                t1[idx] = int(np.array([s1], dtype=np.uint64).view(np.int64)[0])
+            d_srcs.append((t0, t1))
+        ctx.quotening_operation_in_extension(acc0, acc1, d_srcs, vals, at, ch[off:off + len(srcs)])
+        off += len(srcs)
+        del d_srcs
+    assert off == 374
+    le = q["fri_queries"][0]["leaf_elements"]
+    sub = idx % 8
+    got = (int(bj.to_numpy(acc0[idx:idx + 1])[0]), int(bj.to_numpy(acc1[idx:idx + 1])[0]))
+    assert got == (le[sub], le[8 + sub])
+
+
+# ------------------------------------------------------------------------------ gate / quotient evaluator -----
+def _sha_gate_programs():
+    """The SSA programs gpu_synthesizer::GPUDataCapture::from_evaluator records for the three evaluators of the
+    SHA-256 bench circuit (src/gadgets/sha256/mod.rs:348-373), written out by hand."""
+    from era_boojum_b200 import native as N
+    V, C, CS, T = N.IDX_VARIABLE, N.IDX_CONSTANT_POLY, N.IDX_CONSTANT_POLY_SHARED, N.IDX_TEMPORARY
+    fma = dict(relations=[(N.REL_MUL, 0, (V, 2), (CS, 1)),      # contribution = c * linear_coeff
+                          (N.REL_MUL, 1, (V, 0), (V, 1)),       # t = a * b
+                          (N.REL_MUL, 2, (CS, 0), (T, 1)),      # quad * t
+                          (N.REL_ADD, 3, (T, 0), (T, 2)),
+                          (N.REL_SUB, 4, (T, 3), (V, 3))],
+               writes=[(T, 4)], variables_offset=4, constants_offset=0)
+    red = dict(relations=[(N.REL_MUL, 0, (V, 0), (CS, 0)), (N.REL_MUL, 1, (V, 1), (CS, 1)), (N.REL_ADD, 2, (T, 0), (T, 1)),
+                          (N.REL_MUL, 3, (V, 2), (CS, 2)), (N.REL_ADD, 4, (T, 2), (T, 3)),
+                          (N.REL_MUL, 5, (V, 3), (CS, 3)), (N.REL_ADD, 6, (T, 4), (T, 5)),
+                          (N.REL_SUB, 7, (T, 6), (V, 4))],
+               writes=[(T, 7)], variables_offset=5, constants_offset=0)
+    ca = dict(relations=[(N.REL_SUB, 0, (V, 0), (C, 0))], writes=[(T, 0)], variables_offset=1, constants_offset=1)
+    return {"fma": fma, "reduction4": red, "constant_allocator": ca}
+
+
+@pytest.mark.parametrize("log_rows", [5, 11])
+def test_gate_evaluator_sha_circuit_shape(bj, ctx, log_rows):
+    """60 general-purpose columns, 4 + 3 constant columns, gates ConstantAllocator x4 / FMA x15 / Reduction<4> x12 with
+    selector paths of a 3-level tree; compared point by point with the oracle's restatement of the reference."""
+    from oracle import gates as G
+    rows = 1 << log_rows
+    r = rng(log_rows)
+    n_vars, n_consts = 60, 7
+    var_cols = [O.random_field(r, rows) for _ in range(n_vars)]
+    const_cols = [O.random_field(r, rows) for _ in range(n_consts)]
+    layout = [("constant_allocator", 4, [True, False]), ("fma", 15, [True, True]), ("reduction4", 12, [False])]
+    n_terms = sum(reps for _, reps, _ in layout)
+    alphas = [tuple(int(x) for x in O.random_field(r, 2)) for _ in range(n_terms)]
+    progs = _sha_gate_programs()
+    gates = []
+    for name, reps, path in layout:
+        g = dict(progs[name])
+        g.update(num_repetitions=reps, constants_placement_offset=len(path), selector_path=path)
+        gates.append(g)
+    q0, q1 = O.random_field(r, rows), O.random_field(r, rows)
+    d0, d1 = bj.to_device(q0), bj.to_device(q1)
+    ctx.evaluate_gates_over_general_purpose_columns(gates, [bj.to_device(c) for c in var_cols], [],
+                                                    [bj.to_device(c) for c in const_cols], alphas, d0, d1)
+    g0, g1 = bj.to_numpy(d0), bj.to_numpy(d1)
+    check = range(rows) if rows <= 64 else list(range(0, rows, 37)) + [rows - 1]
+    for t in check:
+        vr = [int(c[t]) for c in var_cols]
+        cr = [int(c[t]) for c in const_cols]
+        w0, w1 = G.quotient_gates_row(layout, vr, cr, alphas)
+        assert int(g0[t]) == (int(q0[t]) + w0) % P and int(g1[t]) == (int(q1[t]) + w1) % P, t
+
+
+def test_gate_evaluator_all_relations(bj, ctx):
+    """every Relation kind incl. Double / Negate / Square / Inverse, witness columns and immediate constants."""
+    from era_boojum_b200 import native as N
+    rows = 256
+    r = rng(3)
+    v = [O.random_field(r, rows) for _ in range(2)]
+    w = [O.random_field(r, rows)]
+    w[0][w[0] == 0] = 1
+    c = [O.random_field(r, rows)]
+    V, W, C, T, K = N.IDX_VARIABLE, N.IDX_WITNESS, N.IDX_CONSTANT_POLY, N.IDX_TEMPORARY, N.IDX_CONSTANT_VALUE
+    rel = [(N.REL_DOUBLE, 0, (V, 0), None), (N.REL_NEGATE, 1, (V, 1), None), (N.REL_SQUARE, 2, (T, 0), None),
+           (N.REL_INVERSE, 3, (W, 0), None), (N.REL_MUL, 4, (T, 2), (T, 3)), (N.REL_ADD, 5, (T, 4), (K, 12345)),
+           (N.REL_SUB, 6, (T, 5), (C, 0)), (N.REL_MUL, 7, (T, 6), (T, 1))]
+    gate = dict(relations=rel, writes=[(T, 7), (T, 1)], num_repetitions=1, constants_placement_offset=0, selector_path=[])
+    alphas = [(3, 5), (7, 11)]
+    import torch
+    d0 = torch.zeros(rows, dtype=torch.int64, device="cuda:0")
+    d1 = torch.zeros(rows, dtype=torch.int64, device="cuda:0")
+    ctx.evaluate_gates_over_general_purpose_columns([gate], [bj.to_device(x) for x in v], [bj.to_device(x) for x in w],
+                                                    [bj.to_device(x) for x in c], alphas, d0, d1)
+    g0, g1 = bj.to_numpy(d0), bj.to_numpy(d1)
+    for t in range(rows):
+        a, b, ww, cc = int(v[0][t]), int(v[1][t]), int(w[0][t]), int(c[0][t])
+        t1 = (-b) % P
+        t7 = ((((2 * a) ** 2 % P) * pow(ww, P - 2, P) + 12345 - cc) % P) * t1 % P
+        assert int(g0[t]) == (t7 * 3 + t1 * 7) % P and int(g1[t]) == (t7 * 5 + t1 * 11) % P

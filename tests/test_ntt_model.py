@@ -29,7 +29,7 @@ def test_plans_cover_all_rounds():
             r0 = 0
             for i, (t, w) in enumerate(plan):
                 last = i == len(plan) - 1
-                assert 4 <= t + w <= 14 or m < 4
+                assert 4 <= t + w <= 13 or m < 4
                 if not (inv and last):
                     assert w <= m - r0 - t
                 else:

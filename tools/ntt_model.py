@@ -30,11 +30,11 @@ def twiddle_table(log_n, inverse):
     return [pow(w, brev(k, bits), P) for k in range(1 << bits)] if log_n >= 1 else [1]
 
 
-def make_plan(m, transpose_last, MAXE=14, pass1_w=-1):
+def make_plan(m, transpose_last, MAXE=13, pass1_w=-1):
     if m <= 12:
         return [(m, 0)]
-    TL = MAXE - 3 if transpose_last else MAXE
-    TM = 11
+    TL = MAXE - 2 if transpose_last else MAXE
+    TM = MAXE - 2
     t_last = min(TL, max((m + 1) // 2, m - 10))
     rest = m - t_last
     n_front = (rest + TM - 1) // TM
@@ -42,7 +42,7 @@ def make_plan(m, transpose_last, MAXE=14, pass1_w=-1):
     for i in range(n_front):
         ti = rest // (n_front - i)
         rest -= ti
-        wi = pass1_w if pass1_w >= 0 else max(3, min(5, 13 - ti))
+        wi = pass1_w if pass1_w >= 0 else max(2, min(5, MAXE - ti))
         wi = min(wi, MAXE - ti)
         wi = min(wi, m - r0 - ti)
         if ti + wi < 4:
@@ -141,7 +141,7 @@ def run_pass(src, m, r0, t, w, kind, tab, scale=None, scale_on_load=True):
     return dst
 
 
-def transform(a, coset=1, inverse=False, MAXE=14, pass1_w=-1):
+def transform(a, coset=1, inverse=False, MAXE=13, pass1_w=-1):
     a = [int(x) % P for x in a]
     m = len(a).bit_length() - 1
     assert m >= 4
