@@ -23,7 +23,78 @@ import numpy as np
 from . import native
 from .native import BoojumError, P, lib
 
-__all__ = ["Context", "MerkleTreeWithCap", "BoojumError", "P", "to_device", "to_numpy"]
+__all__ = ["Context", "MerkleTreeWithCap", "Transcript", "FriOracles", "BoojumError", "P", "to_device", "to_numpy"]
+
+
+class Transcript:
+    """GoldilocksPoisedon2Transcript (cs/implementations/transcript.rs:62-129, 140-151) - host side."""
+
+    def __init__(self):
+        self._h = ctypes.c_void_p(lib.bj_transcript_new())
+
+    def witness_field_elements(self, els):
+        a = np.ascontiguousarray(np.array([int(e) for e in els], dtype=np.uint64))
+        lib.bj_transcript_witness_field_elements(self._h, a.ctypes.data_as(ctypes.c_void_p), a.shape[0])
+
+    def witness_merkle_tree_cap(self, cap):
+        a = np.ascontiguousarray(np.array(cap, dtype=np.uint64).reshape(-1, 4))
+        lib.bj_transcript_witness_merkle_tree_cap(self._h, a.ctypes.data_as(ctypes.c_void_p), a.shape[0])
+
+    def get_challenge(self):
+        return int(lib.bj_transcript_get_challenge(self._h))
+
+    def get_multiple_challenges_fixed(self, n=2):
+        return tuple(self.get_challenge() for _ in range(n))
+
+    def get_index_bits(self, num_bits, max_needed):
+        """BoolsBuffer::get_bits (transcript.rs:369-417) packed LSB first."""
+        return int(lib.bj_transcript_get_index_bits(self._h, num_bits, max_needed))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.bj_transcript_free(self._h)
+            self._h = None
+
+
+class FriOracles:
+    """FriOracles (cs/implementations/fri/mod.rs:36-47): base + intermediate oracle caps, monomial forms, queries."""
+
+    def __init__(self, handle, cap_size, keepalive):
+        self._h, self.cap_size, self._keep = handle, cap_size, keepalive
+
+    def num_oracles(self):
+        return int(lib.bj_fri_oracles_num_oracles(self._h))
+
+    def get_cap(self, i):
+        out = np.zeros((self.cap_size, 4), np.uint64)
+        assert lib.bj_fri_oracles_get_cap(self._h, i, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        return out
+
+    def monomial_forms(self):
+        n = int(lib.bj_fri_oracles_num_monomials(self._h))
+        c0, c1 = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        assert lib.bj_fri_oracles_get_monomials(self._h, c0.ctypes.data_as(ctypes.c_void_p), c1.ctypes.data_as(ctypes.c_void_p)) == 0
+        return c0, c1
+
+    def challenges(self):
+        out = np.zeros((self.num_oracles(), 2), np.uint64)
+        assert lib.bj_fri_oracles_get_challenges(self._h, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        return [tuple(int(x) for x in r) for r in out]
+
+    def query(self, oracle_idx, leaf_index, log_fold):
+        le = np.zeros(2 << log_fold, np.uint64)
+        path = np.zeros((40, 4), np.uint64)
+        plen = ctypes.c_uint32()
+        st = lib.bj_fri_oracles_query(self._h, oracle_idx, leaf_index, le.ctypes.data_as(ctypes.c_void_p),
+                                      path.ctypes.data_as(ctypes.c_void_p), ctypes.byref(plen))
+        if st != 0:
+            raise BoojumError(st, "bj_fri_oracles_query")
+        return le, path[: plen.value]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.bj_fri_oracles_free(self._h)
+            self._h = None
 
 
 def to_device(a, device="cuda:0"):
@@ -244,7 +315,36 @@ class Context:
             ptrs(constants), len(constants), al, n_terms, q_c0.numel(), self._ptr(q_c0), self._ptr(q_c1)))
         return q_c0, q_c1
 
+    # ---- queries ----
+    def query_leaf_elements(self, sources, indices, elems_per_leaf=1):
+        n_src = len(sources)
+        ptrs = (ctypes.c_void_p * n_src)(*[s.data_ptr() for s in sources])
+        idx = np.ascontiguousarray(np.array(indices, dtype=np.uint64))
+        out = np.zeros((len(idx), n_src * elems_per_leaf), np.uint64)
+        self._check(lib.bj_query_leaf_elements(self._h, ptrs, n_src, elems_per_leaf, idx.ctypes.data_as(ctypes.c_void_p),
+                                               len(idx), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def merkle_paths(self, tree, indices):
+        n_leaves = tree.leaf_hashes.shape[0]
+        depth = (n_leaves // tree.cap_size).bit_length() - 1
+        idx = np.ascontiguousarray(np.array(indices, dtype=np.uint64))
+        out = np.zeros((len(idx), max(depth, 1), 4), np.uint64)
+        nodes_ptr = self._ptr(tree.nodes) if tree.nodes.numel() else None
+        self._check(lib.bj_merkle_paths(self._h, self._ptr(tree.leaf_hashes), nodes_ptr, n_leaves, tree.cap_size,
+                                        idx.ctypes.data_as(ctypes.c_void_p), len(idx), out.ctypes.data_as(ctypes.c_void_p)))
+        return out[:, :depth, :]
+
     # ---- FRI ----
+    def do_fri(self, transcript, c0, c1, schedule, lde_degree, cap_size):
+        """do_fri (cs/implementations/fri/mod.rs:49-357): commit phase driven from the host transcript."""
+        log_full = c0.numel().bit_length() - 1
+        sched = (ctypes.c_uint32 * len(schedule))(*schedule)
+        h = ctypes.c_void_p()
+        self._check(lib.bj_do_fri(self._h, transcript._h, self._ptr(c0), self._ptr(c1), log_full, sched, len(schedule),
+                                  lde_degree.bit_length() - 1, cap_size, ctypes.byref(h)))
+        return FriOracles(h, cap_size, (c0, c1))
+
     def fri_fold(self, c0, c1, log_fold, alpha, coset_inv):
         """One oracle step (log_fold folds).  Returns (out_c0, out_c1, new_coset_inv)."""
         torch = self._torch

@@ -5,3 +5,5 @@
 #include "fri.cu"
 #include "elementwise.cu"
 #include "gates.cu"
+#include "host_transcript.cu"
+#include "fri_driver.cu"

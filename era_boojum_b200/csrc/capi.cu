@@ -118,6 +118,16 @@ int32_t bj_ctx_destroy(bj_ctx* ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->ptr_table) cudaFree(ctx->ptr_table);
   if (ctx->param_arena) cudaFree(ctx->param_arena);
+  if (ctx->host_ring) cudaFree(ctx->host_ring);
+  if (ctx->copy_streams_ready) {
+    cudaStreamDestroy(ctx->h2d_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
+    for (int i = 0; i < 3; i++) {
+      cudaEventDestroy(ctx->ev_up[i]);
+      cudaEventDestroy(ctx->ev_done[i]);
+      cudaEventDestroy(ctx->ev_down[i]);
+    }
+  }
   delete ctx;
   return BJ_OK;
 }

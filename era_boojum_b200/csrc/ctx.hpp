@@ -38,6 +38,12 @@ struct bj_ctx {
   size_t scratch_bytes = 0;
   void* ptr_table = nullptr;  // device copy of host pointer arrays (Merkle sources)
   size_t ptr_table_bytes = 0;
+  // host-buffer entry points: auxiliary copy streams + device staging ring (created on first use)
+  bool copy_streams_ready = false;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_up[3] = {}, ev_done[3] = {}, ev_down[3] = {};
+  void* host_ring = nullptr;
+  size_t host_ring_bytes = 0;
   void* param_arena = nullptr;  // bump arena for small per-call parameter blocks
   size_t param_off = 0;
   uint64_t launches = 0;  // kernels launched by this library through this context

@@ -565,38 +565,81 @@ int32_t bj_lde(bj_ctx* ctx, const uint64_t* d_in, uint64_t in_col_stride, uint64
   return BJ_OK;
 }
 
+// Host-buffer entry points: the batch is cut into column chunks that flow through a 3-slot device ring, upload of chunk
+// k+1, transform of chunk k and download of chunk k-1 overlapping on three streams (copy engines are full duplex).
+// Overlap needs pinned host memory (bj_alloc_host_pinned / cudaHostRegister); pageable memory still works, serialised.
+static int32_t host_pipeline(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint32_t n_cols, uint64_t coset, bool inverse) {
+  if (!ctx || !h_data || log_n > 32) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "host transform: bad argument");
+  if (n_cols == 0) return BJ_OK;
+  const u64 n = 1ull << log_n;
+  const size_t col_bytes = sizeof(u64) * n;
+  // ~64 MiB chunks, at least one column
+  u32 chunk_cols = (u32)std::max<u64>(1, std::min<u64>(n_cols, ((64ull << 20) / col_bytes)));
+  const u32 n_chunks = (n_cols + chunk_cols - 1) / chunk_cols;
+  const int SLOTS = 3;
+  if (!ctx->copy_streams_ready) {
+    BJ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    BJ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) {
+      BJ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming));
+      BJ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+      BJ_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_down[i], cudaEventDisableTiming));
+    }
+    ctx->copy_streams_ready = true;
+  }
+  const size_t slot_bytes = col_bytes * chunk_cols;
+  if (ctx->host_ring_bytes < slot_bytes * SLOTS) {
+    if (ctx->host_ring) {
+      BJ_CUDA(ctx, cudaDeviceSynchronize());
+      cudaFree(ctx->host_ring);
+      ctx->host_ring = nullptr;
+      ctx->host_ring_bytes = 0;
+    }
+    if (cudaMalloc(&ctx->host_ring, slot_bytes * SLOTS) != cudaSuccess) {
+      cudaGetLastError();
+      BJ_FAIL(ctx, BJ_ERR_OOM, "host transform: device staging allocation failed");
+    }
+    ctx->host_ring_bytes = slot_bytes * SLOTS;
+  }
+  // the ring may still be in use by a previous call's downloads
+  BJ_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+  BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int32_t st = BJ_OK;
+  for (u32 k = 0; k < n_chunks && st == BJ_OK; k++) {
+    const int slot = k % SLOTS;
+    const u32 c0 = k * chunk_cols, cnt = std::min(chunk_cols, n_cols - c0);
+    uint64_t* d = (uint64_t*)((char*)ctx->host_ring + slot_bytes * slot);
+    uint64_t* h = h_data + (u64)c0 * n;
+    if (k >= (u32)SLOTS) BJ_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_down[slot], 0));  // slot drained
+    BJ_CUDA(ctx, cudaMemcpyAsync(d, h, col_bytes * cnt, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    BJ_CUDA(ctx, cudaEventRecord(ctx->ev_up[slot], ctx->h2d_stream));
+    BJ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[slot], 0));
+    st = inverse ? bj_intt_natural_to_natural(ctx, d, log_n, cnt, n, coset)
+                 : bj_ntt_natural_to_bitreversed(ctx, d, log_n, cnt, n, coset);
+    if (st != BJ_OK) break;
+    BJ_CUDA(ctx, cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+    BJ_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_done[slot], 0));
+    BJ_CUDA(ctx, cudaMemcpyAsync(h, d, col_bytes * cnt, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    BJ_CUDA(ctx, cudaEventRecord(ctx->ev_down[slot], ctx->d2h_stream));
+  }
+  cudaError_t e1 = cudaStreamSynchronize(ctx->d2h_stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  if (st == BJ_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+    ctx->last_error = std::string("host transform: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
+    st = BJ_ERR_CUDA;
+  }
+  return st;
+}
+
 int32_t bj_ntt_natural_to_bitreversed_host(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint32_t n_cols,
                                            uint64_t coset) {
-  if (!ctx || !h_data || log_n > 32) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bad argument");
-  const size_t bytes = (sizeof(u64) << log_n) * n_cols;
-  void* d = nullptr;
-  BJ_CUDA(ctx, cudaMallocAsync(&d, bytes, ctx->stream));
-  int32_t st = BJ_OK;
-  if (cudaMemcpyAsync(d, h_data, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = BJ_ERR_CUDA;
-  if (st == BJ_OK) st = bj_ntt_natural_to_bitreversed(ctx, (uint64_t*)d, log_n, n_cols, 1ull << log_n, coset);
-  if (st == BJ_OK && cudaMemcpyAsync(h_data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-    st = BJ_ERR_CUDA;
-  cudaFreeAsync(d, ctx->stream);
-  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && st == BJ_OK) st = BJ_ERR_CUDA;
-  if (st == BJ_ERR_CUDA && ctx->last_error.empty()) ctx->last_error = "host NTT: CUDA failure";
-  return st;
+  return host_pipeline(ctx, h_data, log_n, n_cols, coset, false);
 }
 
 int32_t bj_intt_natural_to_natural_host(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint32_t n_cols,
                                         uint64_t coset) {
-  if (!ctx || !h_data || log_n > 32) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bad argument");
-  const size_t bytes = (sizeof(u64) << log_n) * n_cols;
-  void* d = nullptr;
-  BJ_CUDA(ctx, cudaMallocAsync(&d, bytes, ctx->stream));
-  int32_t st = BJ_OK;
-  if (cudaMemcpyAsync(d, h_data, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = BJ_ERR_CUDA;
-  if (st == BJ_OK) st = bj_intt_natural_to_natural(ctx, (uint64_t*)d, log_n, n_cols, 1ull << log_n, coset);
-  if (st == BJ_OK && cudaMemcpyAsync(h_data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-    st = BJ_ERR_CUDA;
-  cudaFreeAsync(d, ctx->stream);
-  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && st == BJ_OK) st = BJ_ERR_CUDA;
-  if (st == BJ_ERR_CUDA && ctx->last_error.empty()) ctx->last_error = "host iNTT: CUDA failure";
-  return st;
+  if (ctx && gl::canon(coset) == 0) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "coset must be invertible");
+  return host_pipeline(ctx, h_data, log_n, n_cols, coset, true);
 }
 
 }  // extern "C"

@@ -68,6 +68,23 @@ SIGNATURES = {
     "bj_quotient_gates_general_purpose": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _u64, _vp, _vp]),
     "bj_ntt_natural_to_bitreversed_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
     "bj_intt_natural_to_natural_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
+    "bj_transcript_new": (_vp, []),
+    "bj_transcript_free": (None, [_vp]),
+    "bj_transcript_witness_field_elements": (None, [_vp, _vp, _sz]),
+    "bj_transcript_witness_merkle_tree_cap": (None, [_vp, _vp, _sz]),
+    "bj_transcript_get_challenge": (_u64, [_vp]),
+    "bj_transcript_get_index_bits": (_u64, [_vp, _u32, _u32]),
+    "bj_compute_fri_schedule": (_i32, [_u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "bj_do_fri": (_i32, [_vp, _vp, _vp, _vp, _u32, _vp, _u32, _u32, _u32, _pp]),
+    "bj_fri_oracles_free": (None, [_vp]),
+    "bj_fri_oracles_num_oracles": (_u32, [_vp]),
+    "bj_fri_oracles_num_monomials": (_u32, [_vp]),
+    "bj_fri_oracles_get_cap": (_i32, [_vp, _u32, _vp]),
+    "bj_fri_oracles_get_monomials": (_i32, [_vp, _vp, _vp]),
+    "bj_fri_oracles_get_challenges": (_i32, [_vp, _vp]),
+    "bj_fri_oracles_query": (_i32, [_vp, _u32, _u64, _vp, _vp, _vp]),
+    "bj_query_leaf_elements": (_i32, [_vp, _vp, _u32, _u32, _vp, _u32, _vp]),
+    "bj_merkle_paths": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _u32, _vp]),
     "bj_selftest_field": (_i32, [_vp, _u64, _u64, _vp]),
     "bj_host_gl_mul": (_u64, [_u64, _u64]),
     "bj_host_gl_add": (_u64, [_u64, _u64]),

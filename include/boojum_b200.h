@@ -46,7 +46,8 @@ typedef struct bj_ctx bj_ctx;
 BJ_API const char* bj_version(void);
 BJ_API const char* bj_status_string(int32_t status);
 /* stream: a cudaStream_t owned by the caller (e.g. torch.cuda.current_stream().cuda_stream); NULL is the CUDA
- * legacy default stream.  The library never creates streams of its own. */
+ * legacy default stream.  Kernels only ever run on this stream; the host-buffer entry points additionally use two
+ * private copy streams so that upload, transform and download of successive column chunks overlap. */
 BJ_API int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx);
 BJ_API int32_t bj_ctx_destroy(bj_ctx* ctx);
 BJ_API int32_t bj_ctx_set_stream(bj_ctx* ctx, void* stream);
@@ -184,6 +185,51 @@ BJ_API int32_t bj_ntt_natural_to_bitreversed_host(bj_ctx* ctx, uint64_t* h_data,
                                            uint64_t coset);
 BJ_API int32_t bj_intt_natural_to_natural_host(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint32_t n_cols,
                                         uint64_t coset);
+
+/* ---- host-side Fiat-Shamir (never on the GPU; must be replayed bit-exactly):
+ * GoldilocksPoisedon2Transcript = AlgebraicSpongeBasedTranscript<_, 8, 12, 4, Poseidon2, Overwrite>
+ * (src/cs/implementations/transcript.rs:62-129), BoolsBuffer::get_bits (:369-417), compute_fri_schedule
+ * (src/cs/implementations/prover.rs:2281-2372). */
+typedef struct bj_transcript bj_transcript;
+BJ_API bj_transcript* bj_transcript_new(void);
+BJ_API void bj_transcript_free(bj_transcript* t);
+BJ_API void bj_transcript_witness_field_elements(bj_transcript* t, const uint64_t* els, size_t n);
+BJ_API void bj_transcript_witness_merkle_tree_cap(bj_transcript* t, const uint64_t* cap_digests, size_t n_digests);
+BJ_API uint64_t bj_transcript_get_challenge(bj_transcript* t);
+/* num_bits query-index bits, LSB first, as one integer; each refill keeps the (64 - max_needed) low bits of a challenge */
+BJ_API uint64_t bj_transcript_get_index_bits(bj_transcript* t, uint32_t num_bits, uint32_t max_needed);
+/* schedule: caller array of >= 32 entries */
+BJ_API int32_t bj_compute_fri_schedule(uint32_t security_bits, uint32_t cap_size, uint32_t pow_bits, uint32_t rate_log_two,
+                                uint32_t initial_degree_log_two, uint32_t* new_pow_bits, uint32_t* num_queries,
+                                uint32_t* schedule, uint32_t* schedule_len, uint32_t* final_degree);
+
+/* ---- FRI commit phase: do_fri (src/cs/implementations/fri/mod.rs:49-357) ----
+ * d_c0 / d_c1: the DEEP codeword on the full LDE domain (2^log_full_size values each, LDE layout; borrowed - must stay
+ * alive as long as the returned oracles are queried).  schedule: interpolation_log2s_schedule (compute_fri_schedule).
+ * Builds the base oracle and every intermediate oracle (Poseidon2 trees with 2^k c0 values then 2^k c1 values per
+ * leaf), absorbs each cap into the transcript, draws the two challenge elements, folds, and finally bit-reverses +
+ * iNTTs the last vector into the monomial forms which are absorbed as well.  Returns BJ_ERR_INVALID_ARG if the folded
+ * codeword is not of low degree (the reference's self-check panics, fri/mod.rs:326-334). */
+typedef struct bj_fri_oracles bj_fri_oracles;
+BJ_API int32_t bj_do_fri(bj_ctx* ctx, bj_transcript* transcript, const uint64_t* d_c0, const uint64_t* d_c1,
+                  uint32_t log_full_size, const uint32_t* schedule, uint32_t n_schedule, uint32_t log_lde,
+                  uint32_t cap_size, bj_fri_oracles** out);
+BJ_API void bj_fri_oracles_free(bj_fri_oracles* o);
+BJ_API uint32_t bj_fri_oracles_num_oracles(const bj_fri_oracles* o);
+BJ_API uint32_t bj_fri_oracles_num_monomials(const bj_fri_oracles* o);
+BJ_API int32_t bj_fri_oracles_get_cap(const bj_fri_oracles* o, uint32_t oracle_idx, uint64_t* h_out /* 4*cap u64 */);
+BJ_API int32_t bj_fri_oracles_get_monomials(const bj_fri_oracles* o, uint64_t* h_c0, uint64_t* h_c1);
+BJ_API int32_t bj_fri_oracles_get_challenges(const bj_fri_oracles* o, uint64_t* h_out /* 2 u64 per oracle */);
+/* OracleQuery::construct for one FRI oracle (src/cs/implementations/proof.rs:65-97): leaf elements (2 * 2^k u64:
+ * c0 values then c1 values) and the sibling path (path_len digests, bottom-up, cap level excluded). */
+BJ_API int32_t bj_fri_oracles_query(bj_fri_oracles* o, uint32_t oracle_idx, uint64_t leaf_index, uint64_t* h_leaf_elements,
+                             uint64_t* h_path, uint32_t* path_len);
+/* Query helpers for the base oracles (witness / stage 2 / quotient / setup): gather the leaf preimages of n_indices
+ * leaves (h_out[q][s * elems_per_leaf + e]) and their Merkle paths (h_out[q][depth][4]); both synchronise. */
+BJ_API int32_t bj_query_leaf_elements(bj_ctx* ctx, const uint64_t* const* h_sources, uint32_t n_sources, uint32_t elems_per_leaf,
+                               const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out);
+BJ_API int32_t bj_merkle_paths(bj_ctx* ctx, const uint64_t* d_leaf_hashes, const uint64_t* d_nodes, uint64_t n_leaves,
+                        uint32_t cap_size, const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out);
 
 /* device self-test: PTX field arithmetic vs the portable C versions on n pseudo-random + edge inputs */
 BJ_API int32_t bj_selftest_field(bj_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* h_mismatches);

@@ -369,3 +369,91 @@ def replay_proof(fixture, num_variable_polys=None):
                                   alpha=alpha, z=z, deep=c, fri=fri_challenges)
     counters["schedule"] = schedule
     return counters
+
+
+# ------------------------------------------------------------------ prover-side FRI commit phase (oracle) ----------
+def do_fri_oracle(c0, c1, transcript, schedule, log_lde, cap_size):
+    """do_fri restated on the oracle primitives (src/cs/implementations/fri/mod.rs:49-357).
+    c0, c1: flat LDE codeword (numpy uint64).  Returns dict(caps, challenges, levels=[(c0,c1)], monomials=(m0,m1))."""
+    log_full = len(c0).bit_length() - 1
+    roots = O.twiddles(log_full, inverse=True)
+    kappa = O.inv(7)
+    caps, chals, levels, trees = [], [], [], []
+    cur0, cur1 = np.array(c0, dtype=np.uint64), np.array(c1, dtype=np.uint64)
+    for k in schedule:
+        levels.append((cur0, cur1))
+        lh, lv, cap = O.merkle_tree([cur0, cur1], cap_size, elems_per_leaf=1 << k)
+        trees.append((lh, lv))
+        caps.append(cap)
+        transcript.witness_merkle_tree_cap(cap.tolist())
+        a = transcript.get_ext_challenge()
+        chals.append(a)
+        for _ in range(k):
+            cur0, cur1 = O.fri_fold(cur0, cur1, a, roots[: len(cur0) // 2], kappa)
+            a = O.ext_mul(a, a)
+            kappa = O.mul(kappa, kappa)
+    coset = O.inv(kappa)
+    m0 = O.intt_n2n(O.bitreverse(cur0), coset)
+    m1 = O.intt_n2n(O.bitreverse(cur1), coset)
+    final_degree = len(cur0) >> log_lde
+    assert not m0[final_degree:].any() and not m1[final_degree:].any(), "not low degree"
+    transcript.witness_field_elements(m0[:final_degree].tolist())
+    transcript.witness_field_elements(m1[:final_degree].tolist())
+    return dict(caps=caps, challenges=chals, levels=levels, trees=trees, monomials=(m0[:final_degree], m1[:final_degree]))
+
+
+def verify_fri_query(idx, log_n, log_lde, schedule, cap_size, caps, fri_challenges, monomials, queries, start_value=None):
+    """Verifier-side FRI chain for one base-tree index (src/cs/implementations/verifier.rs:2386-2510).
+    queries: per oracle (leaf_elements, path).  Returns the value expected in the first leaf if start_value is None."""
+    max_bits = log_n + log_lde
+    bits = [(idx >> i) & 1 for i in range(max_bits)]
+    powers = [omega(i) for i in range(max_bits + 1)]
+    powers_inv = [finv(x) for x in powers]
+    steps = [1, powers_inv[2], powers_inv[3], fmul(powers_inv[2], powers_inv[3])]
+    x = 1
+    for b, pw in zip(bits, powers[1:]):
+        if b:
+            x = fmul(x, pw)
+    power_chunks, skip = [], 0
+    for k in schedule:
+        d = 1
+        for b, pw in list(zip(bits[skip:], powers_inv[1:]))[k:]:
+            if b:
+                d = fmul(d, pw)
+        skip += k
+        power_chunks.append(d)
+    x_interp = fmul(x, 7)
+    cur, subidx, coset_inv = start_value, idx, finv(7)
+    depth = max_bits - (cap_size.bit_length() - 1)
+    for lvl, (k, (le, path)) in enumerate(zip(schedule, queries)):
+        depth -= k
+        deg = 1 << k
+        sub_in_leaf, tree_idx = subidx % deg, subidx >> k
+        le = [int(v) for v in le]
+        if cur is not None:
+            assert (le[sub_in_leaf], le[deg + sub_in_leaf]) == cur, ("fold chain broken at level", lvl)
+        leaf = O.poseidon2_hash_leaf(np.array(le, dtype=np.uint64))
+        path = np.array(path, dtype=np.uint64).reshape(-1, 4)
+        assert path.shape[0] == depth
+        assert O.merkle_verify(leaf, path, np.array(caps[lvl], dtype=np.uint64), tree_idx), ("path", lvl)
+        els = [(le[i], le[deg + i]) for i in range(deg)]
+        base_pow = power_chunks[lvl]
+        a = fri_challenges[lvl]
+        for _ in range(k):
+            nxt = []
+            for i in range(0, len(els), 2):
+                u, v = els[i], els[i + 1]
+                pw = fmul(fmul(base_pow, steps[i // 2]), coset_inv)
+                nxt.append(e_add(e_add(u, v), e_mul_base(e_mul(e_sub(u, v), a), pw)))
+            els = nxt
+            a = e_mul(a, a)
+            base_pow = fmul(base_pow, base_pow)
+            coset_inv = fmul(coset_inv, coset_inv)
+        for _ in range(k):
+            x_interp = fmul(x_interp, x_interp)
+        subidx, cur = tree_idx, els[0]
+    res = (0, 0)
+    for c0, c1 in reversed(list(zip(*monomials))):
+        res = e_add(e_mul_base(res, x_interp), (int(c0), int(c1)))
+    assert res == cur, "final monomial evaluation mismatch"
+    return True

@@ -499,3 +499,62 @@ def test_gate_evaluator_all_relations(bj, ctx):
         t1 = (-b) % P
         t7 = ((((2 * a) ** 2 % P) * pow(ww, P - 2, P) + 12345 - cc) % P) * t1 % P
         assert int(g0[t]) == (t7 * 3 + t1 * 7) % P and int(g1[t]) == (t7 * 5 + t1 * 11) % P
+
+
+# --------------------------------------------------------------------------------------- do_fri / queries -----
+@pytest.mark.parametrize("log_n,log_lde,cap,schedule", [(8, 3, 16, [3, 3, 1]), (10, 1, 4, [3, 3, 2]), (12, 3, 16, [3, 3, 3, 2])])
+def test_do_fri_matches_oracle_and_verifies(bj, ctx, log_n, log_lde, cap, schedule):
+    """Commit phase on the GPU (host transcript in C++) == the oracle's do_fri: caps, challenges, final monomials;
+    then queries answered by the library verify with the reference verifier's FRI chain (verifier.rs:2386-2510)."""
+    n, L = 1 << log_n, 1 << log_lde
+    r = rng(log_n * 7 + log_lde)
+    m = O.random_field(r, (2, n))                      # two monomial forms: the c0 / c1 parts of a degree < n Fp2 polynomial
+    lde = O.lde(m, log_lde, from_monomials=True)       # [2, L, n]
+    c0, c1 = lde[0].reshape(-1), lde[1].reshape(-1)
+    seed_els = [int(x) for x in O.random_field(r, 5)]
+    t_ref = replay.Poseidon2Transcript()
+    t_ref.witness_field_elements(seed_els)
+    want = replay.do_fri_oracle(c0, c1, t_ref, schedule, log_lde, cap)
+    t_gpu = bj.Transcript()
+    t_gpu.witness_field_elements(seed_els)
+    d0, d1 = bj.to_device(c0), bj.to_device(c1)
+    fo = ctx.do_fri(t_gpu, d0, d1, schedule, L, cap)
+    assert fo.num_oracles() == len(schedule)
+    for i in range(len(schedule)):
+        assert np.array_equal(fo.get_cap(i), want["caps"][i])
+    assert fo.challenges() == [tuple(int(x) for x in a) for a in want["challenges"]]
+    g0, g1 = fo.monomial_forms()
+    assert np.array_equal(g0, want["monomials"][0]) and np.array_equal(g1, want["monomials"][1])
+    # both transcripts are in the same state afterwards
+    assert t_gpu.get_challenge() == t_ref.get_challenge()
+    # queries
+    for idx in [0, 1, (n * L) // 3, n * L - 1]:
+        qs, sub = [], idx
+        for lvl, k in enumerate(schedule):
+            le, path = fo.query(lvl, sub >> k, k)
+            qs.append((le, path))
+            sub >>= k
+        assert replay.verify_fri_query(idx, log_n, log_lde, schedule, cap, [fo.get_cap(i) for i in range(len(schedule))],
+                                       fo.challenges(), (g0, g1), qs, start_value=(int(c0[idx]), int(c1[idx])))
+
+
+def test_do_fri_rejects_high_degree(bj, ctx):
+    r = rng(99)
+    c0, c1 = O.random_field(r, 1 << 9), O.random_field(r, 1 << 9)   # random codeword: not an LDE
+    with pytest.raises(bj.BoojumError):
+        ctx.do_fri(bj.Transcript(), bj.to_device(c0), bj.to_device(c1), [3, 2], 8, 4)
+
+
+def test_query_helpers_match_oracle(bj, ctx):
+    n, C, cap = 1 << 9, 13, 8
+    cols = [O.random_field(rng(c), n) for c in range(C)]
+    d_cols = [bj.to_device(c) for c in cols]
+    tree = ctx.merkle_tree_construct(d_cols, cap)
+    lh, levels, capd = O.merkle_tree(cols, cap)
+    idx = [0, 5, 77, n - 1]
+    rows = ctx.query_leaf_elements(d_cols, idx)
+    paths = ctx.merkle_paths(tree, idx)
+    for q, i in enumerate(idx):
+        assert np.array_equal(rows[q], np.array([c[i] for c in cols], dtype=np.uint64))
+        assert np.array_equal(paths[q], O.merkle_path(lh, levels, i))
+        assert O.merkle_verify(O.poseidon2_hash_leaf(rows[q]), paths[q], capd, i)

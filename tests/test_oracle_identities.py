@@ -152,3 +152,29 @@ def test_merkle_tree_and_paths():
     c0, c1 = O.random_field(r, 64), O.random_field(r, 64)
     lh2 = O.merkle_leaf_hashes([c0, c1], elems_per_leaf=8)
     assert np.array_equal(lh2[3], O.poseidon2_hash_leaf(np.concatenate([c0[24:32], c1[24:32]])))
+
+
+def test_oracle_do_fri_commit_then_verify():
+    """oracle do_fri (prover side) is accepted by the verifier-side chain that the golden fixture pins."""
+    from oracle import replay
+    r = rng(21)
+    log_n, log_lde, cap, schedule = 8, 3, 16, [3, 3, 1]
+    n = 1 << log_n
+    m = O.random_field(r, (2, n))
+    lde = O.lde(m, log_lde, from_monomials=True)
+    c0, c1 = lde[0].reshape(-1), lde[1].reshape(-1)
+    t = replay.Poseidon2Transcript()
+    t.witness_field_elements([1, 2, 3])
+    w = replay.do_fri_oracle(c0, c1, t, schedule, log_lde, cap)
+    assert len(w["monomials"][0]) == n >> sum(schedule)
+    for idx in (0, 5, 1000, n * 8 - 1):
+        qs, sub = [], idx
+        for lvl, k in enumerate(schedule):
+            l0, l1 = w["levels"][lvl]
+            lh, lv = w["trees"][lvl]
+            ti = sub >> k
+            le = np.concatenate([l0[ti << k:(ti + 1) << k], l1[ti << k:(ti + 1) << k]])
+            qs.append((le, O.merkle_path(lh, lv, ti)))
+            sub >>= k
+        assert replay.verify_fri_query(idx, log_n, log_lde, schedule, cap, w["caps"], w["challenges"], w["monomials"], qs,
+                                       (int(c0[idx]), int(c1[idx])))
