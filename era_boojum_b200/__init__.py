@@ -277,6 +277,32 @@ class Context:
                                                self._ptr(acc_c0), self._ptr(acc_c1)))
         return acc_c0, acc_c1
 
+    # ---- stage 2 ----
+    @staticmethod
+    def non_residues_for_copy_permutation(domain_size, num_columns):
+        out = np.zeros(num_columns, np.uint64)
+        assert lib.bj_non_residues_for_copy_permutation(domain_size, num_columns, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        return out
+
+    def compute_partial_products_in_extension(self, variables, sigmas, beta, gamma, max_degree):
+        """copy_permutation.rs:649-766.  variables / sigmas: lists of [n] CUDA tensors (natural order).
+        Returns (z_c0, z_c1, partials[(c0, c1), ...])."""
+        torch = self._torch
+        n_cols, n = len(variables), variables[0].numel()
+        n_chunks = (n_cols + max_degree - 1) // max_degree
+        nr = self.non_residues_for_copy_permutation(n, n_cols)
+        pv = (ctypes.c_void_p * n_cols)(*[v.data_ptr() for v in variables])
+        ps = (ctypes.c_void_p * n_cols)(*[v.data_ptr() for v in sigmas])
+        dev = variables[0].device
+        z0 = torch.empty(n, dtype=torch.int64, device=dev)
+        z1 = torch.empty(n, dtype=torch.int64, device=dev)
+        partials = torch.empty((max(n_chunks - 1, 1), 2, n), dtype=torch.int64, device=dev)
+        b = (ctypes.c_uint64 * 2)(int(beta[0]), int(beta[1]))
+        g = (ctypes.c_uint64 * 2)(int(gamma[0]), int(gamma[1]))
+        self._check(lib.bj_copy_permutation_stage2(self._h, pv, ps, n_cols, nr.ctypes.data_as(ctypes.c_void_p), b, g,
+                                                   n.bit_length() - 1, max_degree, self._ptr(z0), self._ptr(z1), self._ptr(partials)))
+        return z0, z1, [(partials[c, 0], partials[c, 1]) for c in range(n_chunks - 1)]
+
     # ---- gate / quotient evaluator ----
     def evaluate_gates_over_general_purpose_columns(self, gates, variables, witnesses, constants, alpha_powers, q_c0, q_c1):
         """Row loop of prove_cpu_basic over general-purpose columns (cs/implementations/prover.rs:1031-1080).

@@ -313,6 +313,8 @@ static int32_t get_pow_tables(bj_ctx* ctx, u64 c, int log_n, u64 scale, PowTab* 
   return BJ_OK;
 }
 
+int32_t get_pow_tables_public(bj_ctx* ctx, u64 c, int log_n, u64 scale, PowTab* out) { return get_pow_tables(ctx, c, log_n, scale, out); }
+
 struct Plan {
   int n_pass;
   int t[4];

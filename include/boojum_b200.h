@@ -134,6 +134,20 @@ BJ_API int32_t bj_deep_quotient_group(bj_ctx* ctx, const uint64_t* const* h_src_
                                uint32_t n_src, const uint64_t* h_values_at, const uint64_t* h_challenges,
                                const uint64_t h_at[2], uint32_t log_rows, uint64_t* d_acc_c0, uint64_t* d_acc_c1);
 
+/* ---- stage 2, copy-permutation argument: compute_partial_products_in_extension
+ *      (src/cs/implementations/copy_permutation.rs:649-766; rational :114-248, grand product :425-510) ----
+ * Inputs are Lagrange columns on the trace domain in natural row order (n = 2^log_n values each): the copy-permutation
+ * (variable) columns and their sigma columns; non-residues k_j from bj_non_residues_for_copy_permutation.
+ * chunk_size = quotient degree (columns multiplied per partial product).
+ * Outputs: z (c0, c1) = exclusive prefix product of prod_j (w_j + beta k_j x + gamma)/(w_j + beta sigma_j + gamma), and the
+ * ceil(n_cols/chunk_size) - 1 partial products, laid out [partial][c0|c1][n] in d_partials.
+ * Returns BJ_ERR_INVALID_ARG if the grand product over the domain is not 1 (the reference asserts, :479). Synchronises. */
+BJ_API int32_t bj_non_residues_for_copy_permutation(uint64_t domain_size, uint32_t num_columns, uint64_t* h_out);
+BJ_API int32_t bj_copy_permutation_stage2(bj_ctx* ctx, const uint64_t* const* h_variable_cols, const uint64_t* const* h_sigma_cols,
+                                   uint32_t n_cols, const uint64_t* h_non_residues, const uint64_t h_beta[2],
+                                   const uint64_t h_gamma[2], uint32_t log_n, uint32_t chunk_size, uint64_t* d_z_c0,
+                                   uint64_t* d_z_c1, uint64_t* d_partials);
+
 /* ---- gate / quotient evaluator over general-purpose columns: the row loop of prove_cpu_basic
  *      (src/cs/implementations/prover.rs:1031-1080) with GateConstraintEvaluator::evaluate_once (src/cs/traits/evaluator.rs:145-152)
  *      supplied as DATA: the SSA program recorded by the reference's own GPU hook, gpu_synthesizer::GPUDataCapture

@@ -558,3 +558,72 @@ def test_query_helpers_match_oracle(bj, ctx):
         assert np.array_equal(rows[q], np.array([c[i] for c in cols], dtype=np.uint64))
         assert np.array_equal(paths[q], O.merkle_path(lh, levels, i))
         assert O.merkle_verify(O.poseidon2_hash_leaf(rows[q]), paths[q], capd, i)
+
+
+# ------------------------------------------------------------------------------------ stage 2 (copy permutation) -----
+def _satisfying_copy_permutation(r, n_cols, log_n):
+    """variable columns with repeated values and sigma columns encoding the cycles of equal cells
+    (sigma_j[i] = k_j' * omega^i' of the next cell in the cycle; identity for untouched cells)."""
+    from oracle import stage2 as S
+    n = 1 << log_n
+    ks = S.non_residues_for_copy_permutation(n, n_cols)
+    w_n = replay.omega(log_n)
+    vals = [[int(x) for x in O.random_field(r, n)] for _ in range(n_cols)]
+    sig = [[ks[j] * pow(w_n, i, P) % P for i in range(n)] for j in range(n_cols)]
+    cells = [(j, i) for j in range(n_cols) for i in range(n)]
+    perm = r.permutation(len(cells))
+    for g in range(0, len(cells) - 2, 3):           # cycles of three cells sharing one value
+        cyc = [cells[perm[g + t]] for t in range(3)]
+        v = vals[cyc[0][0]][cyc[0][1]]
+        for (j, i), (j2, i2) in zip(cyc, cyc[1:] + cyc[:1]):
+            vals[j][i] = v
+            sig[j][i] = ks[j2] * pow(w_n, i2, P) % P
+    return vals, sig
+
+
+@pytest.mark.parametrize("n_cols,log_n,deg", [(3, 4, 4), (9, 5, 4), (7, 6, 2), (5, 12, 2)])
+def test_copy_permutation_stage2_matches_oracle(bj, ctx, n_cols, log_n, deg):
+    from oracle import stage2 as S
+    r = rng(n_cols * 10 + log_n)
+    vals, sig = _satisfying_copy_permutation(r, n_cols, log_n)
+    beta = tuple(int(x) for x in O.random_field(r, 2))
+    gamma = tuple(int(x) for x in O.random_field(r, 2))
+    d_v = [bj.to_device(np.array(c, dtype=np.uint64)) for c in vals]
+    d_s = [bj.to_device(np.array(c, dtype=np.uint64)) for c in sig]
+    z0, z1, partials = ctx.compute_partial_products_in_extension(d_v, d_s, beta, gamma, deg)
+    g0, g1 = bj.to_numpy(z0), bj.to_numpy(z1)
+    if log_n <= 6:
+        wz, wp = S.partial_products(vals, sig, beta, gamma, deg)
+        assert [(int(a), int(b)) for a, b in zip(g0, g1)] == wz
+        assert len(partials) == len(wp)
+        for (p0, p1), w in zip(partials, wp):
+            assert [(int(a), int(b)) for a, b in zip(bj.to_numpy(p0), bj.to_numpy(p1))] == w
+    else:
+        # large domain: z[0] = 1 and the defining recurrence z[i+1] = z[i] * prod_j num_j / den_j at sampled rows
+        assert (int(g0[0]), int(g1[0])) == (1, 0)
+        ks = S.non_residues_for_copy_permutation(1 << log_n, n_cols)
+        w_n = replay.omega(log_n)
+        for i in [0, 1, 77, 2047, (1 << log_n) - 2]:
+            x = pow(w_n, i, P)
+            num, den = (1, 0), (1, 0)
+            for j in range(n_cols):
+                w = vals[j][i]
+                num = replay.e_mul(num, replay.e_add(replay.e_add(replay.e_mul_base(beta, ks[j] * x % P), (w, 0)), gamma))
+                den = replay.e_mul(den, replay.e_add(replay.e_add(replay.e_mul_base(beta, sig[j][i]), (w, 0)), gamma))
+            lhs = replay.e_mul((int(g0[i + 1]), int(g1[i + 1])), den)
+            assert lhs == replay.e_mul((int(g0[i]), int(g1[i])), num)
+
+
+def test_copy_permutation_rejects_unsatisfied(bj, ctx):
+    r = rng(4)
+    vals, sig = _satisfying_copy_permutation(r, 3, 5)
+    vals[1][7] = (vals[1][7] + 1) % P   # break one copy constraint (cell is in a cycle with overwhelming probability)
+    broken = any(sig[1][7] != v for v in [0])
+    d_v = [bj.to_device(np.array(c, dtype=np.uint64)) for c in vals]
+    d_s = [bj.to_device(np.array(c, dtype=np.uint64)) for c in sig]
+    from oracle import stage2 as S
+    ks = S.non_residues_for_copy_permutation(32, 3)
+    if sig[1][7] == ks[1] * pow(replay.omega(5), 7, P) % P:
+        pytest.skip("cell happened to be untouched")
+    with pytest.raises(bj.BoojumError):
+        ctx.compute_partial_products_in_extension(d_v, d_s, (3, 4), (5, 6), 2)
