@@ -303,6 +303,35 @@ class Context:
                                                    n.bit_length() - 1, max_degree, self._ptr(z0), self._ptr(z1), self._ptr(partials)))
         return z0, z1, [(partials[c, 0], partials[c, 1]) for c in range(n_chunks - 1)]
 
+    def quotient_copy_permutation(self, var_ldes, sigma_ldes, z, partials, beta, gamma, alphas, log_n, log_lde, log_q, chunk,
+                                  q_c0, q_c1):
+        """copy-permutation relations + z(1)=1 term on the first 2^log_q cosets (copy_permutation.rs:1000-1249,
+        prover.rs:1189-1227).  *_ldes: flat [L*n] CUDA tensors; partials: list of (c0, c1); alphas: n_chunks+1 Fp2."""
+        n_cols = len(var_ldes)
+        pv = (ctypes.c_void_p * n_cols)(*[v.data_ptr() for v in var_ldes])
+        ps = (ctypes.c_void_p * n_cols)(*[v.data_ptr() for v in sigma_ldes])
+        flat = [t for pr in partials for t in pr]
+        pp = (ctypes.c_void_p * max(1, len(flat)))(*[t.data_ptr() for t in flat])
+        nr = self.non_residues_for_copy_permutation(1 << log_n, n_cols)
+        b = (ctypes.c_uint64 * 2)(int(beta[0]), int(beta[1]))
+        g = (ctypes.c_uint64 * 2)(int(gamma[0]), int(gamma[1]))
+        al = (ctypes.c_uint64 * (2 * len(alphas)))(*[int(x) for a in alphas for x in a])
+        self._check(lib.bj_quotient_copy_permutation(self._h, pv, ps, n_cols, nr.ctypes.data_as(ctypes.c_void_p),
+                                                     self._ptr(z[0]), self._ptr(z[1]), pp, b, g, al, log_n, log_lde, log_q, chunk,
+                                                     self._ptr(q_c0), self._ptr(q_c1)))
+
+    def divide_by_vanishing(self, q_c0, q_c1, log_n, log_q):
+        self._check(lib.bj_quotient_divide_by_vanishing(self._h, self._ptr(q_c0), self._ptr(q_c1), log_n, log_q))
+
+    def barycentric_evaluate(self, cols, log_n, at):
+        """values of base-field polynomials at an Fp2 point from coset 0 of their LDE -> list of (c0, c1)."""
+        n_cols = len(cols)
+        pc = (ctypes.c_void_p * n_cols)(*[c.data_ptr() for c in cols])
+        a = (ctypes.c_uint64 * 2)(int(at[0]), int(at[1]))
+        out = np.zeros((n_cols, 2), np.uint64)
+        self._check(lib.bj_barycentric_evaluate(self._h, pc, n_cols, log_n, a, out.ctypes.data_as(ctypes.c_void_p)))
+        return [(int(r[0]), int(r[1])) for r in out]
+
     # ---- gate / quotient evaluator ----
     def evaluate_gates_over_general_purpose_columns(self, gates, variables, witnesses, constants, alpha_powers, q_c0, q_c1):
         """Row loop of prove_cpu_basic over general-purpose columns (cs/implementations/prover.rs:1031-1080).

@@ -193,6 +193,27 @@ BJ_API int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_desc
                                           const uint64_t* h_alpha_powers, uint32_t n_alpha_powers,
                                           uint64_t n_points, uint64_t* d_q_c0, uint64_t* d_q_c1);
 
+/* ---- quotient: copy-permutation relations + the z(1) = 1 term (src/cs/implementations/copy_permutation.rs:1000-1249,
+ *      src/cs/implementations/prover.rs:1189-1227) over the first 2^log_quotient_degree cosets of the LDE ----
+ * All polynomial arguments are LDE columns (flat [L][n], 2^log_lde cosets).  h_partial_ldes: 2*(n_chunks-1) device
+ * pointers (c0, c1 per partial product).  h_alphas: (n_chunks + 1) Fp2 challenge powers: the z(1)=1 term first, then one
+ * per copy-permutation relation (order of prover.rs:1176-1250).  Accumulates into q. */
+BJ_API int32_t bj_quotient_copy_permutation(bj_ctx* ctx, const uint64_t* const* h_variable_ldes, const uint64_t* const* h_sigma_ldes,
+                                     uint32_t n_cols, const uint64_t* h_non_residues, const uint64_t* d_z_c0,
+                                     const uint64_t* d_z_c1, const uint64_t* const* h_partial_ldes, const uint64_t h_beta[2],
+                                     const uint64_t h_gamma[2], const uint64_t* h_alphas, uint32_t log_n, uint32_t log_lde,
+                                     uint32_t log_quotient_degree, uint32_t chunk_size, uint64_t* d_q_c0, uint64_t* d_q_c1);
+/* divide_by_vanishing_for_bitreversed_coset_enumeration (src/cs/implementations/utils.rs:770-817): q[coset j] *= 1/((7 w^bitrev(j))^n - 1) */
+BJ_API int32_t bj_quotient_divide_by_vanishing(bj_ctx* ctx, uint64_t* d_q_c0, uint64_t* d_q_c1, uint32_t log_n,
+                                        uint32_t log_quotient_degree);
+
+/* ---- openings: values of n_cols base-field polynomials at the Fp2 point `at`, from their first LDE coset
+ *      (barycentric evaluation, src/cs/implementations/utils.rs:907-1243; prover.rs:1519-1802).
+ * h_cols: host array of device pointers to LDE columns (only the first 2^log_n values, coset 0, are read).
+ * h_out: n_cols (c0, c1) pairs.  `at` must not lie on the coset 7<w_n>.  Synchronises. */
+BJ_API int32_t bj_barycentric_evaluate(bj_ctx* ctx, const uint64_t* const* h_cols, uint32_t n_cols, uint32_t log_n,
+                                const uint64_t h_at[2], uint64_t* h_out);
+
 /* ---- host-buffer convenience entry points (what the Rust shim calls when columns live in host Vecs).
  * They upload, run, download and synchronise; used for the end-to-end measurement. */
 BJ_API int32_t bj_ntt_natural_to_bitreversed_host(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint32_t n_cols,

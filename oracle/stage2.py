@@ -54,3 +54,51 @@ def partial_products(variables, sigmas, beta, gamma, max_degree):
         prev = [e_mul(p, q) for p, q in zip(prev, r)]
         partials.append(prev)
     return z, partials
+
+
+def horner_ext(monomials, at):
+    """f(at) for base-field coefficients (low degree first) at an Fp2 point."""
+    acc = (0, 0)
+    for c in reversed([int(x) for x in monomials]):
+        acc = e_add(e_mul(acc, at), (c % P, 0))
+    return acc
+
+
+def lde_point(log_n, log_lde, t):
+    """x(t) = 7 * w_{nL}^{bitrev_{nL}(t)} for the flat LDE index t."""
+    bits = log_n + log_lde
+    r = int(format(t, "0%db" % bits)[::-1], 2) if bits else 0
+    return 7 * pow(omega(bits), r, P) % P
+
+
+def quotient_copy_permutation_point(t, log_n, log_lde, var_ldes, sigma_ldes, z, partials, beta, gamma, alphas, chunk):
+    """z(1)=1 term + copy-permutation relations at flat LDE index t (prover.rs:1189-1227, copy_permutation.rs:1000-1249).
+    var_ldes / sigma_ldes: flat LDE columns; z, partials: (c0, c1) flat LDE columns."""
+    n = 1 << log_n
+    n_cols = len(var_ldes)
+    ks = non_residues_for_copy_permutation(n, n_cols)
+    x = lde_point(log_n, log_lde, t)
+    coset, i = t >> log_n, t & (n - 1)
+    br = lambda v: int(format(v, "0%db" % log_n)[::-1], 2) if log_n else 0
+    tsh = (coset << log_n) | br((br(i) + 1) % n)
+    zt = (int(z[0][t]), int(z[1][t]))
+    l1 = (pow(x, n, P) - 1) * pow(x - 1, P - 2, P) % P
+    q = e_mul(e_mul_base(((zt[0] - 1) % P, zt[1]), l1), alphas[0])
+    chunks = [range(s, min(s + chunk, n_cols)) for s in range(0, n_cols, chunk)]
+    for c, ch in enumerate(chunks):
+        lhs = (int(partials[c][0][t]), int(partials[c][1][t])) if c + 1 < len(chunks) else (int(z[0][tsh]), int(z[1][tsh]))
+        rhs = zt if c == 0 else (int(partials[c - 1][0][t]), int(partials[c - 1][1][t]))
+        for j in ch:
+            w = int(var_ldes[j][t])
+            lhs = e_mul(lhs, e_add(e_add(e_mul_base(beta, int(sigma_ldes[j][t])), (w, 0)), gamma))
+            rhs = e_mul(rhs, e_add(e_add(e_mul_base(beta, ks[j] * x % P), (w, 0)), gamma))
+        d = ((lhs[0] - rhs[0]) % P, (lhs[1] - rhs[1]) % P)
+        q = e_add(q, e_mul(d, alphas[c + 1]))
+    return q
+
+
+def vanishing_inverse(log_n, log_q, coset):
+    n = 1 << log_n
+    r = int(format(coset, "0%db" % log_q)[::-1], 2) if log_q else 0
+    shift = 7 * pow(omega(log_n + log_q), r, P) % P
+    return pow((pow(shift, n, P) - 1) % P, P - 2, P)

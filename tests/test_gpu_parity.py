@@ -627,3 +627,64 @@ def test_copy_permutation_rejects_unsatisfied(bj, ctx):
         pytest.skip("cell happened to be untouched")
     with pytest.raises(bj.BoojumError):
         ctx.compute_partial_products_in_extension(d_v, d_s, (3, 4), (5, 6), 2)
+
+
+# ----------------------------------------------------------------------------- openings / quotient pieces -----
+@pytest.mark.parametrize("log_n,n_cols", [(3, 2), (8, 11), (13, 20)])
+def test_barycentric_evaluate_matches_horner(bj, ctx, log_n, n_cols):
+    from oracle import stage2 as S
+    r = rng(log_n + n_cols)
+    vals = O.random_field(r, (n_cols, 1 << log_n))
+    mono = O.intt_n2n(vals)
+    lde = ctx.transform_raw_storages_to_lde(bj.to_device(vals), 2)
+    cols = [lde[c].reshape(-1) for c in range(n_cols)]
+    for at in (tuple(int(x) for x in O.random_field(r, 2)), (0, 0), (int(O.omega(log_n + 1)), 0)):
+        got = ctx.barycentric_evaluate(cols, log_n, at)
+        for c in range(0, n_cols, max(1, n_cols // 5)):
+            assert got[c] == S.horner_ext(mono[c], at)
+
+
+def test_quotient_copy_permutation_and_vanishing_match_oracle(bj, ctx):
+    from oracle import stage2 as S
+    log_n, log_lde, log_q, n_cols, chunk = 5, 3, 2, 5, 2
+    r = rng(55)
+    vals, sig = _satisfying_copy_permutation(r, n_cols, log_n)
+    beta = tuple(int(x) for x in O.random_field(r, 2))
+    gamma = tuple(int(x) for x in O.random_field(r, 2))
+    v_np = np.array(vals, dtype=np.uint64)
+    s_np = np.array(sig, dtype=np.uint64)
+    d_v, d_s = bj.to_device(v_np), bj.to_device(s_np)
+    z0, z1, partials = ctx.compute_partial_products_in_extension([d_v[c] for c in range(n_cols)], [d_s[c] for c in range(n_cols)],
+                                                                 beta, gamma, chunk)
+    L = 1 << log_lde
+    lde_v = ctx.transform_raw_storages_to_lde(d_v, L)
+    lde_s = ctx.transform_raw_storages_to_lde(d_s, L)
+    import torch
+    st2 = torch.stack([z0, z1] + [t for pr in partials for t in pr])
+    lde_2 = ctx.transform_raw_storages_to_lde(st2.contiguous(), L)
+    flat = lambda t: t.reshape(-1)
+    n_chunks = (n_cols + chunk - 1) // chunk
+    alphas = [tuple(int(x) for x in O.random_field(r, 2)) for _ in range(n_chunks + 1)]
+    npts = 1 << (log_n + log_q)
+    q0 = torch.zeros(npts, dtype=torch.int64, device="cuda:0")
+    q1 = torch.zeros(npts, dtype=torch.int64, device="cuda:0")
+    part_ldes = [(flat(lde_2[2 + 2 * c]), flat(lde_2[3 + 2 * c])) for c in range(n_chunks - 1)]
+    ctx.quotient_copy_permutation([flat(lde_v[c]) for c in range(n_cols)], [flat(lde_s[c]) for c in range(n_cols)],
+                                  (flat(lde_2[0]), flat(lde_2[1])), part_ldes, beta, gamma, alphas, log_n, log_lde, log_q, chunk,
+                                  q0, q1)
+    g0, g1 = bj.to_numpy(q0), bj.to_numpy(q1)
+    hv, hs, h2 = bj.to_numpy(lde_v).reshape(n_cols, -1), bj.to_numpy(lde_s).reshape(n_cols, -1), bj.to_numpy(lde_2).reshape(2 * n_chunks, -1)
+    hz = (h2[0], h2[1])
+    hp = [(h2[2 + 2 * c], h2[3 + 2 * c]) for c in range(n_chunks - 1)]
+    for t in list(range(0, npts, 7)) + [npts - 1]:
+        want = S.quotient_copy_permutation_point(t, log_n, log_lde, hv, hs, hz, hp, beta, gamma, alphas, chunk)
+        assert (int(g0[t]), int(g1[t])) == want, t
+    ctx.divide_by_vanishing(q0, q1, log_n, log_q)
+    d0, d1 = bj.to_numpy(q0), bj.to_numpy(q1)
+    for t in (0, 33, 100, npts - 1):
+        vi = S.vanishing_inverse(log_n, log_q, t >> log_n)
+        assert int(d0[t]) == int(g0[t]) * vi % P and int(d1[t]) == int(g1[t]) * vi % P
+    # the quotient restricted to these terms is a polynomial of degree < n*Q: after un-bit-reversing and an iNTT on
+    # coset 7 of size n*Q the top quarter of the coefficients is not constrained, but the value must re-evaluate:
+    # cheap check instead: the relation terms vanish on the trace domain => division produced no poles; verified by
+    # re-multiplying and comparing with the undivided values above.
