@@ -1,0 +1,104 @@
+"""Synthetic SHA-256-bench-shaped circuit (workload generator for tests and bench.py; there is no Rust toolchain here
+to synthesise the real circuit).
+
+Geometry of the reference bench (src/gadgets/sha256/mod.rs:307-373): 60 general-purpose columns under copy permutation,
+gates ConstantsAllocator (4 repetitions), FmaGateInBaseFieldWithoutConstant (15) and ReductionGate<4> (12) selected per
+row through a binary selector tree in the first constant columns, quotient degree 4.  (The lookup argument of the real
+bench is not part of this synthetic circuit.)  Every row satisfies the gate its selector picks, and neighbouring
+repetitions of a row are tied by copy constraints (the output of repetition k-1 is an input of repetition k), so the
+sigma polynomials are a non-trivial permutation.  All values are kept small enough that plain 64-bit integer arithmetic
+is exact, so the trace can be generated with torch on the GPU without field multiplications; the identity permutation
+k_j * omega^i comes from the library's own NTT.
+"""
+import numpy as np
+
+from . import native
+
+N = native
+_V, _C, _T, _CS = N.IDX_VARIABLE, N.IDX_CONSTANT_POLY, N.IDX_TEMPORARY, N.IDX_CONSTANT_POLY_SHARED
+
+# GPUDataCapture-style programs (src/gpu_synthesizer/mod.rs:354-443) of the three evaluators
+FMA = dict(name="fma", relations=[(N.REL_MUL, 0, (_V, 2), (_CS, 1)), (N.REL_MUL, 1, (_V, 0), (_V, 1)), (N.REL_MUL, 2, (_CS, 0), (_T, 1)),
+                                  (N.REL_ADD, 3, (_T, 0), (_T, 2)), (N.REL_SUB, 4, (_T, 3), (_V, 3))],
+           writes=[(_T, 4)], variables_offset=4, constants_offset=0)
+REDUCTION4 = dict(name="reduction4",
+                  relations=[(N.REL_MUL, 0, (_V, 0), (_CS, 0)), (N.REL_MUL, 1, (_V, 1), (_CS, 1)), (N.REL_ADD, 2, (_T, 0), (_T, 1)),
+                             (N.REL_MUL, 3, (_V, 2), (_CS, 2)), (N.REL_ADD, 4, (_T, 2), (_T, 3)), (N.REL_MUL, 5, (_V, 3), (_CS, 3)),
+                             (N.REL_ADD, 6, (_T, 4), (_T, 5)), (N.REL_SUB, 7, (_T, 6), (_V, 4))],
+                  writes=[(_T, 7)], variables_offset=5, constants_offset=0)
+CONSTANT_ALLOCATOR = dict(name="constant_allocator", relations=[(N.REL_SUB, 0, (_V, 0), (_C, 0))], writes=[(_T, 0)],
+                          variables_offset=1, constants_offset=1)
+
+
+def sha_shaped_gates(num_variables=60):
+    """gate list in registration order with repetitions for `num_variables` columns and a 3-leaf selector tree."""
+    def g(base, reps, path):
+        d = dict(base)
+        d.update(num_repetitions=reps, constants_placement_offset=len(path), selector_path=path)
+        return d
+    return [g(CONSTANT_ALLOCATOR, min(4, num_variables), [True, True]), g(FMA, num_variables // 4, [True, False]),
+            g(REDUCTION4, num_variables // 5, [False])]
+
+
+def generate(ctx, log_n, num_variables=60, seed=0):
+    """Returns (variables [V, n], sigmas [V, n], constants [6, n], gates, quotient_degree) as int64 CUDA tensors."""
+    torch = ctx._torch
+    V, n, C = num_variables, 1 << log_n, 6
+    dev = "cuda:%d" % ctx.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    rnd = lambda shape, hi: torch.randint(0, hi, shape, dtype=torch.int64, device=dev, generator=gen)
+    gates = sha_shaped_gates(V)
+    n_fma, n_red = V // 4, V // 5
+    kind = rnd((n,), 3)                     # 0 = constant allocator, 1 = fma, 2 = reduction
+    is_ca, is_fma, is_red = kind == 0, kind == 1, kind == 2
+    variables = rnd((V, n), 1 << 20)
+    constants = torch.zeros((C, n), dtype=torch.int64, device=dev)
+    # selector tree: column 0 splits {reduction | others}, column 1 splits {fma | constant allocator}
+    constants[0] = (~is_red).to(torch.int64)
+    # ---- fma rows: d_k = c0 * a_k * b_k + c1 * c_k, c1 = 1, c_k = d_{k-1}
+    c0 = rnd((n,), 1 << 10) + 1
+    fma = rnd((V, n), 1 << 20)
+    for k in range(n_fma):
+        if k > 0:
+            fma[4 * k + 2] = fma[4 * k - 1]
+        fma[4 * k + 3] = c0 * fma[4 * k] * fma[4 * k + 1] + fma[4 * k + 2]
+    # ---- reduction rows: r_k = sum_i c_i * v_{k,i}, v_{k,0} = r_{k-1}
+    rc = rnd((4, n), 1 << 8)
+    red = rnd((V, n), 1 << 16)
+    for k in range(n_red):
+        if k > 0:
+            red[5 * k] = red[5 * k - 1]
+        red[5 * k + 4] = sum(rc[i] * red[5 * k + i] for i in range(4))
+    # ---- constant allocator rows: variable r = constant at column 2 + r
+    cc = rnd((4, n), 1 << 30)
+    variables = torch.where(is_fma[None, :], fma, variables)
+    variables = torch.where(is_red[None, :], red, variables)
+    n_ca = min(4, V)
+    variables[:n_ca] = torch.where(is_ca[None, :], cc[:n_ca], variables[:n_ca])
+    # constants per row type
+    constants[1] = torch.where(is_red, rc[0], is_ca.to(torch.int64))       # reduction: its 1st constant; else selector bit
+    constants[2] = torch.where(is_red, rc[1], torch.where(is_fma, c0, cc[0]))
+    constants[3] = torch.where(is_red, rc[2], torch.where(is_fma, torch.ones_like(c0), cc[1]))
+    constants[4] = torch.where(is_red, rc[3], torch.where(is_ca, cc[2], torch.zeros_like(c0)))
+    constants[5] = torch.where(is_ca, cc[3], torch.zeros_like(c0))
+    # ---- sigmas: identity k_j * omega^i from the library NTT of the polynomial k_j * X, then swap the tied cells
+    ks = ctx.non_residues_for_copy_permutation(n, V)
+    mono = torch.zeros((V, n), dtype=torch.int64, device=dev)
+    if n > 1:
+        mono[:, 1] = torch.from_numpy(ks.view(np.int64)).to(dev)
+    else:
+        mono[:, 0] = torch.from_numpy(ks.view(np.int64)).to(dev)
+    ctx.fft_natural_to_bitreversed(mono, 1)
+    ctx.bitreverse_enumeration_inplace(mono)
+    ident = mono
+    sigmas = ident.clone()
+    for k in range(1, n_fma):
+        a, b = 4 * k + 2, 4 * k - 1
+        sigmas[a] = torch.where(is_fma, ident[b], sigmas[a])
+        sigmas[b] = torch.where(is_fma, ident[a], sigmas[b])
+    for k in range(1, n_red):
+        a, b = 5 * k, 5 * k - 1
+        sigmas[a] = torch.where(is_red, ident[b], sigmas[a])
+        sigmas[b] = torch.where(is_red, ident[a], sigmas[b])
+    return variables.contiguous(), sigmas.contiguous(), constants.contiguous(), gates, 4

@@ -1,0 +1,179 @@
+"""ORACLE (test infrastructure): restatement of the reference verifier for circuits built from the bench's three gates
+over general-purpose columns, no lookups, no public inputs (the acceptance oracle of the prove -> verify tests).
+
+Follows Verifier::verify (src/cs/implementations/verifier.rs:888-2510):
+  transcript order :898-1068, alpha-power split :978-1023, quotient identity at z :1144-1828 (gates over general purpose
+  columns :1646-1700, z(1)=1 :1708-1722, copy-permutation relations :1724-1768, t_from_chunks :1772-1790),
+  DEEP regrouping + FRI chain :1817-2510 (shared with oracle/replay.py, which proof.json pins).
+Gate terms at z use the same formulas as oracle/gates.py, lifted to Fp2.
+"""
+import numpy as np
+
+from . import oracle as O
+from . import replay as R
+from .stage2 import non_residues_for_copy_permutation
+
+P = O.P
+
+
+def _ext(d):
+    return (d["coeffs"][0], d["coeffs"][1])
+
+
+def e_pow(a, e):
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = R.e_mul(r, a)
+        a = R.e_mul(a, a)
+        e >>= 1
+    return r
+
+
+# gate terms at an Fp2 point: v = opened variable values, c = opened constants (starting at the gate's placement)
+def _fma(v, c):
+    return [R.e_sub(R.e_add(R.e_mul(R.e_mul(c[0], v[0]), v[1]), R.e_mul(c[1], v[2])), v[3])]
+
+
+def _reduction4(v, c):
+    acc = (0, 0)
+    for i in range(4):
+        acc = R.e_add(acc, R.e_mul(c[i], v[i]))
+    return [R.e_sub(acc, v[4])]
+
+
+def _constant_allocator(v, c):
+    return [R.e_sub(v[0], c[0])]
+
+
+GATES = {"fma": (_fma, 4, (4, 0)), "reduction4": (_reduction4, 5, (5, 0)), "constant_allocator": (_constant_allocator, 1, (1, 1))}
+
+
+def verify(vk, proof):
+    """vk: dict(domain_size, num_variables, num_constants, quotient_degree, gates=[(name, reps, path)], fri_lde_factor,
+    cap_size, setup_merkle_tree_cap).  proof: dict in the reference's serde shape.  Returns True or raises AssertionError."""
+    n = vk["domain_size"]
+    log_n = n.bit_length() - 1
+    L = proof["proof_config"]["fri_lde_factor"]
+    log_L = L.bit_length() - 1
+    cap_size = proof["proof_config"]["merkle_tree_cap_size"]
+    assert L == vk["fri_lde_factor"] and cap_size == vk["cap_size"]
+    V, C, Q = vk["num_variables"], vk["num_constants"], vk["quotient_degree"]
+    gates = vk["gates"]
+    n_partial = 0 if V <= Q else (V + Q - 1) // Q - 1
+
+    tr = R.Poseidon2Transcript()
+    tr.witness_merkle_tree_cap(vk["setup_merkle_tree_cap"])
+    assert proof["public_inputs"] == []
+    tr.witness_merkle_tree_cap(proof["witness_oracle_cap"])
+    beta = tr.get_ext_challenge()
+    gamma = tr.get_ext_challenge()
+    tr.witness_merkle_tree_cap(proof["stage_2_oracle_cap"])
+    alpha = tr.get_ext_challenge()
+    n_gate_terms = sum(reps for _, reps, _ in gates)  # one term per repetition for the three bench gates
+    total_terms = n_gate_terms + 1 + 1 + n_partial
+    powers = [(1, 0)]
+    for _ in range(1, total_terms):
+        powers.append(R.e_mul(powers[-1], alpha))
+    gp_ch, rest_ch = powers[:n_gate_terms], powers[n_gate_terms:]
+    tr.witness_merkle_tree_cap(proof["quotient_oracle_cap"])
+    z = tr.get_ext_challenge()
+    vals_z = [_ext(v) for v in proof["values_at_z"]]
+    vals_zw = [_ext(v) for v in proof["values_at_z_omega"]]
+    assert proof["values_at_0"] == []
+    for v in vals_z + vals_zw:
+        tr.witness_field_elements(v)
+    assert len(vals_z) == V + C + V + 1 + n_partial + Q and len(vals_zw) == 1
+
+    # ---- quotient identity at z ----
+    it = iter(vals_z)
+    var_v = [next(it) for _ in range(V)]
+    const_v = [next(it) for _ in range(C)]
+    sigma_v = [next(it) for _ in range(V)]
+    z_at_z = next(it)
+    partial_v = [next(it) for _ in range(n_partial)]
+    quot_v = [next(it) for _ in range(Q)]
+    z_at_zw = vals_zw[0]
+    t_acc = (0, 0)
+    k = 0
+    for name, reps, path in gates:
+        fn, width, (voff, coff) = GATES[name]
+        sel = (1, 0)
+        for i, bit in enumerate(path):
+            sel = R.e_mul(sel, const_v[i] if bit else R.e_sub((1, 0), const_v[i]))
+        acc = (0, 0)
+        for rep in range(reps):
+            v = var_v[rep * voff: rep * voff + width]
+            c = const_v[len(path) + rep * coff:]
+            for term in fn(v, c):
+                acc = R.e_add(acc, R.e_mul(term, gp_ch[k]))
+                k += 1
+        t_acc = R.e_add(t_acc, R.e_mul(acc, sel))
+    assert k == n_gate_terms
+    z_n = e_pow(z, n)
+    vanishing = R.e_sub(z_n, (1, 0))
+    ch_it = iter(rest_ch)
+    l1 = R.e_mul(vanishing, R.e_inv(R.e_sub(z, (1, 0))))
+    t_acc = R.e_add(t_acc, R.e_mul(R.e_mul(R.e_sub(z_at_z, (1, 0)), l1), next(ch_it)))
+    ks = non_residues_for_copy_permutation(n, V)
+    lhs_l = partial_v + [z_at_zw]
+    rhs_l = [z_at_z] + partial_v
+    for c, (lhs, rhs) in enumerate(zip(lhs_l, rhs_l)):
+        a = next(ch_it)
+        for j in range(c * Q, min((c + 1) * Q, V)):
+            lhs = R.e_mul(lhs, R.e_add(R.e_add(R.e_mul(sigma_v[j], beta), var_v[j]), gamma))
+            rhs = R.e_mul(rhs, R.e_add(R.e_add(R.e_mul(R.e_mul_base(z, ks[j]), beta), var_v[j]), gamma))
+        t_acc = R.e_add(t_acc, R.e_mul(R.e_sub(lhs, rhs), a))
+    assert next(ch_it, None) is None
+    t_chunks, pw = (0, 0), (1, 0)
+    for q in quot_v:
+        t_chunks = R.e_add(t_chunks, R.e_mul(q, pw))
+        pw = R.e_mul(pw, z_n)
+    assert t_acc == R.e_mul(t_chunks, vanishing), "Invalid quotient at Z"
+
+    # ---- DEEP + FRI ----
+    c = tr.get_ext_challenge()
+    ch = R.ext_powers(c, len(vals_z) + len(vals_zw))
+    new_pow, num_queries, schedule, final_degree = R.compute_fri_schedule(
+        proof["proof_config"]["security_level"], cap_size, proof["proof_config"]["pow_bits"], log_L, log_n)
+    assert new_pow == 0 and num_queries == len(proof["queries_per_fri_repetition"])
+    fri_caps = [proof["fri_base_oracle_cap"]] + list(proof["fri_intermediate_oracles_caps"])
+    assert len(fri_caps) == len(schedule)
+    fri_ch = []
+    for cap in fri_caps:
+        tr.witness_merkle_tree_cap(cap)
+        fri_ch.append(tr.get_ext_challenge())
+    mono = proof["final_fri_monomials"]
+    assert len(mono[0]) == final_degree == len(mono[1])
+    tr.witness_field_elements(mono[0])
+    tr.witness_field_elements(mono[1])
+    max_bits = log_n + log_L
+    bools = R.BoolsBuffer(max_bits)
+    w_n = R.omega(log_n)
+    z_omega = R.e_mul_base(z, w_n)
+    depth = max_bits - (cap_size.bit_length() - 1)
+    for q in proof["queries_per_fri_repetition"]:
+        bits = bools.get_bits(tr, max_bits)
+        idx = sum(b << i for i, b in enumerate(bits))
+        for name, cap in (("witness_query", proof["witness_oracle_cap"]), ("stage_2_query", proof["stage_2_oracle_cap"]),
+                          ("quotient_query", proof["quotient_oracle_cap"]), ("setup_query", vk["setup_merkle_tree_cap"])):
+            leaf = O.poseidon2_hash_leaf(np.array(q[name]["leaf_elements"], dtype=np.uint64))
+            path = np.array(q[name]["proof"], dtype=np.uint64).reshape(-1, 4)
+            assert path.shape[0] == depth
+            assert O.merkle_verify(leaf, path, np.array(cap, dtype=np.uint64), idx), (name, idx)
+        wq, sq = q["witness_query"]["leaf_elements"], q["stage_2_query"]["leaf_elements"]
+        qq, uq = q["quotient_query"]["leaf_elements"], q["setup_query"]["leaf_elements"]
+        assert len(wq) == V and len(sq) == 2 * (1 + n_partial) and len(qq) == 2 * Q and len(uq) == V + C
+        base = lambda els: [(e, 0) for e in els]
+        ext = lambda els: [(els[i], els[i + 1]) for i in range(0, len(els), 2)]
+        src = base(wq) + base(uq[V:V + C]) + base(uq[:V]) + ext(sq[0:2]) + ext(sq[2:]) + ext(qq)
+        x = 1
+        for b, pw in zip(bits, [R.omega(i) for i in range(1, max_bits + 1)]):
+            if b:
+                x = R.fmul(x, pw)
+        x_q = R.fmul(x, 7)
+        acc = O.deep_point((0, 0), src, vals_z, ch[:len(src)], x_q, z)
+        acc = O.deep_point(acc, ext(sq[0:2]), vals_zw, ch[len(src):], x_q, z_omega)
+        fqs = [(fq["leaf_elements"], fq["proof"]) for fq in q["fri_queries"]]
+        R.verify_fri_query(idx, log_n, log_L, schedule, cap_size, fri_caps, fri_ch, (mono[0], mono[1]), fqs, start_value=acc)
+    return True

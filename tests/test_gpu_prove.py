@@ -1,0 +1,73 @@
+"""End to end on the GPU: synthetic SHA-bench-shaped circuit -> setup -> prove (every heavy step through the C-ABI) ->
+the oracle's restatement of the reference verifier accepts the proof; tampered proofs are rejected.  This is the
+prove-then-verify pattern of the reference's own integration tests (src/cs/implementations/cs.rs:1075-1203)."""
+import copy
+import json
+
+import numpy as np
+import pytest
+
+from oracle import verifier as OV
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    assert torch.cuda.is_available()
+    import era_boojum_b200 as bj
+    from era_boojum_b200 import prover, synthetic
+    ctx = bj.Context.on_current_stream(0)
+    yield bj, ctx, prover, synthetic
+    ctx.synchronize()
+    ctx.close()
+
+
+def _prove(env, log_n, V, lde=8, cap=16, seed=0):
+    bj, ctx, prover, synthetic = env
+    variables, sigmas, constants, gates, Q = synthetic.generate(ctx, log_n, V, seed)
+    cfg = prover.ProofConfig(fri_lde_factor=lde, merkle_tree_cap_size=cap, security_level=100)
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg)
+    proof = prover.prove(ctx, setup, variables)
+    return setup.vk(), proof
+
+
+@pytest.mark.parametrize("log_n,V,lde,cap", [(8, 20, 8, 16), (10, 60, 8, 16), (9, 60, 4, 8), (12, 60, 8, 16)])
+def test_prove_then_verify(env, log_n, V, lde, cap):
+    vk, proof = _prove(env, log_n, V, lde, cap, seed=log_n)
+    json.dumps(proof)  # serialisable in the reference's shape
+    assert OV.verify(vk, proof)
+    assert len(proof["queries_per_fri_repetition"]) == -(-100 // (lde.bit_length() - 1))
+
+
+def test_tampered_proofs_are_rejected(env):
+    vk, proof = _prove(env, 8, 20, seed=5)
+    assert OV.verify(vk, proof)
+    bad = copy.deepcopy(proof)
+    bad["values_at_z"][3]["coeffs"][0] ^= 1
+    with pytest.raises(AssertionError):
+        OV.verify(vk, bad)
+    bad = copy.deepcopy(proof)
+    bad["queries_per_fri_repetition"][0]["witness_query"]["leaf_elements"][0] ^= 1
+    with pytest.raises(AssertionError):
+        OV.verify(vk, bad)
+    bad = copy.deepcopy(proof)
+    bad["final_fri_monomials"][0][0] ^= 1
+    with pytest.raises(AssertionError):
+        OV.verify(vk, bad)
+    bad = copy.deepcopy(proof)
+    bad["quotient_oracle_cap"][0][0] ^= 1
+    with pytest.raises(AssertionError):
+        OV.verify(vk, bad)
+
+
+def test_unsatisfied_circuit_fails_in_prover(env):
+    """a trace that violates a gate cannot produce a low-degree quotient: do_fri's self-check (fri/mod.rs:326-334) fires."""
+    bj, ctx, prover, synthetic = env
+    variables, sigmas, constants, gates, Q = synthetic.generate(ctx, 8, 20, 3)
+    cfg = prover.ProofConfig()
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg)
+    variables[7, 13] += 1   # breaks a gate equation and (possibly) a copy constraint
+    with pytest.raises(bj.BoojumError):
+        prover.prove(ctx, setup, variables)
