@@ -149,6 +149,10 @@ def prove(ctx, setup, variables, timings=None):
     qq = torch.stack([q0, q1]).contiguous()
     ctx.bitreverse_enumeration_inplace(qq)
     ctx.ifft_natural_to_natural(qq, 7)
+    # the reference's satisfiability guard: the top coefficient of the interpolant must vanish (prover.rs:1425-1438)
+    top = to_numpy(qq[:, npts - 1])
+    if int(top[0]) != 0 or int(top[1]) != 0:
+        raise ValueError("unsatisfied: quotient is not a polynomial of degree < n * quotient_degree")
     chunks = torch.stack([qq[k][j * n:(j + 1) * n] for j in range(Q) for k in (0, 1)]).contiguous()   # c0,c1 of chunk 0, ...
     qt_lde = ctx.transform_raw_storages_to_lde(chunks, L, from_monomials=True)
     qt_cols = [flat(qt_lde[c]) for c in range(2 * Q)]

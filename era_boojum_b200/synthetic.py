@@ -65,6 +65,7 @@ def generate(ctx, log_n, num_variables=60, seed=0):
         fma[4 * k + 3] = c0 * fma[4 * k] * fma[4 * k + 1] + fma[4 * k + 2]
     # ---- reduction rows: r_k = sum_i c_i * v_{k,i}, v_{k,0} = r_{k-1}
     rc = rnd((4, n), 1 << 8)
+    rc[0] = 1                               # the chained input enters with coefficient 1 so values grow additively
     red = rnd((V, n), 1 << 16)
     for k in range(n_red):
         if k > 0:
