@@ -68,6 +68,6 @@ def test_unsatisfied_circuit_fails_in_prover(env):
     variables, sigmas, constants, gates, Q = synthetic.generate(ctx, 8, 20, 3)
     cfg = prover.ProofConfig()
     setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg)
-    variables[7, 13] += 1   # breaks a gate equation and (possibly) a copy constraint
+    variables[3, 13] += 1   # column 3 is constrained by every gate type (and tied by a copy constraint in fma rows)
     with pytest.raises((ValueError, bj.BoojumError)):
         prover.prove(ctx, setup, variables)
