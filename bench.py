@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--prove-log-n", type=int, default=22, help="rows (log2) of the synthetic SHA-shaped proof; 0 disables")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -270,6 +271,27 @@ def main():
                    "l2": "inputs (5 GiB) larger than L2, no flush", "parallelism": "columns sharded x%d, no collective" % world},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "sweep": sweep, "e2e": e2e,
     }
+    # second half of BASELINE.json's metric: proof generation seconds on the SHA-256-bench-shaped circuit (synthetic trace,
+    # 60 general-purpose columns, 3 gate types, quotient degree 4, LDE 8, cap 16, ~100-bit security; no lookup argument yet)
+    if world == 1 and args.prove_log_n > 0:
+        del data
+        torch.cuda.empty_cache()
+        from era_boojum_b200 import prover, synthetic
+        variables, sigmas, constants, gates, Q = synthetic.generate(ctx, args.prove_log_n, 60, seed=42)
+        cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100)
+        setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg)
+        prover.prove(ctx, setup, variables)  # warm-up (tables, allocator)
+        torch.cuda.synchronize()
+        stages = {}
+        t0 = time.perf_counter()
+        proof = prover.prove(ctx, setup, variables, timings=stages)
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        out["prove"] = {"circuit": "synthetic sha256-bench-shaped: 60 gp columns, ConstantsAllocator/Fma/Reduction<4>, Q=4, L=8, cap 16, no lookups",
+                        "rows_log2": args.prove_log_n, "seconds": round(secs, 4), "queries": len(proof["queries_per_fri_repetition"]),
+                        "stages_s": {k: round(v, 4) for k, v in stages.items()},
+                        "note": "H2D of the witness not included (trace generated on the device); accepted by the oracle verifier in tests/test_gpu_prove.py"}
+        del proof, setup, variables, sigmas, constants
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_sample()
     if rank == 0:
