@@ -271,10 +271,30 @@ def main():
                    "l2": "inputs (5 GiB) larger than L2, no flush", "parallelism": "columns sharded x%d, no collective" % world},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "sweep": sweep, "e2e": e2e,
     }
+    # BASELINE configs[2]: Poseidon2 Merkle tree over 2^22 leaves x 100 columns (cap 16), device-resident columns
+    if world == 1 and args.prove_log_n > 0:
+        del data
+        data = None
+        torch.cuda.empty_cache()
+        m_cols, m_log = 100, 22
+        srcs = [torch.randint(0, 2**63 - 1, (1 << m_log,), dtype=torch.int64, device=dev, generator=gen) for _ in range(m_cols)]
+        ctx.merkle_tree_construct(srcs, 16)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            tree = ctx.merkle_tree_construct(srcs, 16)
+        c1.record()
+        torch.cuda.synchronize()
+        m_ms = c0.elapsed_time(c1) / 3
+        perms = (1 << m_log) * ((m_cols + 7) // 8) + (1 << m_log) - 16
+        out["merkle"] = {"workload": "poseidon2 tree, 2^22 leaves x 100 columns, cap 16", "ms": round(m_ms, 3),
+                         "leaves_per_s": round((1 << m_log) / m_ms * 1e3), "gperms_per_s": round(perms / m_ms / 1e6, 4),
+                         "algo_gbs": round(((8 * m_cols + 32) * (1 << m_log) + 96 * ((1 << m_log) - 16)) / m_ms / 1e6, 1)}
+        del srcs, tree
     # second half of BASELINE.json's metric: proof generation seconds on the SHA-256-bench-shaped circuit (synthetic trace,
     # 60 general-purpose columns, 3 gate types, quotient degree 4, LDE 8, cap 16, ~100-bit security; no lookup argument yet)
     if world == 1 and args.prove_log_n > 0:
-        del data
         torch.cuda.empty_cache()
         from era_boojum_b200 import prover, synthetic
         variables, sigmas, constants, gates, Q = synthetic.generate(ctx, args.prove_log_n, 60, seed=42)

@@ -176,6 +176,107 @@ __host__ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
 }
 __host__ __device__ __forceinline__ u64 sqr(u64 a) { return mul(a, a); }
 
+
+// Product with a LAZY result (< 2^64, congruent, not canonical): mul() without the final canonicalising step.
+// Used where the consumer accepts lazy values (wide accumulators, further multiplications).
+__host__ __device__ __forceinline__ u64 mul_lazy(u64 a, u64 b) {
+#ifdef BJ_GL_PTX
+  u32 a0, a1, b0, b1, v0, v1;
+  unpack2(a, a0, a1);
+  unpack2(b, b0, b1);
+  asm("{\n\t"
+      ".reg .u64 p0, p1, p2, p3, z;\n\t"
+      ".reg .u32 r0, r1, r2, r3, x, y, w, c, bb;\n\t"
+      "mul.wide.u32 p0, %2, %4;\n\t"
+      "mov.b64 {r0, x}, p0;\n\t"
+      "cvt.u64.u32 z, x;\n\t"
+      "mad.wide.u32 p1, %2, %5, z;\n\t"
+      "mov.b64 {x, y}, p1;\n\t"
+      "cvt.u64.u32 z, x;\n\t"
+      "mad.wide.u32 p2, %3, %4, z;\n\t"
+      "mov.b64 {r1, w}, p2;\n\t"
+      "cvt.u64.u32 z, y;\n\t"
+      "mad.wide.u32 p3, %3, %5, z;\n\t"
+      "cvt.u64.u32 z, w;\n\t"
+      "add.u64 p3, p3, z;\n\t"
+      "mov.b64 {r2, r3}, p3;\n\t"
+      "mad.lo.cc.u32 %0, r2, 0xffffffff, r0;\n\t"
+      "madc.hi.cc.u32 %1, r2, 0xffffffff, r1;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "mad.lo.cc.u32 %0, c, 0xffffffff, %0;\n\t"
+      "madc.hi.u32 %1, c, 0xffffffff, %1;\n\t"
+      "sub.cc.u32 %0, %0, r3;\n\t"
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 bb, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, bb;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(v0), "=&r"(v1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return pack2(v0, v1);
+#else
+  return mul_c(a, b);
+#endif
+}
+
+// ---- 96-bit accumulator (u64 + u32 carry word) for sums of lazy values with small coefficients: additions are plain
+// integer carry chains, one reduction (2^64 = EPS) at the end.  Valid while the true sum stays below 2^96.
+struct w96 {
+  u64 lo;
+  u32 hi;
+};
+__host__ __device__ __forceinline__ w96 w96_from(u64 a) { return {a, 0u}; }
+__host__ __device__ __forceinline__ w96 w96_add(w96 a, w96 b) {
+#ifdef BJ_GL_PTX
+  w96 r;
+  asm("add.cc.u64 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=l"(r.lo), "=r"(r.hi) : "l"(a.lo), "r"(a.hi), "l"(b.lo), "r"(b.hi));
+  return r;
+#else
+  const u64 lo = a.lo + b.lo;
+  return {lo, a.hi + b.hi + (lo < a.lo ? 1u : 0u)};
+#endif
+}
+__host__ __device__ __forceinline__ w96 w96_add64(w96 a, u64 b) {
+#ifdef BJ_GL_PTX
+  w96 r;
+  asm("add.cc.u64 %0, %2, %4;\n\taddc.u32 %1, %3, 0;" : "=l"(r.lo), "=r"(r.hi) : "l"(a.lo), "r"(a.hi), "l"(b));
+  return r;
+#else
+  const u64 lo = a.lo + b;
+  return {lo, a.hi + (lo < a.lo ? 1u : 0u)};
+#endif
+}
+__host__ __device__ __forceinline__ w96 w96_shl(w96 a, unsigned s) {  // 0 < s < 32
+  return {a.lo << s, (a.hi << s) | (u32)(a.lo >> (64 - s))};
+}
+// a * 2^s as a 96-bit value, 0 <= s < 32
+__host__ __device__ __forceinline__ w96 w96_from_shl(u64 a, unsigned s) {
+  if (s == 0) return {a, 0u};
+  return {a << s, (u32)(a >> (64 - s))};
+}
+// -> lazy u64
+__host__ __device__ __forceinline__ u64 w96_reduce(w96 a) {
+#ifdef BJ_GL_PTX
+  u32 l0, l1, v0, v1;
+  unpack2(a.lo, l0, l1);
+  asm("{\n\t.reg .u32 c;\n\t"
+      "mad.lo.cc.u32 %0, %4, 0xffffffff, %2;\n\t"
+      "madc.hi.cc.u32 %1, %4, 0xffffffff, %3;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "mad.lo.cc.u32 %0, c, 0xffffffff, %0;\n\t"
+      "madc.hi.u32 %1, c, 0xffffffff, %1;\n\t"
+      "}"
+      : "=&r"(v0), "=&r"(v1)
+      : "r"(l0), "r"(l1), "r"(a.hi));
+  return pack2(v0, v1);
+#else
+  const u64 t1 = (u64)a.hi * EPS;
+  u64 r = a.lo + t1;
+  if (r < t1) r += EPS;  // hi * EPS < 2^64 - 2^33, so the wrapped sum + EPS cannot wrap again
+  return r;
+#endif
+}
+
 // a * 2^s for 0 <= s < 64 (s compile-time or uniform): 128-bit shift then reduce
 __host__ __device__ __forceinline__ u64 mul_pow2(u64 a, unsigned s) {
   if (s == 0) return canon(a);
