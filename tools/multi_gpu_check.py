@@ -1,0 +1,49 @@
+"""torchrun check on N GPUs: column-sharded iNTT -> NCCL all-gather of monomials -> coset-sharded LDE + Merkle subtrees
+-> all-gather of caps equals the single-GPU commitment (bit-exact), plus timings.  Usage:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+import era_boojum_b200 as bj
+from era_boojum_b200 import parallel
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+ctx = bj.Context.on_current_stream(local)
+log_n = int(os.environ.get("LOG_N", "20"))
+V, L, cap = 64, 8, 16
+gen = torch.Generator(device="cuda:%d" % local)
+gen.manual_seed(123)   # same data on every rank
+cols = torch.randint(0, 2**63 - 1, (V, 1 << log_n), dtype=torch.int64, device="cuda:%d" % local, generator=gen)
+blk = parallel.column_block(rank, world, V)
+backend = parallel.TorchBackend(ctx)
+res = parallel.commit_sharded(backend, dist, cols[blk.start:blk.stop].contiguous(), V, L, cap)
+torch.cuda.synchronize(); dist.barrier()
+t0 = time.perf_counter()
+for _ in range(3):
+    res = parallel.commit_sharded(backend, dist, cols[blk.start:blk.stop].contiguous(), V, L, cap)
+torch.cuda.synchronize(); dist.barrier()
+t_sharded = (time.perf_counter() - t0) / 3
+# single-GPU reference commitment, computed redundantly on every rank
+lde = ctx.transform_raw_storages_to_lde(cols, L)
+tree = ctx.merkle_tree_construct([lde[c].reshape(-1) for c in range(V)], cap)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(3):
+    lde = ctx.transform_raw_storages_to_lde(cols, L)
+    tree = ctx.merkle_tree_construct([lde[c].reshape(-1) for c in range(V)], cap)
+torch.cuda.synchronize()
+t_single = (time.perf_counter() - t0) / 3
+ok = np.array_equal(bj.to_numpy(res["cap"]), tree.get_cap())
+for j, ev in res["cosets"].items():
+    ok = ok and bool(torch.equal(ev, lde[:, j, :]))
+flag = torch.tensor([1 if ok else 0], device="cuda:%d" % local)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print({"world": world, "log_n": log_n, "cols": V, "bit_identical_to_single_gpu": bool(flag.item()),
+           "commit_sharded_s": round(t_sharded, 4), "commit_single_gpu_s": round(t_single, 4),
+           "speedup": round(t_single / t_sharded, 2)})
+dist.destroy_process_group()
