@@ -226,7 +226,7 @@ class Context:
         return out
 
     # ---- Merkle ----
-    def merkle_tree_construct(self, sources, cap_size, elems_per_leaf=1):
+    def merkle_tree_construct(self, sources, cap_size, elems_per_leaf=1, hasher="poseidon2"):
         """sources: list of flat int64 CUDA tensors in leaf-preimage order (MerkleTreeWithCap::construct for
         elems_per_leaf == 1, construct_by_chunking[_from_flat_sources] otherwise)."""
         torch = self._torch
@@ -237,8 +237,8 @@ class Context:
         dev = sources[0].device
         leaf_hashes = torch.empty((n_leaves, 4), dtype=torch.int64, device=dev)
         nodes = torch.empty((max(n_leaves - cap_size, 1), 4), dtype=torch.int64, device=dev)
-        self._check(lib.bj_merkle_build_poseidon2(self._h, ptrs, len(sources), n_leaves, elems_per_leaf, cap_size,
-                                                  self._ptr(leaf_hashes), self._ptr(nodes)))
+        build = {"poseidon2": lib.bj_merkle_build_poseidon2, "blake2s": lib.bj_merkle_build_blake2s}[hasher]
+        self._check(build(self._h, ptrs, len(sources), n_leaves, elems_per_leaf, cap_size, self._ptr(leaf_hashes), self._ptr(nodes)))
         return MerkleTreeWithCap(cap_size, leaf_hashes, nodes[:max(n_leaves - cap_size, 0)])
 
     def poseidon2_hash_rows(self, rows):

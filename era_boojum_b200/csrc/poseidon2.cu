@@ -144,25 +144,12 @@ int32_t bj_merkle_build_poseidon2(bj_ctx* ctx, const uint64_t* const* h_sources,
       (elems_per_leaf & (elems_per_leaf - 1)) || elems_per_leaf == 0)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_merkle_build_poseidon2: sizes must be powers of two, cap <= leaves");
   if (n_leaves > cap_size && !d_nodes) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_merkle_build_poseidon2: d_nodes is NULL");
-  // pointer table -> device (kept in a dedicated small buffer)
-  const size_t bytes = sizeof(u64*) * n_sources;
-  if (ctx->ptr_table_bytes < bytes) {
-    if (ctx->ptr_table) {
-      BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      cudaFree(ctx->ptr_table);
-    }
-    ctx->ptr_table = nullptr;
-    ctx->ptr_table_bytes = 0;
-    BJ_CUDA(ctx, cudaMalloc(&ctx->ptr_table, std::max<size_t>(bytes, 4096)));
-    ctx->ptr_table_bytes = std::max<size_t>(bytes, 4096);
-  }
-  // the previous launch that read the table must be done before we overwrite it
-  BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  BJ_CUDA(ctx, cudaMemcpyAsync(ctx->ptr_table, h_sources, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  void* d_src;
+  BJ_TRY(param_upload(ctx, h_sources, sizeof(u64*) * n_sources, &d_src));
   int log_epl = 0;
   while ((1u << log_epl) < elems_per_leaf) log_epl++;
   poseidon2_leaf_kernel<<<(unsigned)((n_leaves + 127) / 128), 128, 0, ctx->stream>>>(
-      (const u64* const*)ctx->ptr_table, n_sources, n_leaves, log_epl, (u64*)d_leaf_hashes);
+      (const u64* const*)d_src, n_sources, n_leaves, log_epl, (u64*)d_leaf_hashes);
   BJ_LAUNCH_CHECK(ctx);
   if (n_leaves > cap_size) BJ_TRY(merkle_nodes_poseidon2(ctx, (const u64*)d_leaf_hashes, n_leaves, cap_size, (u64*)d_nodes));
   return BJ_OK;

@@ -59,6 +59,7 @@ SIGNATURES = {
     "bj_bitreverse": (_i32, [_vp, _vp, _u32, _u32, _u64]),
     "bj_lde": (_i32, [_vp, _vp, _u64, _vp, _u32, _u32, _u32, _i32]),
     "bj_merkle_build_poseidon2": (_i32, [_vp, _vp, _u32, _u64, _u32, _u32, _vp, _vp]),
+    "bj_merkle_build_blake2s": (_i32, [_vp, _vp, _u32, _u64, _u32, _u32, _vp, _vp]),
     "bj_poseidon2_hash_rows": (_i32, [_vp, _vp, _u64, _u32, _vp]),
     "bj_poseidon2_permute": (_i32, [_vp, _vp, _u64]),
     "bj_fri_fold": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),

@@ -102,6 +102,10 @@ BJ_API int32_t bj_lde(bj_ctx* ctx, const uint64_t* d_in, uint64_t in_col_stride,
 BJ_API int32_t bj_merkle_build_poseidon2(bj_ctx* ctx, const uint64_t* const* h_sources, uint32_t n_sources,
                                   uint64_t n_leaves, uint32_t elems_per_leaf, uint32_t cap_size,
                                   uint64_t* d_leaf_hashes, uint64_t* d_nodes);
+/* Same tree with H = blake2::Blake2s256 (src/cs/oracle/mod.rs:179-245): leaf = Blake2s-256 over the LE bytes of the reduced
+ * elements, node = Blake2s-256(left || right); 32-byte digests stored as 4 LE u64 (same [n][4] layout). */
+BJ_API int32_t bj_merkle_build_blake2s(bj_ctx* ctx, const uint64_t* const* h_sources, uint32_t n_sources, uint64_t n_leaves,
+                                uint32_t elems_per_leaf, uint32_t cap_size, uint64_t* d_leaf_hashes, uint64_t* d_nodes);
 /* TreeHasher::hash_into_leaf on rows given contiguously: n_rows rows of row_len u64 (row-major) -> digests */
 BJ_API int32_t bj_poseidon2_hash_rows(bj_ctx* ctx, const uint64_t* d_rows, uint64_t n_rows, uint32_t row_len,
                                uint64_t* d_digests);
