@@ -332,6 +332,35 @@ class Context:
         self._check(lib.bj_barycentric_evaluate(self._h, pc, n_cols, log_n, a, out.ctypes.data_as(ctypes.c_void_p)))
         return [(int(r[0]), int(r[1])) for r in out]
 
+    # ---- lookup argument ----
+    def compute_lookup_poly_pairs_specialized(self, lookup_cols, width, table_id_col, table_cols, multiplicity, beta, gamma):
+        """lookup_argument_in_ext.rs:320-947.  lookup_cols: flat list of n_sub*width [n] tensors.  Returns
+        ([(A_i.c0, A_i.c1)], (B.c0, B.c1))."""
+        torch = self._torch
+        n_sub, n = len(lookup_cols) // width, lookup_cols[0].numel()
+        pl = (ctypes.c_void_p * len(lookup_cols))(*[c.data_ptr() for c in lookup_cols])
+        pt = (ctypes.c_void_p * len(table_cols))(*[c.data_ptr() for c in table_cols])
+        out = torch.empty((n_sub + 1, 2, n), dtype=torch.int64, device=lookup_cols[0].device)
+        b = (ctypes.c_uint64 * 2)(int(beta[0]), int(beta[1]))
+        g = (ctypes.c_uint64 * 2)(int(gamma[0]), int(gamma[1]))
+        self._check(lib.bj_lookup_polys_specialized(self._h, pl, n_sub, width, self._ptr(table_id_col) if table_id_col is not None else None,
+                                                    pt, len(table_cols), self._ptr(multiplicity), b, g, n.bit_length() - 1, self._ptr(out)))
+        return [(out[i, 0], out[i, 1]) for i in range(n_sub)], (out[n_sub, 0], out[n_sub, 1])
+
+    def quotient_lookup_specialized(self, lookup_ldes, width, table_id_lde, table_ldes, multiplicity_lde, a_ldes, b_lde, beta, gamma,
+                                    alphas, q_c0, q_c1):
+        n_sub = len(lookup_ldes) // width
+        pl = (ctypes.c_void_p * len(lookup_ldes))(*[c.data_ptr() for c in lookup_ldes])
+        pt = (ctypes.c_void_p * len(table_ldes))(*[c.data_ptr() for c in table_ldes])
+        flat = [t for pr in a_ldes for t in pr]
+        pa = (ctypes.c_void_p * len(flat))(*[t.data_ptr() for t in flat])
+        b = (ctypes.c_uint64 * 2)(int(beta[0]), int(beta[1]))
+        g = (ctypes.c_uint64 * 2)(int(gamma[0]), int(gamma[1]))
+        al = (ctypes.c_uint64 * (2 * len(alphas)))(*[int(x) for a in alphas for x in a])
+        self._check(lib.bj_quotient_lookup_specialized(self._h, pl, n_sub, width, self._ptr(table_id_lde) if table_id_lde is not None else None,
+                                                       pt, len(table_ldes), self._ptr(multiplicity_lde), pa, self._ptr(b_lde[0]),
+                                                       self._ptr(b_lde[1]), b, g, al, q_c0.numel(), self._ptr(q_c0), self._ptr(q_c1)))
+
     # ---- gate / quotient evaluator ----
     def evaluate_gates_over_general_purpose_columns(self, gates, variables, witnesses, constants, alpha_powers, q_c0, q_c1):
         """Row loop of prove_cpu_basic over general-purpose columns (cs/implementations/prover.rs:1031-1080).

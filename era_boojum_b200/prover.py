@@ -56,7 +56,9 @@ class Setup:
     """SetupStorage + setup Merkle tree + the fixed parameters of the VerificationKey (setup.rs:1093-1255,
     verifier.rs:31-79): sigma and constant columns, their LDEs, the tree over [sigmas | constants]."""
 
-    def __init__(self, ctx, sigmas, constants, gates, quotient_degree, config):
+    def __init__(self, ctx, sigmas, constants, gates, quotient_degree, config, lookup=None):
+        """lookup: None or dict(width, num_repetitions, variables_offset, table_id_column (index into constants),
+        tables=[width + 1, n] tensor of lookup-table setup columns, multiplicities are part of the witness)."""
         torch = ctx._torch
         self.gates = gates                      # [dict(name, program..., num_repetitions, selector_path, ...)]
         self.quotient_degree = quotient_degree
@@ -65,8 +67,11 @@ class Setup:
         self.num_constants = constants.shape[0]
         self.log_n = sigmas.shape[1].bit_length() - 1
         self.sigmas = sigmas                    # [V, n] natural order (needed by stage 2)
+        self.constants_natural = constants      # [C, n] natural order (table-id column of the lookup argument)
         L = config.fri_lde_factor
-        cols = torch.cat([sigmas, constants], dim=0).contiguous()
+        self.lookup = lookup
+        parts = [sigmas, constants] + ([lookup["tables"]] if lookup else [])
+        cols = torch.cat(parts, dim=0).contiguous()
         self.lde = ctx.transform_raw_storages_to_lde(cols, L)      # [V + C, L, n]
         self.tree = ctx.merkle_tree_construct([self.lde[c].reshape(-1) for c in range(cols.shape[0])],
                                               config.merkle_tree_cap_size)
@@ -78,16 +83,23 @@ class Setup:
     def constant_lde(self, j):
         return self.lde[self.num_variables + j].reshape(-1)
 
+    def table_lde(self, j):
+        return self.lde[self.num_variables + self.num_constants + j].reshape(-1)
+
     def vk(self):
-        return {"domain_size": 1 << self.log_n, "num_variables": self.num_variables, "num_constants": self.num_constants,
+        lk = None
+        if self.lookup:
+            lk = {k: self.lookup[k] for k in ("width", "num_repetitions", "variables_offset", "table_id_column")}
+        return {"lookup": lk, "domain_size": 1 << self.log_n, "num_variables": self.num_variables, "num_constants": self.num_constants,
                 "quotient_degree": self.quotient_degree, "fri_lde_factor": self.config.fri_lde_factor,
                 "cap_size": self.config.merkle_tree_cap_size,
                 "gates": [(g["name"], g["num_repetitions"], list(g["selector_path"])) for g in self.gates],
                 "setup_merkle_tree_cap": self.cap.tolist()}
 
 
-def prove(ctx, setup, variables, timings=None):
-    """variables: [V, n] int64 CUDA tensor (copy-permutation columns, natural row order).  Returns the proof dict."""
+def prove(ctx, setup, variables, timings=None, multiplicities=None):
+    """variables: [V, n] int64 CUDA tensor (copy-permutation columns incl. the lookup sub-argument columns, natural row
+    order); multiplicities: [n] tensor when the setup has a lookup argument.  Returns the proof dict."""
     torch = ctx._torch
     cfg = setup.config
     L, cap = cfg.fri_lde_factor, cfg.merkle_tree_cap_size
@@ -108,9 +120,14 @@ def prove(ctx, setup, variables, timings=None):
     tr.witness_merkle_tree_cap(setup.cap)                                   # prover.rs:211
     # ---- round 1: witness commitment (prover.rs:313-353) ----
     t0 = time.perf_counter()
+    lk = setup.lookup
     w_lde = ctx.transform_raw_storages_to_lde(variables, L)                  # [V, L, n]
     w_cols = [flat(w_lde[c]) for c in range(V)]
-    w_tree = ctx.merkle_tree_construct(w_cols, cap)
+    m_col = None
+    if lk:
+        m_lde = ctx.transform_raw_storages_to_lde(multiplicities.reshape(1, -1).contiguous(), L)
+        m_col = flat(m_lde[0])
+    w_tree = ctx.merkle_tree_construct(w_cols + ([m_col] if lk else []), cap)   # variables | witness (none) | multiplicities
     w_cap = w_tree.get_cap()
     tr.witness_merkle_tree_cap(w_cap)
     mark("1_witness_lde_commit", t0)
@@ -118,9 +135,19 @@ def prove(ctx, setup, variables, timings=None):
     t0 = time.perf_counter()
     beta = tr.get_multiple_challenges_fixed(2)
     gamma = tr.get_multiple_challenges_fixed(2)
+    if lk:
+        lookup_beta = tr.get_multiple_challenges_fixed(2)                    # prover.rs:402-406
+        lookup_gamma = tr.get_multiple_challenges_fixed(2)
     z0, z1, partials = ctx.compute_partial_products_in_extension([variables[c] for c in range(V)],
                                                                  [setup.sigmas[c] for c in range(V)], beta, gamma, Q)
-    st2 = torch.stack([z0, z1] + [t for pr in partials for t in pr]).contiguous()
+    lk_polys = []
+    if lk:
+        wdt, nsub, voff = lk["width"], lk["num_repetitions"], lk["variables_offset"]
+        a_polys, b_poly = ctx.compute_lookup_poly_pairs_specialized(
+            [variables[voff + i] for i in range(wdt * nsub)], wdt, setup.constants_natural[lk["table_id_column"]],
+            [lk["tables"][j] for j in range(wdt + 1)], multiplicities, lookup_beta, lookup_gamma)
+        lk_polys = [t for pr in a_polys for t in pr] + [b_poly[0], b_poly[1]]
+    st2 = torch.stack([z0, z1] + [t for pr in partials for t in pr] + lk_polys).contiguous()
     s2_lde = ctx.transform_raw_storages_to_lde(st2, L)
     s2_cols = [flat(s2_lde[c]) for c in range(st2.shape[0])]
     s2_tree = ctx.merkle_tree_construct(s2_cols, cap)
@@ -132,7 +159,8 @@ def prove(ctx, setup, variables, timings=None):
     t0 = time.perf_counter()
     alpha = tr.get_multiple_challenges_fixed(2)
     n_gate_terms = sum(len(g["writes"]) * g["num_repetitions"] for g in setup.gates)
-    total_terms = n_gate_terms + 1 + 1 + n_partial
+    n_lk_terms = (lk["num_repetitions"] + 1) if lk else 0      # lookup terms come first (prover.rs:608-625)
+    total_terms = n_lk_terms + n_gate_terms + 1 + 1 + n_partial
     powers = [(1, 0)]
     for _ in range(1, total_terms):
         powers.append(e_mul(powers[-1], alpha))
@@ -140,10 +168,18 @@ def prove(ctx, setup, variables, timings=None):
     q0 = torch.zeros(npts, dtype=torch.int64, device=dev)
     q1 = torch.zeros(npts, dtype=torch.int64, device=dev)
     const_cols = [setup.constant_lde(j) for j in range(C)]
-    ctx.evaluate_gates_over_general_purpose_columns(setup.gates, w_cols, [], const_cols, powers[:n_gate_terms], q0, q1)
+    a_off = 2 + 2 * n_partial
+    if lk:
+        a_ldes = [(s2_cols[a_off + 2 * i], s2_cols[a_off + 2 * i + 1]) for i in range(nsub)]
+        b_lde = (s2_cols[a_off + 2 * nsub], s2_cols[a_off + 2 * nsub + 1])
+        ctx.quotient_lookup_specialized([w_cols[voff + i] for i in range(wdt * nsub)], wdt, const_cols[lk["table_id_column"]],
+                                        [setup.table_lde(j) for j in range(wdt + 1)], m_col, a_ldes, b_lde, lookup_beta, lookup_gamma,
+                                        powers[:n_lk_terms], q0, q1)
+    ctx.evaluate_gates_over_general_purpose_columns(setup.gates, w_cols, [], const_cols,
+                                                    powers[n_lk_terms:n_lk_terms + n_gate_terms], q0, q1)
     part_ldes = [(s2_cols[2 + 2 * c], s2_cols[3 + 2 * c]) for c in range(n_partial)]
     ctx.quotient_copy_permutation(w_cols, [setup.sigma_lde(j) for j in range(V)], (s2_cols[0], s2_cols[1]), part_ldes, beta, gamma,
-                                  powers[n_gate_terms:], log_n, log_L, log_q, Q, q0, q1)
+                                  powers[n_lk_terms + n_gate_terms:], log_n, log_L, log_q, Q, q0, q1)
     ctx.divide_by_vanishing(q0, q1, log_n, log_q)
     # flatten the cosets into natural order, interpolate once at size n*Q on coset 7, split into Q chunks (prover.rs:1399-1467)
     qq = torch.stack([q0, q1]).contiguous()
@@ -165,28 +201,45 @@ def prove(ctx, setup, variables, timings=None):
     z = tr.get_multiple_challenges_fixed(2)
     w_n = _omega(log_n)
     z_omega = e_mul_base(z, w_n)
-    base_cols = w_cols + const_cols + [setup.sigma_lde(j) for j in range(V)]
-    ext_cols = s2_cols + qt_cols
-    ev = ctx.barycentric_evaluate(base_cols + ext_cols, log_n, z)
-    nb = len(base_cols)
-    values_at_z = ev[:nb] + [_combine_ext(ev[nb + 2 * i], ev[nb + 2 * i + 1]) for i in range(len(ext_cols) // 2)]
-    ev_w = ctx.barycentric_evaluate([s2_cols[0], s2_cols[1]], log_n, z_omega)
-    values_at_z_omega = [_combine_ext(ev_w[0], ev_w[1])]
-    for v in values_at_z + values_at_z_omega:
+    # opening order (prover.rs:1549-1683): variables, witness, constants, sigmas, z, partial products, multiplicities,
+    # lookup A, lookup B, lookup tables, quotient chunks.  `sources` keeps (c0, c1-or-None) per opened polynomial.
+    sources = [(c, None) for c in w_cols] + [(c, None) for c in const_cols] + [(setup.sigma_lde(j), None) for j in range(V)]
+    sources += [(s2_cols[2 * i], s2_cols[2 * i + 1]) for i in range(1 + n_partial)]
+    if lk:
+        sources += [(m_col, None)]
+        sources += [(s2_cols[a_off + 2 * i], s2_cols[a_off + 2 * i + 1]) for i in range(nsub + 1)]
+        sources += [(setup.table_lde(j), None) for j in range(wdt + 1)]
+    sources += [(qt_cols[2 * i], qt_cols[2 * i + 1]) for i in range(Q)]
+
+    def open_at(srcs, at):
+        flat_cols, spans = [], []
+        for c0, c1 in srcs:
+            spans.append((len(flat_cols), c1 is not None))
+            flat_cols += [c0] + ([c1] if c1 is not None else [])
+        ev = ctx.barycentric_evaluate(flat_cols, log_n, at)
+        return [(_combine_ext(ev[i], ev[i + 1]) if is_ext else ev[i]) for i, is_ext in spans]
+
+    values_at_z = open_at(sources, z)
+    values_at_z_omega = open_at([(s2_cols[0], s2_cols[1])], z_omega)
+    zero_sources = [(s2_cols[a_off + 2 * i], s2_cols[a_off + 2 * i + 1]) for i in range(nsub + 1)] if lk else []
+    values_at_0 = open_at(zero_sources, (0, 0)) if lk else []
+    for v in values_at_z + values_at_z_omega + values_at_0:
         tr.witness_field_elements(v)
     mark("4_openings", t0)
     # ---- round 5: DEEP + FRI (prover.rs:1828-2102) ----
     t0 = time.perf_counter()
     c = tr.get_multiple_challenges_fixed(2)
-    n_ch = len(values_at_z) + 1
+    n_ch = len(values_at_z) + 1 + len(values_at_0)
     ch = [(1, 0), c]
     for _ in range(2, n_ch):
         ch.append(e_mul(ch[-1], c))
     deep0 = torch.zeros(n * L, dtype=torch.int64, device=dev)
     deep1 = torch.zeros(n * L, dtype=torch.int64, device=dev)
-    sources = [(col, None) for col in base_cols] + [(ext_cols[2 * i], ext_cols[2 * i + 1]) for i in range(len(ext_cols) // 2)]
     ctx.quotening_operation_in_extension(deep0, deep1, sources, values_at_z, z, ch[:len(sources)])
-    ctx.quotening_operation_in_extension(deep0, deep1, [(s2_cols[0], s2_cols[1])], values_at_z_omega, z_omega, ch[len(sources):])
+    ctx.quotening_operation_in_extension(deep0, deep1, [(s2_cols[0], s2_cols[1])], values_at_z_omega, z_omega,
+                                         ch[len(sources):len(sources) + 1])
+    if lk:
+        ctx.quotening_operation_in_extension(deep0, deep1, zero_sources, values_at_0, (0, 0), ch[len(sources) + 1:])
     import ctypes
     from .native import lib
     np_, nq, sl, fd = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
@@ -202,8 +255,8 @@ def prove(ctx, setup, variables, timings=None):
     t0 = time.perf_counter()
     max_bits = log_n + log_L
     idxs = [tr.get_index_bits(max_bits, max_bits) for _ in range(nq.value)]
-    setup_cols = [setup.lde[c].reshape(-1) for c in range(V + C)]
-    oracles = [("witness_query", w_cols, w_tree), ("stage_2_query", s2_cols, s2_tree), ("quotient_query", qt_cols, qt_tree),
+    setup_cols = [setup.lde[c].reshape(-1) for c in range(setup.lde.shape[0])]
+    oracles = [("witness_query", w_cols + ([m_col] if lk else []), w_tree), ("stage_2_query", s2_cols, s2_tree), ("quotient_query", qt_cols, qt_tree),
                ("setup_query", setup_cols, setup.tree)]
     rows = {name: (ctx.query_leaf_elements(cols, idxs), ctx.merkle_paths(tree, idxs)) for name, cols, tree in oracles}
     queries = []
@@ -222,7 +275,7 @@ def prove(ctx, setup, variables, timings=None):
         "witness_oracle_cap": w_cap.tolist(), "stage_2_oracle_cap": s2_cap.tolist(), "quotient_oracle_cap": qt_cap.tolist(),
         "final_fri_monomials": [mono0.tolist(), mono1.tolist()],
         "values_at_z": [_ext_dict(v) for v in values_at_z], "values_at_z_omega": [_ext_dict(v) for v in values_at_z_omega],
-        "values_at_0": [],
+        "values_at_0": [_ext_dict(v) for v in values_at_0],
         "fri_base_oracle_cap": fri.get_cap(0).tolist(),
         "fri_intermediate_oracles_caps": [fri.get_cap(i).tolist() for i in range(1, fri.num_oracles())],
         "queries_per_fri_repetition": queries, "pow_challenge": 0, "_marker": None,

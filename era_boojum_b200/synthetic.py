@@ -40,9 +40,13 @@ def sha_shaped_gates(num_variables=60):
             g(REDUCTION4, num_variables // 5, [False])]
 
 
-def generate(ctx, log_n, num_variables=60, seed=0):
-    """Returns (variables [V, n], sigmas [V, n], constants [6, n], gates, quotient_degree) as int64 CUDA tensors."""
+def generate(ctx, log_n, num_variables=60, seed=0, lookup=False):
+    """Returns (variables [V, n], sigmas [V, n], constants [C, n], gates, quotient_degree) as int64 CUDA tensors, C = 6.
+    With lookup=True (the bench's 8 sub-arguments of width 4 with a shared table id in a constant column,
+    src/gadgets/sha256/mod.rs:340-346): V grows by 32 specialised lookup columns, C = 7 (column 6 = table id) and a sixth
+    return value dict(width, num_repetitions, variables_offset, table_id_column, tables [5, n], multiplicities [n])."""
     torch = ctx._torch
+    n_gp = num_variables
     V, n, C = num_variables, 1 << log_n, 6
     dev = "cuda:%d" % ctx.device
     gen = torch.Generator(device=dev)
@@ -102,4 +106,33 @@ def generate(ctx, log_n, num_variables=60, seed=0):
         a, b = 5 * k, 5 * k - 1
         sigmas[a] = torch.where(is_red, ident[b], sigmas[a])
         sigmas[b] = torch.where(is_red, ident[a], sigmas[b])
-    return variables.contiguous(), sigmas.contiguous(), constants.contiguous(), gates, 4
+    if not lookup:
+        return variables.contiguous(), sigmas.contiguous(), constants.contiguous(), gates, 4
+    # ---- lookup argument: every row looks up 8 random entries of one width-4 table (table id 1)
+    width, nsub = 4, 8
+    T = min(n, 1 << 16)
+    tables = torch.zeros((width + 1, n), dtype=torch.int64, device=dev)
+    idx = torch.arange(T, dtype=torch.int64, device=dev)
+    tables[0, :T] = idx
+    tables[1, :T] = idx * idx + 3
+    tables[2, :T] = idx ^ 0x5555
+    tables[3, :T] = 7 * idx + 1
+    tables[4, :T] = 1                      # table id column
+    picks = rnd((nsub, n), T)
+    lk_cols = torch.stack([tables[j][picks[i]] for i in range(nsub) for j in range(width)])      # [32, n]
+    mult = torch.bincount(picks.reshape(-1), minlength=n).to(torch.int64)
+    table_id_const = torch.ones((1, n), dtype=torch.int64, device=dev)
+    variables = torch.cat([variables, lk_cols], dim=0)
+    constants = torch.cat([constants, table_id_const], dim=0)
+    # identity sigmas for the lookup columns
+    Vt = n_gp + nsub * width
+    ks = ctx.non_residues_for_copy_permutation(n, Vt)
+    mono = torch.zeros((Vt, n), dtype=torch.int64, device=dev)
+    mono[:, 1 if n > 1 else 0] = torch.from_numpy(ks.view(np.int64)).to(dev)
+    ctx.fft_natural_to_bitreversed(mono, 1)
+    ctx.bitreverse_enumeration_inplace(mono)
+    # the first n_gp non-residues are a prefix of the longer list, so the gp sigmas computed above stay valid
+    sigmas = torch.cat([sigmas, mono[n_gp:]], dim=0)
+    lk = dict(width=width, num_repetitions=nsub, variables_offset=n_gp, table_id_column=6, tables=tables.contiguous(),
+              multiplicities=mult.contiguous())
+    return variables.contiguous(), sigmas.contiguous(), constants.contiguous(), gates, 4, lk

@@ -152,6 +152,26 @@ BJ_API int32_t bj_copy_permutation_stage2(bj_ctx* ctx, const uint64_t* const* h_
                                    const uint64_t h_gamma[2], uint32_t log_n, uint32_t chunk_size, uint64_t* d_z_c0,
                                    uint64_t* d_z_c1, uint64_t* d_partials);
 
+/* ---- lookup argument over specialised columns, table id in a constant column
+ *      (LookupParameters::UseSpecializedColumnsWithTableIdAsConstant; src/cs/implementations/lookup_argument_in_ext.rs) ----
+ * stage 2 (compute_lookup_poly_pairs_specialized, :320-947), trace domain, natural order:
+ *   A_i[r] = 1/(beta + sum_j gamma^j col_{i,j}[r] + gamma^w table_id[r]),  B[r] = m[r]/(beta + sum_j gamma^j t_j[r]).
+ * h_lookup_cols: n_subarguments*width device pointers (the sub-arguments' variable columns, in order); d_table_id_col: the
+ * constant column with the table id (NULL if none); h_table_cols: the n_table_cols = width (+1) lookup-table setup columns.
+ * d_out: [n_subarguments + 1][c0|c1][n]  (A_0, ..., A_{k-1}, B). */
+BJ_API int32_t bj_lookup_polys_specialized(bj_ctx* ctx, const uint64_t* const* h_lookup_cols, uint32_t n_subarguments, uint32_t width,
+                                    const uint64_t* d_table_id_col, const uint64_t* const* h_table_cols, uint32_t n_table_cols,
+                                    const uint64_t* d_multiplicity, const uint64_t h_beta[2], const uint64_t h_gamma[2],
+                                    uint32_t log_n, uint64_t* d_out);
+/* quotient terms (compute_quotient_terms_for_lookup_specialized, :949-1319) on the first n_points = Q*n points of the LDE:
+ *   q += alpha_i (A_i (beta + sum gamma^j col_ij + gamma^w id) - 1)  for every sub-argument,  + alpha_k (B (beta + sum gamma^j t_j) - m).
+ * All column arguments are LDE columns; h_a_ldes: 2*n_subarguments pointers (c0, c1); h_alphas: n_subarguments + 1 Fp2. */
+BJ_API int32_t bj_quotient_lookup_specialized(bj_ctx* ctx, const uint64_t* const* h_lookup_ldes, uint32_t n_subarguments, uint32_t width,
+                                       const uint64_t* d_table_id_lde, const uint64_t* const* h_table_ldes, uint32_t n_table_cols,
+                                       const uint64_t* d_multiplicity_lde, const uint64_t* const* h_a_ldes, const uint64_t* d_b_c0,
+                                       const uint64_t* d_b_c1, const uint64_t h_beta[2], const uint64_t h_gamma[2],
+                                       const uint64_t* h_alphas, uint64_t n_points, uint64_t* d_q_c0, uint64_t* d_q_c1);
+
 /* ---- gate / quotient evaluator over general-purpose columns: the row loop of prove_cpu_basic
  *      (src/cs/implementations/prover.rs:1031-1080) with GateConstraintEvaluator::evaluate_once (src/cs/traits/evaluator.rs:145-152)
  *      supplied as DATA: the SSA program recorded by the reference's own GPU hook, gpu_synthesizer::GPUDataCapture

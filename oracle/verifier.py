@@ -61,6 +61,11 @@ def verify(vk, proof):
     V, C, Q = vk["num_variables"], vk["num_constants"], vk["quotient_degree"]
     gates = vk["gates"]
     n_partial = 0 if V <= Q else (V + Q - 1) // Q - 1
+    lk = vk.get("lookup")
+    nsub, wdt = (lk["num_repetitions"], lk["width"]) if lk else (0, 0)
+    n_lk_terms = nsub + 1 if lk else 0
+    n_mult = 1 if lk else 0
+    n_tables = wdt + 1 if lk else 0
 
     tr = R.Poseidon2Transcript()
     tr.witness_merkle_tree_cap(vk["setup_merkle_tree_cap"])
@@ -68,22 +73,27 @@ def verify(vk, proof):
     tr.witness_merkle_tree_cap(proof["witness_oracle_cap"])
     beta = tr.get_ext_challenge()
     gamma = tr.get_ext_challenge()
+    if lk:
+        lookup_beta = tr.get_ext_challenge()
+        lookup_gamma = tr.get_ext_challenge()
     tr.witness_merkle_tree_cap(proof["stage_2_oracle_cap"])
     alpha = tr.get_ext_challenge()
     n_gate_terms = sum(reps for _, reps, _ in gates)  # one term per repetition for the three bench gates
-    total_terms = n_gate_terms + 1 + 1 + n_partial
+    total_terms = n_lk_terms + n_gate_terms + 1 + 1 + n_partial
     powers = [(1, 0)]
     for _ in range(1, total_terms):
         powers.append(R.e_mul(powers[-1], alpha))
-    gp_ch, rest_ch = powers[:n_gate_terms], powers[n_gate_terms:]
+    lk_ch = powers[:n_lk_terms]
+    gp_ch, rest_ch = powers[n_lk_terms:n_lk_terms + n_gate_terms], powers[n_lk_terms + n_gate_terms:]
     tr.witness_merkle_tree_cap(proof["quotient_oracle_cap"])
     z = tr.get_ext_challenge()
     vals_z = [_ext(v) for v in proof["values_at_z"]]
     vals_zw = [_ext(v) for v in proof["values_at_z_omega"]]
-    assert proof["values_at_0"] == []
-    for v in vals_z + vals_zw:
+    vals_0 = [_ext(v) for v in proof["values_at_0"]]
+    for v in vals_z + vals_zw + vals_0:
         tr.witness_field_elements(v)
-    assert len(vals_z) == V + C + V + 1 + n_partial + Q and len(vals_zw) == 1
+    assert len(vals_z) == V + C + V + 1 + n_partial + n_mult + n_lk_terms + n_tables + Q and len(vals_zw) == 1
+    assert len(vals_0) == n_lk_terms
 
     # ---- quotient identity at z ----
     it = iter(vals_z)
@@ -92,9 +102,35 @@ def verify(vk, proof):
     sigma_v = [next(it) for _ in range(V)]
     z_at_z = next(it)
     partial_v = [next(it) for _ in range(n_partial)]
+    mult_v = [next(it) for _ in range(n_mult)]
+    a_v = [next(it) for _ in range(nsub)]
+    b_v = [next(it) for _ in range(n_mult)]
+    table_v = [next(it) for _ in range(n_tables)]
     quot_v = [next(it) for _ in range(Q)]
     z_at_zw = vals_zw[0]
     t_acc = (0, 0)
+    if lk:
+        # log-derivative sumcheck from the openings at 0 (verifier.rs:1238-1257), then the relations at z (:1258-1560)
+        sa, sb = (0, 0), (0, 0)
+        for v in vals_0[:nsub]:
+            sa = R.e_add(sa, v)
+        for v in vals_0[nsub:]:
+            sb = R.e_add(sb, v)
+        assert sa == sb, "Lookup sumcheck is invalid"
+        gp = [(1, 0)]
+        for _ in range(wdt):
+            gp.append(R.e_mul(gp[-1], lookup_gamma))
+        voff, tid = lk["variables_offset"], lk["table_id_column"]
+        for i in range(nsub):
+            d = lookup_beta
+            for j in range(wdt):
+                d = R.e_add(d, R.e_mul(gp[j], var_v[voff + i * wdt + j]))
+            d = R.e_add(d, R.e_mul(gp[wdt], const_v[tid]))
+            t_acc = R.e_add(t_acc, R.e_mul(R.e_sub(R.e_mul(a_v[i], d), (1, 0)), lk_ch[i]))
+        d = lookup_beta
+        for j in range(wdt + 1):
+            d = R.e_add(d, R.e_mul(gp[j], table_v[j]))
+        t_acc = R.e_add(t_acc, R.e_mul(R.e_sub(R.e_mul(b_v[0], d), mult_v[0]), lk_ch[nsub]))
     k = 0
     for name, reps, path in gates:
         fn, width, (voff, coff) = GATES[name]
@@ -133,7 +169,7 @@ def verify(vk, proof):
 
     # ---- DEEP + FRI ----
     c = tr.get_ext_challenge()
-    ch = R.ext_powers(c, len(vals_z) + len(vals_zw))
+    ch = R.ext_powers(c, len(vals_z) + len(vals_zw) + len(vals_0))
     new_pow, num_queries, schedule, final_degree = R.compute_fri_schedule(
         proof["proof_config"]["security_level"], cap_size, proof["proof_config"]["pow_bits"], log_L, log_n)
     assert new_pow == 0 and num_queries == len(proof["queries_per_fri_repetition"])
@@ -163,17 +199,22 @@ def verify(vk, proof):
             assert O.merkle_verify(leaf, path, np.array(cap, dtype=np.uint64), idx), (name, idx)
         wq, sq = q["witness_query"]["leaf_elements"], q["stage_2_query"]["leaf_elements"]
         qq, uq = q["quotient_query"]["leaf_elements"], q["setup_query"]["leaf_elements"]
-        assert len(wq) == V and len(sq) == 2 * (1 + n_partial) and len(qq) == 2 * Q and len(uq) == V + C
+        assert len(wq) == V + n_mult and len(sq) == 2 * (1 + n_partial + n_lk_terms) and len(qq) == 2 * Q
+        assert len(uq) == V + C + n_tables
         base = lambda els: [(e, 0) for e in els]
         ext = lambda els: [(els[i], els[i + 1]) for i in range(0, len(els), 2)]
-        src = base(wq) + base(uq[V:V + C]) + base(uq[:V]) + ext(sq[0:2]) + ext(sq[2:]) + ext(qq)
+        off_a = 2 + 2 * n_partial
+        src = base(wq[:V]) + base(uq[V:V + C]) + base(uq[:V]) + ext(sq[0:2]) + ext(sq[2:off_a]) + base(wq[V:]) + ext(sq[off_a:]) \
+            + base(uq[V + C:]) + ext(qq)
         x = 1
         for b, pw in zip(bits, [R.omega(i) for i in range(1, max_bits + 1)]):
             if b:
                 x = R.fmul(x, pw)
         x_q = R.fmul(x, 7)
         acc = O.deep_point((0, 0), src, vals_z, ch[:len(src)], x_q, z)
-        acc = O.deep_point(acc, ext(sq[0:2]), vals_zw, ch[len(src):], x_q, z_omega)
+        acc = O.deep_point(acc, ext(sq[0:2]), vals_zw, ch[len(src):len(src) + 1], x_q, z_omega)
+        if lk:
+            acc = O.deep_point(acc, ext(sq[off_a:]), vals_0, ch[len(src) + 1:], x_q, (0, 0))
         fqs = [(fq["leaf_elements"], fq["proof"]) for fq in q["fri_queries"]]
         R.verify_fri_query(idx, log_n, log_L, schedule, cap_size, fri_caps, fri_ch, (mono[0], mono[1]), fqs, start_value=acc)
     return True

@@ -41,6 +41,23 @@ def test_prove_then_verify(env, log_n, V, lde, cap):
     assert len(proof["queries_per_fri_repetition"]) == -(-100 // (lde.bit_length() - 1))
 
 
+@pytest.mark.parametrize("log_n", [8, 11])
+def test_prove_then_verify_with_lookup_argument(env, log_n):
+    """the bench geometry incl. the log-derivative lookup: 60 gp + 8x4 specialised lookup columns, table id in a constant."""
+    bj, ctx, prover, synthetic = env
+    variables, sigmas, constants, gates, Q, lk = synthetic.generate(ctx, log_n, 60, seed=log_n, lookup=True)
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100)
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg, lookup=lk)
+    proof = prover.prove(ctx, setup, variables, multiplicities=lk["multiplicities"])
+    vk = setup.vk()
+    assert len(proof["values_at_0"]) == 9 and len(proof["queries_per_fri_repetition"][0]["witness_query"]["leaf_elements"]) == 93
+    assert OV.verify(vk, proof)
+    bad = copy.deepcopy(proof)
+    bad["values_at_0"][2]["coeffs"][1] ^= 1
+    with pytest.raises(AssertionError):
+        OV.verify(vk, bad)
+
+
 def test_tampered_proofs_are_rejected(env):
     vk, proof = _prove(env, 8, 20, seed=5)
     assert OV.verify(vk, proof)
