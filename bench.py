@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """bench.py - headline measurement for the Boojum polynomial-commitment hot path on B200.
 
-metric  : Goldilocks NTT G-elements/s (BASELINE.json metric, first half; the SHA-256 full-prove seconds need the
-          complete prover and are not produced by this round's bench).
+metric  : Goldilocks NTT G-elements/s (BASELINE.json metric, first half).  The second half, proof-generation seconds
+          at 2^22 rows, is reported in the extra "prove" object on a synthetic SHA-256-bench-shaped circuit (the real
+          circuit needs the Rust synthesiser); "merkle" reports BASELINE configs[2].
 workload: BASELINE.json configs[1] "2^20-2^24 Goldilocks NTT/LDE sweep on 1xB200": one step = forward
           natural->bit-reversed NTT on coset 7 (benches/benchmarks.rs:541 uses coset 7) of five resident batches,
           n = 2^20..2^24 with 128/64/32/16/8 columns (1 GiB each, SURVEY.md 8(d) cfg 2), in place, through the
@@ -297,21 +298,21 @@ def main():
     if world == 1 and args.prove_log_n > 0:
         torch.cuda.empty_cache()
         from era_boojum_b200 import prover, synthetic
-        variables, sigmas, constants, gates, Q = synthetic.generate(ctx, args.prove_log_n, 60, seed=42)
+        variables, sigmas, constants, gates, Q, lk = synthetic.generate(ctx, args.prove_log_n, 60, seed=42, lookup=True)
         cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100)
-        setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg)
-        prover.prove(ctx, setup, variables)  # warm-up (tables, allocator)
+        setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg, lookup=lk)
+        prover.prove(ctx, setup, variables, multiplicities=lk["multiplicities"])  # warm-up (tables, allocator)
         torch.cuda.synchronize()
         stages = {}
         t0 = time.perf_counter()
-        proof = prover.prove(ctx, setup, variables, timings=stages)
+        proof = prover.prove(ctx, setup, variables, timings=stages, multiplicities=lk["multiplicities"])
         torch.cuda.synchronize()
         secs = time.perf_counter() - t0
-        out["prove"] = {"circuit": "synthetic sha256-bench-shaped: 60 gp columns, ConstantsAllocator/Fma/Reduction<4>, Q=4, L=8, cap 16, no lookups",
+        out["prove"] = {"circuit": "synthetic sha256-bench-shaped: 60 gp columns + 8 lookup sub-arguments of width 4 (92 copy-permutation columns, 1 multiplicity column), ConstantsAllocator/Fma/Reduction<4>, Q=4, L=8, cap 16, Poseidon2 tree + transcript",
                         "rows_log2": args.prove_log_n, "seconds": round(secs, 4), "queries": len(proof["queries_per_fri_repetition"]),
                         "stages_s": {k: round(v, 4) for k, v in stages.items()},
                         "note": "H2D of the witness not included (trace generated on the device); accepted by the oracle verifier in tests/test_gpu_prove.py"}
-        del proof, setup, variables, sigmas, constants
+        del proof, setup, variables, sigmas, constants, lk
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_sample()
     if rank == 0:

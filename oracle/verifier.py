@@ -1,9 +1,11 @@
 """ORACLE (test infrastructure): restatement of the reference verifier for circuits built from the bench's three gates
-over general-purpose columns, no lookups, no public inputs (the acceptance oracle of the prove -> verify tests).
+over general-purpose columns, optionally with the bench's lookup argument over specialised columns (table id in a constant
+column), no public inputs (the acceptance oracle of the prove -> verify tests).
 
 Follows Verifier::verify (src/cs/implementations/verifier.rs:888-2510):
   transcript order :898-1068, alpha-power split :978-1023, quotient identity at z :1144-1828 (gates over general purpose
-  columns :1646-1700, z(1)=1 :1708-1722, copy-permutation relations :1724-1768, t_from_chunks :1772-1790),
+  columns :1646-1700, z(1)=1 :1708-1722, copy-permutation relations :1724-1768, t_from_chunks :1772-1790; lookup
+  sumcheck at 0 and relations at z :1238-1560),
   DEEP regrouping + FRI chain :1817-2510 (shared with oracle/replay.py, which proof.json pins).
 Gate terms at z use the same formulas as oracle/gates.py, lifted to Fp2.
 """
