@@ -24,26 +24,13 @@ __global__ void __launch_bounds__(128) poseidon2_leaf_kernel(const u64* const* _
   const u64 total = (u64)n_src << log_epl;
   const u64 epl_mask = (1ull << log_epl) - 1;
   const u64 row0 = m << log_epl;
-  u64 i = 0;
-  for (; i + 8 <= total; i += 8) {
+  // one loop (a single inlined copy of the permutation): the last block is zero-filled when it is partial
+  for (u64 i = 0; i < total; i += 8) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const u64 idx = i + k;
-      const u64* col = srcs[idx >> log_epl];
-      st[k] = col[row0 + (idx & epl_mask)];
-    }
-    poseidon2_permutation(st);
-  }
-  if (i < total) {
-    const int f = (int)(total - i);
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
       u64 v = 0;
-      if (k < f) {
-        const u64 idx = i + k;
-        const u64* col = srcs[idx >> log_epl];
-        v = col[row0 + (idx & epl_mask)];
-      }
+      if (idx < total) v = srcs[idx >> log_epl][row0 + (idx & epl_mask)];
       st[k] = v;
     }
     poseidon2_permutation(st);
@@ -83,13 +70,7 @@ __global__ void __launch_bounds__(128) poseidon2_rows_kernel(const u64* __restri
   u64 st[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) st[i] = 0;
-  u32 i = 0;
-  for (; i + 8 <= row_len; i += 8) {
-#pragma unroll
-    for (int k = 0; k < 8; k++) st[k] = row[i + k];
-    poseidon2_permutation(st);
-  }
-  if (i < row_len) {
+  for (u32 i = 0; i < row_len; i += 8) {
 #pragma unroll
     for (int k = 0; k < 8; k++) st[k] = (i + k < row_len) ? row[i + k] : 0;
     poseidon2_permutation(st);
@@ -110,7 +91,7 @@ __global__ void __launch_bounds__(128) poseidon2_permute_kernel(u64* __restrict_
 }
 
 int32_t poseidon2_init_constants(bj_ctx* ctx) {
-  BJ_CUDA(ctx, cudaMemcpyToSymbol(c_poseidon_rc, BJ_POSEIDON_RC_HOST, sizeof(u64) * 360));
+  BJ_CUDA(ctx, cudaMemcpyToSymbol(c_poseidon_layer_rc, p2_layer_constants_host().v, sizeof(u64) * 31 * 12));
   return BJ_OK;
 }
 

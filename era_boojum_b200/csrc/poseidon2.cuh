@@ -10,12 +10,39 @@
 namespace bj {
 using gl::u64;
 
-__constant__ u64 c_poseidon_rc[360];
+// "Constants added after linear layer k": the round constants of round r are folded into the linear layer that ends
+// round r-1 (layer 0 is the initial M_E).  Layers are numbered 0..30 in execution order: layer 0 = initial external,
+// layers 1..4 = after full rounds 0..3, layers 5..26 = after partial rounds 4..25, layers 27..30 = after full rounds
+// 26..29.  Row k holds the 12 constants to add (zeros where the next round takes none), so every layer has one code shape.
+__constant__ u64 c_poseidon_layer_rc[31 * 12];
+
+struct P2LayerConstants {
+  u64 v[31 * 12];
+};
+inline P2LayerConstants make_p2_layer_constants() {
+  P2LayerConstants t;
+  for (int k = 0; k < 31; k++) {
+    const int next_round = k;  // layer k is followed by round k (k = 30: nothing follows)
+    for (int i = 0; i < 12; i++) {
+      u64 c = 0;
+      if (next_round < 30) {
+        const bool full = next_round < 4 || next_round >= 26;
+        if (full || i == 0) c = BJ_POSEIDON_RC_HOST[next_round * 12 + i];
+      }
+      t.v[k * 12 + i] = c;
+    }
+  }
+  return t;
+}
+inline const P2LayerConstants& p2_layer_constants_host() {
+  static const P2LayerConstants t = make_p2_layer_constants();
+  return t;
+}
 
 #ifdef __CUDA_ARCH__
-#define BJ_P2_RC(i) c_poseidon_rc[(i)]
+#define BJ_P2_LRC(i) c_poseidon_layer_rc[(i)]
 #else
-#define BJ_P2_RC(i) BJ_POSEIDON_RC_HOST[(i)]
+#define BJ_P2_LRC(i) p2_layer_constants_host().v[(i)]
 #endif
 
 // All state values are LAZY (any u64 congruent mod p) throughout the permutation: the linear layers sum in 96-bit
@@ -37,9 +64,8 @@ __host__ __device__ __forceinline__ void p2_m4_wide(u64 x0, u64 x1, u64 x2, u64 
   y[3] = t4;
 }
 
-// s <- circ(2 M4, M4, M4) s  (+ optional round constants of the NEXT full round folded into the same reduction)
-template <bool ADD_RC>
-__host__ __device__ __forceinline__ void p2_external(u64 (&s)[12], int rc_base) {
+// s <- circ(2 M4, M4, M4) s + constants of layer `layer`
+__host__ __device__ __forceinline__ void p2_external(u64 (&s)[12], int layer) {
   gl::w96 b[3][4];
   p2_m4_wide(s[0], s[1], s[2], s[3], b[0]);
   p2_m4_wide(s[4], s[5], s[6], s[7], b[1]);
@@ -48,11 +74,8 @@ __host__ __device__ __forceinline__ void p2_external(u64 (&s)[12], int rc_base) 
   for (int i = 0; i < 4; i++) {
     const gl::w96 sum = gl::w96_add(gl::w96_add(b[0][i], b[1][i]), b[2][i]);
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      gl::w96 v = gl::w96_add(b[k][i], sum);
-      if (ADD_RC) v = gl::w96_add64(v, BJ_P2_RC(rc_base + 4 * k + i));
-      s[4 * k + i] = gl::w96_reduce(v);
-    }
+    for (int k = 0; k < 3; k++)
+      s[4 * k + i] = gl::w96_reduce(gl::w96_add64(gl::w96_add(b[k][i], sum), BJ_P2_LRC(layer * 12 + 4 * k + i)));
   }
 }
 
@@ -61,56 +84,37 @@ __host__ __device__ __forceinline__ u64 p2_pow7(u64 x) {
   return gl::mul_lazy(x4, x3);
 }
 
-// s <- (diag(2^sh) + J) s, optionally adding the next partial round's constant to s[0]
-template <bool ADD_RC>
-__host__ __device__ __forceinline__ void p2_internal(u64 (&s)[12], int rc_idx) {
+// s <- (diag(2^sh) + J) s + constants of layer `layer`; `x7` = new s[0] (S-box output), rest_sum = s[1] + ... + s[11]
+// (computed by the caller before the S-box so that it is off the critical path)
+__host__ __device__ __forceinline__ void p2_internal(u64 (&s)[12], gl::w96 rest_sum, int layer) {
   constexpr unsigned SH[12] = {4, 14, 11, 8, 0, 5, 2, 9, 13, 6, 3, 12};
-  gl::w96 sum = gl::w96_from(s[0]);
+  const u64 sr = gl::w96_reduce(gl::w96_add64(rest_sum, s[0]));
 #pragma unroll
-  for (int i = 1; i < 12; i++) sum = gl::w96_add64(sum, s[i]);
-  const u64 sr = gl::w96_reduce(sum);
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    gl::w96 v = gl::w96_add64(gl::w96_from_shl(s[i], SH[i]), sr);
-    if (ADD_RC && i == 0) v = gl::w96_add64(v, BJ_P2_RC(rc_idx));
-    s[i] = gl::w96_reduce(v);
-  }
+  for (int i = 0; i < 12; i++)
+    s[i] = gl::w96_reduce(gl::w96_add64(gl::w96_add64(gl::w96_from_shl(s[i], SH[i]), sr), BJ_P2_LRC(layer * 12 + i)));
 }
 
-// rounds r = 0..29 with one running constant index (state_generic_impl.rs:219-233); the constants of round r are added
-// inside the linear layer that ends round r-1
+// 30 rounds (4 full, 22 partial, 4 full; state_generic_impl.rs:219-233) as ONE loop with two bodies so that the code
+// stays inside the instruction cache; layer k's constants are those of round k.
 __host__ __device__ __forceinline__ void poseidon2_permutation(u64 (&s)[12]) {
-  p2_external<true>(s, 0);  // initial M_E, + RC of full round 0
+  p2_external(s, 0);
 #pragma unroll 1
-  for (int r = 0; r < 4; r++) {
+  for (int r = 0; r < 30; r++) {
+    if (r < 4 || r >= 26) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = p2_pow7(s[i]);
-    if (r < 3) {
-      p2_external<true>(s, (r + 1) * 12);
+      for (int i = 0; i < 12; i++) s[i] = p2_pow7(s[i]);
+      p2_external(s, r + 1);
     } else {
-      // next is partial round 4: only s[0] receives a constant
-      p2_external<false>(s, 0);
-      s[0] = gl::w96_reduce(gl::w96_add64(gl::w96_from(s[0]), BJ_P2_RC(4 * 12)));
+      gl::w96 rest = gl::w96_add64(gl::w96_from(s[1]), s[2]);
+      gl::w96 rest2 = gl::w96_add64(gl::w96_from(s[3]), s[4]);
+      gl::w96 rest3 = gl::w96_add64(gl::w96_from(s[5]), s[6]);
+      gl::w96 rest4 = gl::w96_add64(gl::w96_from(s[7]), s[8]);
+      rest = gl::w96_add64(gl::w96_add64(rest, s[9]), s[10]);
+      rest2 = gl::w96_add64(gl::w96_add(rest2, rest3), s[11]);
+      rest = gl::w96_add(gl::w96_add(rest, rest2), rest4);
+      s[0] = p2_pow7(s[0]);
+      p2_internal(s, rest, r + 1);
     }
-  }
-#pragma unroll 1
-  for (int r = 4; r < 26; r++) {
-    s[0] = p2_pow7(s[0]);
-    if (r < 25) {
-      p2_internal<true>(s, (r + 1) * 12);
-    } else {
-      // next is full round 26: every word receives a constant
-      p2_internal<false>(s, 0);
-#pragma unroll
-      for (int i = 0; i < 12; i++) s[i] = gl::w96_reduce(gl::w96_add64(gl::w96_from(s[i]), BJ_P2_RC(26 * 12 + i)));
-    }
-  }
-#pragma unroll 1
-  for (int r = 26; r < 30; r++) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = p2_pow7(s[i]);
-    if (r < 29) p2_external<true>(s, (r + 1) * 12);
-    else p2_external<false>(s, 0);
   }
 }
 
