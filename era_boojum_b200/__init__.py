@@ -180,6 +180,14 @@ class Context:
     def synchronize(self):
         self._check(lib.bj_ctx_synchronize(self._h))
 
+    shard_rank, shard_world = 0, 1
+
+    def set_coset_shard(self, rank, world, lde_degree):
+        """bj_ctx_set_coset_shard: this context holds the LDE cosets j = rank (mod world) of every committed polynomial
+        (multi-GPU proving, one process per GPU).  Sizes passed to the C-ABI stay global; tensors are local."""
+        self._check(lib.bj_ctx_set_coset_shard(self._h, rank, world, lde_degree.bit_length() - 1))
+        self.shard_rank, self.shard_world = rank, world
+
     def launch_count(self):
         return int(lib.bj_launch_count(self._h))
 
@@ -220,8 +228,8 @@ class Context:
         """[n_cols, n] Lagrange values -> [n_cols, lde_degree, n] (coset-major, bit-reversed in coset)."""
         log_n, n_cols, n = self._cols(cols)
         log_l = lde_degree.bit_length() - 1
-        if out is None:
-            out = self._torch.empty((n_cols, lde_degree, n), dtype=self._torch.int64, device=cols.device)
+        if out is None:   # a coset shard produces only its own lde_degree / world cosets
+            out = self._torch.empty((n_cols, lde_degree // self.shard_world, n), dtype=self._torch.int64, device=cols.device)
         self._check(lib.bj_lde(self._h, self._ptr(cols), n, self._ptr(out), log_n, log_l, n_cols, int(from_monomials)))
         return out
 
@@ -272,7 +280,7 @@ class Context:
         vals = (ctypes.c_uint64 * (2 * n_src))(*[int(x) for v in values_at for x in v])
         chs = (ctypes.c_uint64 * (2 * n_src))(*[int(x) for v in challenges for x in v])
         at_ = (ctypes.c_uint64 * 2)(int(at[0]), int(at[1]))
-        log_rows = acc_c0.numel().bit_length() - 1
+        log_rows = (acc_c0.numel() * self.shard_world).bit_length() - 1      # global domain size
         self._check(lib.bj_deep_quotient_group(self._h, p0, p1, n_src, vals, chs, at_, log_rows,
                                                self._ptr(acc_c0), self._ptr(acc_c1)))
         return acc_c0, acc_c1
@@ -433,7 +441,7 @@ class Context:
         """One oracle step (log_fold folds).  Returns (out_c0, out_c1, new_coset_inv)."""
         torch = self._torch
         m = c0.numel()
-        log_m = m.bit_length() - 1
+        log_m = (m * self.shard_world).bit_length() - 1                      # global vector size
         o0 = torch.empty(m >> log_fold, dtype=torch.int64, device=c0.device)
         o1 = torch.empty(m >> log_fold, dtype=torch.int64, device=c0.device)
         al = (ctypes.c_uint64 * 2)(alpha[0], alpha[1])

@@ -139,6 +139,18 @@ int32_t bj_ctx_set_stream(bj_ctx* ctx, void* stream) {
   return BJ_OK;
 }
 
+int32_t bj_ctx_set_coset_shard(bj_ctx* ctx, uint32_t rank, uint32_t world, uint32_t log_lde) {
+  if (!ctx) return BJ_ERR_INVALID_ARG;
+  if (world == 0 || (world & (world - 1)) || rank >= world || log_lde > 16 || world > (1u << log_lde))
+    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_ctx_set_coset_shard: world must be a power of two <= the LDE factor and rank < world");
+  uint32_t ls = 0;
+  while ((1u << ls) < world) ls++;
+  ctx->shard_log_lde = log_lde;
+  ctx->shard.first = rank;
+  ctx->shard.log_stride = ls;
+  return BJ_OK;
+}
+
 int32_t bj_ctx_synchronize(bj_ctx* ctx) {
   if (!ctx) return BJ_ERR_INVALID_ARG;
   BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -22,6 +22,25 @@ struct PowTab {
   u64* hi;
 };
 
+// Coset shard of a multi-GPU prover: LDE-domain buffers of this context hold only the cosets j = first + k * 2^log_stride
+// (k = 0, 1, ...), stored [local coset k][row].  A local flat index [k | i] maps to the global index [k | first | i].
+struct CosetShard {
+  uint32_t first = 0;
+  uint32_t log_stride = 0;
+  __host__ __device__ __forceinline__ u64 global_index(u64 t_loc, int log_coset_len) const {
+    if (log_stride == 0) return t_loc;
+    const u64 i = t_loc & ((1ull << log_coset_len) - 1);
+    const u64 k = t_loc >> log_coset_len;
+    return ((((k << log_stride) | first)) << log_coset_len) | i;
+  }
+  // how many of the first `group` (power of two) global cosets are local
+  __host__ __device__ __forceinline__ u64 local_cosets(u64 group) const {
+    const u64 stride = 1ull << log_stride;
+    if (group >= stride) return group >> log_stride;
+    return first < group ? 1 : 0;
+  }
+};
+
 }  // namespace bj
 
 struct bj_ctx {
@@ -54,6 +73,8 @@ struct bj_ctx {
   int ntt_max_tile_log = 13;  // tunables (env BJ_NTT_*)
   int ntt_pass1_w = -1;
   int ntt_chunk_mb = 0;
+  bj::CosetShard shard;  // bj_ctx_set_coset_shard; default = the whole domain
+  uint32_t shard_log_lde = 0;  // LDE factor the shard was declared for (locates the coset bits of flat indices)
 };
 
 #define BJ_FAIL(ctx, code, msg)          \

@@ -108,8 +108,10 @@ struct DeepParams {
   const u64* const* src_c1;  // n_src device pointers, NULL entry = base-field column
   const u64* ch;             // n_src (c0, c1) challenge coefficients
   u32 n_src;
-  u64 n_rows;                // n * L
-  const u64* tab;            // forward twiddles, >= n_rows / 2 entries
+  u64 n_rows;                // n * (local cosets)
+  int log_n;                 // coset length (locates the coset bits when the context holds a coset shard)
+  CosetShard shard;
+  const u64* tab;            // forward twiddles of the whole LDE domain
   gl::e2 at;
   gl::e2 k_const;            // sum_i ch_i * value_at_i  (precomputed on the host)
   u64* acc_c0;
@@ -156,8 +158,9 @@ __global__ void __launch_bounds__(256) deep_group_kernel(const DeepParams p) {
     const u64 t = t0 + r * stride;
     pre[r] = acc;
     if (t < p.n_rows) {
-      u64 x = gl::mul(__ldg(p.tab + (t >> 1)), gl::MULT_GEN);
-      if (t & 1) x = gl::neg(x);
+      const u64 tg = p.shard.global_index(t, p.log_n);
+      u64 x = gl::mul(__ldg(p.tab + (tg >> 1)), gl::MULT_GEN);
+      if (tg & 1) x = gl::neg(x);
       den[r] = {gl::canon(gl::sub(x, p.at.c0)), neg_at1};
       acc = gl::e2_mul(acc, den[r]);
     }
@@ -249,6 +252,13 @@ int32_t bj_deep_quotient_group(bj_ctx* ctx, const uint64_t* const* h_src_c0, con
   p.ch = (const u64*)dch;
   p.n_src = n_src;
   p.n_rows = 1ull << log_rows;
+  p.log_n = (int)log_rows;
+  p.shard = ctx->shard;
+  if (ctx->shard.log_stride) {
+    if (log_rows < ctx->shard_log_lde + 1) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_deep_quotient_group: domain smaller than the sharded LDE factor");
+    p.log_n = (int)(log_rows - ctx->shard_log_lde);
+    p.n_rows = ctx->shard.local_cosets(1ull << ctx->shard_log_lde) << p.log_n;
+  }
   p.tab = ctx->tw_fwd;
   p.at = {gl::canon(h_at[0]), gl::canon(h_at[1])};
   p.k_const = k;

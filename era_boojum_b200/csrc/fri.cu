@@ -12,6 +12,8 @@ namespace bj {
 struct FoldParams {
   gl::e2 alpha[3];
   u64 kappa[3];
+  CosetShard shard;   // coset shard of a multi-GPU prover: local pair indices are mapped to global ones for the roots
+  int log_coset_out;  // log2 of the coset length of the OUTPUT vector
 };
 
 template <int K>
@@ -37,7 +39,8 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const u64* __restrict__ c
     const int cnt = N >> (l + 1);  // outputs of this level held by the thread
 #pragma unroll
     for (int j = 0; j < cnt; j++) {
-      const u64 gidx = o * cnt + j;
+      // pair index at this level: the level's output vector has cosets of 2^(log_coset_out + log2(cnt)) elements
+      const u64 gidx = fp.shard.global_index(o * cnt + j, fp.log_coset_out + (K - 1 - l));
       const u64 r = gl::mul(__ldg(roots + gidx), fp.kappa[l]);
       const u64 x0 = a0[2 * j], y0 = a0[2 * j + 1], x1 = a1[2 * j], y1 = a1[2 * j + 1];
       gl::e2 d = {gl::mul(gl::sub(x0, y0), r), gl::mul(gl::sub(x1, y1), r)};
@@ -74,7 +77,15 @@ extern "C" int32_t bj_fri_fold(bj_ctx* ctx, const uint64_t* d_c0, const uint64_t
       kappa = gl::sqr(kappa);
     }
   }
-  const u64 n_out = 1ull << (log_m - log_fold);
+  u64 n_out = 1ull << (log_m - log_fold);
+  fp.shard = ctx->shard;
+  fp.log_coset_out = 0;
+  if (ctx->shard.log_stride) {
+    // local vectors hold the owned cosets only; a fold never crosses a coset while the folded coset is >= 1 element
+    if (log_m < ctx->shard_log_lde + log_fold) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_fri_fold: fold would cross cosets of the shard");
+    fp.log_coset_out = (int)(log_m - log_fold - ctx->shard_log_lde);
+    n_out = ctx->shard.local_cosets(1ull << ctx->shard_log_lde) << fp.log_coset_out;
+  }
   const unsigned blocks = (unsigned)((n_out + 255) / 256);
   const u64* roots = ctx->tw_inv;
   switch (log_fold) {

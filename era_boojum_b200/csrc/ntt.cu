@@ -537,6 +537,9 @@ int32_t bj_lde(bj_ctx* ctx, const uint64_t* d_in, uint64_t in_col_stride, uint64
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_lde: bad argument");
   if (n_cols == 0) return BJ_OK;
   const u64 n = 1ull << log_n, L = 1ull << log_lde;
+  if (ctx->shard.log_stride && log_lde != ctx->shard_log_lde)
+    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_lde: LDE factor differs from the one the coset shard was declared for");
+  const u64 L_loc = ctx->shard.local_cosets(L);  // cosets owned by this context (all of them without a shard)
   const int m = (int)log_n;
   // per chunk of columns: monomials (natural order) in scratch, then one forward transform per coset that
   // reads the monomials and writes straight into the coset's slot of d_out.
@@ -556,12 +559,13 @@ int32_t bj_lde(bj_ctx* ctx, const uint64_t* d_in, uint64_t in_col_stride, uint64
       mono = mbuf;
       mono_stride = n;
     }
-    for (u64 j = 0; j < L; j++) {
+    for (u64 k = 0; k < L_loc; k++) {
+      const u64 j = (k << ctx->shard.log_stride) | ctx->shard.first;  // global coset of local slot k
       u64 jr = 0;
       for (uint32_t b = 0; b < log_lde; b++) jr |= ((j >> b) & 1) << (log_lde - 1 - b);
       const u64 shift = gl::mul(gl::MULT_GEN, gl::pow(w_big, jr));
-      u64* out = (u64*)d_out + ((u64)c0 * L + j) * n;
-      BJ_TRY(run_transform(ctx, mono, mono_stride, out, n * L, m, cnt, shift, false, nullptr, 0));
+      u64* out = (u64*)d_out + ((u64)c0 * L_loc + k) * n;
+      BJ_TRY(run_transform(ctx, mono, mono_stride, out, n * L_loc, m, cnt, shift, false, nullptr, 0));
     }
   }
   return BJ_OK;

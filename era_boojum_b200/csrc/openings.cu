@@ -84,6 +84,7 @@ extern "C" int32_t bj_barycentric_evaluate(bj_ctx* ctx, const uint64_t* const* h
                                            const uint64_t h_at[2], uint64_t* h_out) {
   if (!ctx || !h_cols || !h_at || !h_out || n_cols == 0 || log_n > 32)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_barycentric_evaluate: bad argument");
+  if (ctx->shard.first != 0) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_barycentric_evaluate: coset 0 belongs to shard rank 0");
   const u64 n = 1ull << log_n;
   BJ_TRY(ensure_twiddles(ctx, (int)log_n));
   const gl::e2 at = {gl::canon(h_at[0]), gl::canon(h_at[1])};

@@ -26,7 +26,8 @@ struct QCopyPermParams {
   const u64* tab;              // forward twiddles of the full LDE domain
   const u64* coset_xn_minus_1; // per coset: x^n - 1
   int log_n;
-  u64 n_points;                // Q * n
+  u64 n_points;                // (local cosets among the first Q) * n
+  CosetShard shard;
   u64* q_c0;
   u64* q_c1;
 };
@@ -35,14 +36,15 @@ __global__ void __launch_bounds__(128) quotient_copy_perm_kernel(const QCopyPerm
   const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= p.n_points) return;
   const u64 n = 1ull << p.log_n;
-  const u64 coset = t >> p.log_n, i = t & (n - 1);
-  u64 x = gl::mul(__ldg(p.tab + (t >> 1)), gl::MULT_GEN);
-  if (t & 1) x = gl::neg(x);
+  const u64 coset = t >> p.log_n, i = t & (n - 1);   // local coset slot
+  const u64 tg = p.shard.global_index(t, p.log_n);   // index in the whole LDE domain
+  u64 x = gl::mul(__ldg(p.tab + (tg >> 1)), gl::MULT_GEN);
+  if (tg & 1) x = gl::neg(x);
   const gl::e2 z = {p.z_c0[t], p.z_c1[t]};
   gl::e2 q = {0, 0};
   {
     // alpha_0 * (z - 1) * (x^n - 1) / (x - 1)
-    const u64 l1 = gl::mul(__ldg(p.coset_xn_minus_1 + coset), gl_inv_chain(gl::canon(gl::sub(x, 1))));
+    const u64 l1 = gl::mul(__ldg(p.coset_xn_minus_1 + (tg >> p.log_n)), gl_inv_chain(gl::canon(gl::sub(x, 1))));
     gl::e2 v = {gl::mul(gl::sub(z.c0, 1), l1), gl::mul(z.c1, l1)};
     q = gl::e2_mul(v, {__ldg(p.alphas), __ldg(p.alphas + 1)});
   }
@@ -85,10 +87,10 @@ __global__ void __launch_bounds__(128) quotient_copy_perm_kernel(const QCopyPerm
 }
 
 __global__ void __launch_bounds__(256) scale_by_coset_constant_kernel(u64* __restrict__ c0, u64* __restrict__ c1, int log_n,
-                                                                       u64 n_points, const u64* __restrict__ per_coset) {
+                                                                       u64 n_points, const u64* __restrict__ per_coset, CosetShard shard) {
   const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_points) return;
-  const u64 m = __ldg(per_coset + (t >> log_n));
+  const u64 m = __ldg(per_coset + (shard.global_index(t, log_n) >> log_n));
   c0[t] = gl::mul(c0[t], m);
   c1[t] = gl::mul(c1[t], m);
 }
@@ -154,7 +156,9 @@ int32_t bj_quotient_copy_permutation(bj_ctx* ctx, const uint64_t* const* h_varia
   p.gamma = {gl::canon(h_gamma[0]), gl::canon(h_gamma[1])};
   p.tab = ctx->tw_fwd;
   p.log_n = (int)log_n;
-  p.n_points = 1ull << (log_n + log_quotient_degree);
+  p.shard = ctx->shard;
+  p.n_points = ctx->shard.local_cosets(1ull << log_quotient_degree) << log_n;
+  if (p.n_points == 0) return BJ_OK;  // this shard owns none of the quotient cosets
   p.q_c0 = (u64*)d_q_c0;
   p.q_c1 = (u64*)d_q_c1;
   quotient_copy_perm_kernel<<<(unsigned)((p.n_points + 127) / 128), 128, 0, ctx->stream>>>(p);
@@ -171,9 +175,10 @@ int32_t bj_quotient_divide_by_vanishing(bj_ctx* ctx, uint64_t* d_q_c0, uint64_t*
   for (auto& v : van) v = gl::inv(v);
   void* d;
   BJ_TRY(param_upload(ctx, van.data(), sizeof(u64) * van.size(), &d));
-  const u64 n_points = 1ull << (log_n + log_quotient_degree);
+  const u64 n_points = ctx->shard.local_cosets(1ull << log_quotient_degree) << log_n;
+  if (n_points == 0) return BJ_OK;
   scale_by_coset_constant_kernel<<<(unsigned)((n_points + 255) / 256), 256, 0, ctx->stream>>>((u64*)d_q_c0, (u64*)d_q_c1, (int)log_n, n_points,
-                                                                                              (const u64*)d);
+                                                                                              (const u64*)d, ctx->shard);
   BJ_LAUNCH_CHECK(ctx);
   return BJ_OK;
 }

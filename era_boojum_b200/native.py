@@ -44,6 +44,7 @@ SIGNATURES = {
     "bj_ctx_create": (_i32, [_i32, _vp, _pp]),
     "bj_ctx_destroy": (_i32, [_vp]),
     "bj_ctx_set_stream": (_i32, [_vp, _vp]),
+    "bj_ctx_set_coset_shard": (_i32, [_vp, _u32, _u32, _u32]),
     "bj_ctx_synchronize": (_i32, [_vp]),
     "bj_last_error": (ctypes.c_char_p, [_vp]),
     "bj_launch_count": (_u64, [_vp]),

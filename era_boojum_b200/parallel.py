@@ -139,3 +139,106 @@ def commit_sharded(backend, dist, local_cols, n_cols_total, lde_factor, cap_size
     if cap_size < lde_factor:
         raise NotImplementedError("cap_size < lde_factor: hash the gathered coset roots down to the cap")
     return {"cosets": cosets, "trees": trees, "cap": cap}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Coset-sharded PROVING (era_boojum_b200.prover.prove with comm=...): every rank holds the full witness and the cosets
+# j = rank (mod world) of every committed polynomial (Context.set_coset_shard).  What crosses ranks:
+#   * cap digests of every oracle (32 bytes each) - all ranks replay the same transcript;
+#   * the quotient values on the first Q cosets (2 * Q * n u64, one all-reduce) - the one step where the owned cosets have
+#     to recombine, because the quotient is interpolated at size n*Q (src/cs/implementations/prover.rs:1399-1467);
+#   * the openings at z (computed by the owner of coset 0), the last FRI codeword (a few KiB), and the query answers.
+# ---------------------------------------------------------------------------------------------------------------------
+class LocalComm:
+    """world of one (single GPU): the collectives are identities."""
+    rank, world = 0, 1
+
+    def all_gather_host(self, obj):
+        return [obj]
+
+    def all_reduce_sum_(self, t):
+        return t
+
+    def broadcast_host(self, obj, src=0):
+        return obj
+
+
+class TorchDistComm:
+    """one process per GPU over torch.distributed (NCCL on the GPU box)."""
+
+    def __init__(self, dist, group=None):
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_gather_host(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def all_reduce_sum_(self, t):
+        self.dist.all_reduce(t, group=self.group)     # int64 sum; exact here because only one rank holds a non-zero value
+        return t
+
+    def broadcast_host(self, obj, src=0):
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=src, group=self.group)
+        return box[0]
+
+
+class ThreadComm:
+    """`world` ranks as threads of ONE process sharing one GPU - lets a single-GPU test run the sharded prover with
+    real coset shards (each thread owns a Context with its own shard).  ThreadComm(world).rank_view(r) is rank r's handle."""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self._barrier = threading.Barrier(world)
+        self._slots = [None] * world
+
+    def rank_view(self, rank):
+        return _ThreadCommRank(self, rank)
+
+
+class _ThreadCommRank:
+    def __init__(self, shared, rank):
+        self._s, self.rank, self.world = shared, rank, shared.world
+
+    def all_gather_host(self, obj):
+        self._s._slots[self.rank] = obj
+        self._s._barrier.wait()
+        out = list(self._s._slots)
+        self._s._barrier.wait()
+        return out
+
+    def all_reduce_sum_(self, t):
+        parts = self.all_gather_host(t)
+        total = parts[0].clone()
+        for p in parts[1:]:
+            total += p
+        self._s._barrier.wait()      # every rank has enqueued its reads (one shared stream keeps them ordered)
+        t.copy_(total)
+        return t
+
+    def broadcast_host(self, obj, src=0):
+        return self.all_gather_host(obj if self.rank == src else None)[src]
+
+
+def assemble_cap(comm, local_cap, lde_factor, cap_size):
+    """global cap (cap_size digests) from the per-rank caps of the local trees.  A rank's tree covers its cosets
+    [k][row]; with cap_size >= lde_factor every coset ends in cap_size / lde_factor cap nodes, and the cap node c of the
+    global tree belongs to coset c // (cap_size / lde_factor) (leaf index = coset * n + row)."""
+    per = cap_size // lde_factor
+    parts = comm.all_gather_host(np.ascontiguousarray(local_cap))
+    out = np.zeros((cap_size, 4), np.uint64)
+    for r, part in enumerate(parts):
+        part = np.asarray(part, dtype=np.uint64).reshape(-1, 4)
+        for k in range(lde_factor // comm.world):
+            j = k * comm.world + r
+            out[j * per:(j + 1) * per] = part[k * per:(k + 1) * per]
+    return out
+
+
+def local_leaf_index(global_index, log_coset_len, world):
+    """(owner rank, index in the owner's local [k][row] layout) of element `global_index` of a coset-major vector."""
+    j, i = global_index >> log_coset_len, global_index & ((1 << log_coset_len) - 1)
+    return j % world, ((j // world) << log_coset_len) | i

@@ -12,6 +12,7 @@ import time
 import numpy as np
 
 from . import Transcript, to_numpy
+from .parallel import LocalComm, assemble_cap, local_leaf_index
 
 P = 0xFFFFFFFF00000001
 
@@ -56,10 +57,16 @@ class Setup:
     """SetupStorage + setup Merkle tree + the fixed parameters of the VerificationKey (setup.rs:1093-1255,
     verifier.rs:31-79): sigma and constant columns, their LDEs, the tree over [sigmas | constants]."""
 
-    def __init__(self, ctx, sigmas, constants, gates, quotient_degree, config, lookup=None):
+    def __init__(self, ctx, sigmas, constants, gates, quotient_degree, config, lookup=None, comm=None):
         """lookup: None or dict(width, num_repetitions, variables_offset, table_id_column (index into constants),
-        tables=[width + 1, n] tensor of lookup-table setup columns, multiplicities are part of the witness)."""
+        tables=[width + 1, n] tensor of lookup-table setup columns, multiplicities are part of the witness).
+        comm: None (one GPU) or a communicator of era_boojum_b200.parallel - every rank then keeps the LDE cosets
+        j = rank (mod world) only and ctx must carry the matching coset shard (Context.set_coset_shard)."""
         torch = ctx._torch
+        self.comm = comm
+        world = comm.world if comm else 1
+        assert ctx.shard_world == world, "Context.set_coset_shard(rank, world, L) must match the communicator"
+        assert world == 1 or config.merkle_tree_cap_size >= config.fri_lde_factor, "sharded proving needs cap_size >= LDE factor"
         self.gates = gates                      # [dict(name, program..., num_repetitions, selector_path, ...)]
         self.quotient_degree = quotient_degree
         self.config = config
@@ -72,10 +79,12 @@ class Setup:
         self.lookup = lookup
         parts = [sigmas, constants] + ([lookup["tables"]] if lookup else [])
         cols = torch.cat(parts, dim=0).contiguous()
-        self.lde = ctx.transform_raw_storages_to_lde(cols, L)      # [V + C, L, n]
+        self.lde = ctx.transform_raw_storages_to_lde(cols, L)      # [V + C, L / world, n]
         self.tree = ctx.merkle_tree_construct([self.lde[c].reshape(-1) for c in range(cols.shape[0])],
-                                              config.merkle_tree_cap_size)
+                                              config.merkle_tree_cap_size // world)
         self.cap = self.tree.get_cap()
+        if comm:
+            self.cap = assemble_cap(comm, self.cap, L, config.merkle_tree_cap_size)
 
     def sigma_lde(self, j):
         return self.lde[j].reshape(-1)
@@ -97,16 +106,66 @@ class Setup:
                 "setup_merkle_tree_cap": self.cap.tolist()}
 
 
+def _commit(ctx, comm, cols, L, cap):
+    """Merkle oracle over LDE columns: local tree (this rank's cosets) + the global cap."""
+    world = comm.world if comm else 1
+    tree = ctx.merkle_tree_construct(cols, cap // world)
+    local_cap = tree.get_cap()
+    return tree, (assemble_cap(comm, local_cap, L, cap) if comm else local_cap)
+
+
+class _ShardedFri:
+    """do_fri (src/cs/implementations/fri/mod.rs:49-357) over coset shards: folds and oracle subtrees are local (a fold of
+    2^k neighbours never leaves a coset), every oracle cap is gathered so that all ranks draw the same challenges, the last
+    codeword (a few hundred elements) is gathered and interpolated by every rank."""
+
+    def __init__(self, ctx, comm, tr, c0, c1, schedule, L, cap):
+        torch = ctx._torch
+        self.levels, self.caps, self.schedule = [], [], list(schedule)
+        kappa = pow(7, P - 2, P)                                              # coset_inverse (fri/mod.rs:194)
+        cur0, cur1 = c0, c1
+        for k in schedule:
+            tree = ctx.merkle_tree_construct([cur0, cur1], cap // comm.world, elems_per_leaf=1 << k)
+            gcap = assemble_cap(comm, tree.get_cap(), L, cap)
+            tr.witness_merkle_tree_cap(gcap)
+            alpha = tr.get_multiple_challenges_fixed(2)
+            self.levels.append((cur0, cur1, tree, k))
+            self.caps.append(gcap)
+            cur0, cur1, kappa = ctx.fri_fold(cur0, cur1, k, alpha, kappa)
+        # final codeword: local [L / world][m] -> global [L][m] -> monomials (fri/mod.rs:312-334)
+        m = cur0.numel() // (L // comm.world)
+        parts = comm.all_gather_host(np.stack([to_numpy(cur0), to_numpy(cur1)]).reshape(2, L // comm.world, m))
+        full = np.zeros((2, L, m), np.uint64)
+        for r, part in enumerate(parts):
+            for kk in range(L // comm.world):
+                full[:, kk * comm.world + r] = part[:, kk]
+        fin = torch.from_numpy(full.reshape(2, L * m).view(np.int64)).to(c0.device).contiguous()
+        ctx.bitreverse_enumeration_inplace(fin)
+        ctx.ifft_natural_to_natural(fin, pow(kappa, P - 2, P))
+        mono = to_numpy(fin)
+        if mono[:, m:].any():
+            raise ValueError("FRI: folded codeword is not of low degree")
+        self.mono = (mono[0, :m].copy(), mono[1, :m].copy())
+        tr.witness_field_elements(self.mono[0].tolist())
+        tr.witness_field_elements(self.mono[1].tolist())
+
+
 def prove(ctx, setup, variables, timings=None, multiplicities=None):
     """variables: [V, n] int64 CUDA tensor (copy-permutation columns incl. the lookup sub-argument columns, natural row
-    order); multiplicities: [n] tensor when the setup has a lookup argument.  Returns the proof dict."""
+    order); multiplicities: [n] tensor when the setup has a lookup argument.  Returns the proof dict.
+    With setup.comm set (coset-sharded proving, one process per GPU) every rank passes the same full witness, works on
+    its own LDE cosets and returns the same proof."""
     torch = ctx._torch
     cfg = setup.config
+    comm = setup.comm
+    rank, world = (comm.rank, comm.world) if comm else (0, 1)
     L, cap = cfg.fri_lde_factor, cfg.merkle_tree_cap_size
     log_L = L.bit_length() - 1
     V, C, Q = setup.num_variables, setup.num_constants, setup.quotient_degree
     log_n, log_q = setup.log_n, Q.bit_length() - 1
     n = 1 << log_n
+    L_loc = L // world
+    Q_loc = Q // world if Q >= world else (1 if rank < Q else 0)     # owned cosets among the first Q
     dev = variables.device
     tm = timings if timings is not None else {}
 
@@ -121,17 +180,16 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     # ---- round 1: witness commitment (prover.rs:313-353) ----
     t0 = time.perf_counter()
     lk = setup.lookup
-    w_lde = ctx.transform_raw_storages_to_lde(variables, L)                  # [V, L, n]
+    w_lde = ctx.transform_raw_storages_to_lde(variables, L)                  # [V, L_loc, n]
     w_cols = [flat(w_lde[c]) for c in range(V)]
     m_col = None
     if lk:
         m_lde = ctx.transform_raw_storages_to_lde(multiplicities.reshape(1, -1).contiguous(), L)
         m_col = flat(m_lde[0])
-    w_tree = ctx.merkle_tree_construct(w_cols + ([m_col] if lk else []), cap)   # variables | witness (none) | multiplicities
-    w_cap = w_tree.get_cap()
+    w_tree, w_cap = _commit(ctx, comm, w_cols + ([m_col] if lk else []), L, cap)   # variables | witness (none) | multiplicities
     tr.witness_merkle_tree_cap(w_cap)
     mark("1_witness_lde_commit", t0)
-    # ---- round 2: copy-permutation products (prover.rs:360-554) ----
+    # ---- round 2: copy-permutation products (prover.rs:360-554); the trace-domain part is replicated on every rank ----
     t0 = time.perf_counter()
     beta = tr.get_multiple_challenges_fixed(2)
     gamma = tr.get_multiple_challenges_fixed(2)
@@ -150,8 +208,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     st2 = torch.stack([z0, z1] + [t for pr in partials for t in pr] + lk_polys).contiguous()
     s2_lde = ctx.transform_raw_storages_to_lde(st2, L)
     s2_cols = [flat(s2_lde[c]) for c in range(st2.shape[0])]
-    s2_tree = ctx.merkle_tree_construct(s2_cols, cap)
-    s2_cap = s2_tree.get_cap()
+    s2_tree, s2_cap = _commit(ctx, comm, s2_cols, L, cap)
     tr.witness_merkle_tree_cap(s2_cap)
     n_partial = len(partials)
     mark("2_stage2_products_lde_commit", t0)
@@ -165,24 +222,33 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     for _ in range(1, total_terms):
         powers.append(e_mul(powers[-1], alpha))
     npts = n * Q
-    q0 = torch.zeros(npts, dtype=torch.int64, device=dev)
-    q1 = torch.zeros(npts, dtype=torch.int64, device=dev)
     const_cols = [setup.constant_lde(j) for j in range(C)]
     a_off = 2 + 2 * n_partial
-    if lk:
-        a_ldes = [(s2_cols[a_off + 2 * i], s2_cols[a_off + 2 * i + 1]) for i in range(nsub)]
-        b_lde = (s2_cols[a_off + 2 * nsub], s2_cols[a_off + 2 * nsub + 1])
-        ctx.quotient_lookup_specialized([w_cols[voff + i] for i in range(wdt * nsub)], wdt, const_cols[lk["table_id_column"]],
-                                        [setup.table_lde(j) for j in range(wdt + 1)], m_col, a_ldes, b_lde, lookup_beta, lookup_gamma,
-                                        powers[:n_lk_terms], q0, q1)
-    ctx.evaluate_gates_over_general_purpose_columns(setup.gates, w_cols, [], const_cols,
-                                                    powers[n_lk_terms:n_lk_terms + n_gate_terms], q0, q1)
-    part_ldes = [(s2_cols[2 + 2 * c], s2_cols[3 + 2 * c]) for c in range(n_partial)]
-    ctx.quotient_copy_permutation(w_cols, [setup.sigma_lde(j) for j in range(V)], (s2_cols[0], s2_cols[1]), part_ldes, beta, gamma,
-                                  powers[n_lk_terms + n_gate_terms:], log_n, log_L, log_q, Q, q0, q1)
-    ctx.divide_by_vanishing(q0, q1, log_n, log_q)
+    qq = torch.zeros((2, Q, n), dtype=torch.int64, device=dev)          # quotient values on the first Q cosets (global)
+    if Q_loc:
+        # the quotient lives on the first Q cosets = the first Q_loc local slots of every LDE column
+        q0 = torch.zeros(n * Q_loc, dtype=torch.int64, device=dev)
+        q1 = torch.zeros(n * Q_loc, dtype=torch.int64, device=dev)
+        if lk:
+            a_ldes = [(s2_cols[a_off + 2 * i], s2_cols[a_off + 2 * i + 1]) for i in range(nsub)]
+            b_lde = (s2_cols[a_off + 2 * nsub], s2_cols[a_off + 2 * nsub + 1])
+            ctx.quotient_lookup_specialized([w_cols[voff + i] for i in range(wdt * nsub)], wdt, const_cols[lk["table_id_column"]],
+                                            [setup.table_lde(j) for j in range(wdt + 1)], m_col, a_ldes, b_lde, lookup_beta, lookup_gamma,
+                                            powers[:n_lk_terms], q0, q1)
+        ctx.evaluate_gates_over_general_purpose_columns(setup.gates, w_cols, [], const_cols,
+                                                        powers[n_lk_terms:n_lk_terms + n_gate_terms], q0, q1)
+        part_ldes = [(s2_cols[2 + 2 * c], s2_cols[3 + 2 * c]) for c in range(n_partial)]
+        ctx.quotient_copy_permutation(w_cols, [setup.sigma_lde(j) for j in range(V)], (s2_cols[0], s2_cols[1]), part_ldes, beta, gamma,
+                                      powers[n_lk_terms + n_gate_terms:], log_n, log_L, log_q, Q, q0, q1)
+        ctx.divide_by_vanishing(q0, q1, log_n, log_q)
+        for k in range(Q_loc):                                              # local slot k = global coset k * world + rank
+            qq[0, k * world + rank] = q0[k * n:(k + 1) * n]
+            qq[1, k * world + rank] = q1[k * n:(k + 1) * n]
+        del q0, q1
+    if comm:
+        comm.all_reduce_sum_(qq)          # the cosets recombine here: every rank needs all Q of them for the interpolation
     # flatten the cosets into natural order, interpolate once at size n*Q on coset 7, split into Q chunks (prover.rs:1399-1467)
-    qq = torch.stack([q0, q1]).contiguous()
+    qq = qq.reshape(2, npts)
     ctx.bitreverse_enumeration_inplace(qq)
     ctx.ifft_natural_to_natural(qq, 7)
     # the reference's satisfiability guard: the top coefficient of the interpolant must vanish (prover.rs:1425-1438)
@@ -192,8 +258,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     chunks = torch.stack([qq[k][j * n:(j + 1) * n] for j in range(Q) for k in (0, 1)]).contiguous()   # c0,c1 of chunk 0, ...
     qt_lde = ctx.transform_raw_storages_to_lde(chunks, L, from_monomials=True)
     qt_cols = [flat(qt_lde[c]) for c in range(2 * Q)]
-    qt_tree = ctx.merkle_tree_construct(qt_cols, cap)
-    qt_cap = qt_tree.get_cap()
+    qt_tree, qt_cap = _commit(ctx, comm, qt_cols, L, cap)
     tr.witness_merkle_tree_cap(qt_cap)
     mark("3_quotient", t0)
     # ---- round 4: openings (prover.rs:1501-1802) ----
@@ -219,10 +284,13 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
         ev = ctx.barycentric_evaluate(flat_cols, log_n, at)
         return [(_combine_ext(ev[i], ev[i + 1]) if is_ext else ev[i]) for i, is_ext in spans]
 
-    values_at_z = open_at(sources, z)
-    values_at_z_omega = open_at([(s2_cols[0], s2_cols[1])], z_omega)
     zero_sources = [(s2_cols[a_off + 2 * i], s2_cols[a_off + 2 * i + 1]) for i in range(nsub + 1)] if lk else []
-    values_at_0 = open_at(zero_sources, (0, 0)) if lk else []
+    opened = None
+    if rank == 0:                          # barycentric evaluation reads coset 0, which rank 0 owns
+        opened = (open_at(sources, z), open_at([(s2_cols[0], s2_cols[1])], z_omega), open_at(zero_sources, (0, 0)) if lk else [])
+    if comm:
+        opened = comm.broadcast_host(opened, 0)
+    values_at_z, values_at_z_omega, values_at_0 = opened
     for v in values_at_z + values_at_z_omega + values_at_0:
         tr.witness_field_elements(v)
     mark("4_openings", t0)
@@ -233,8 +301,8 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     ch = [(1, 0), c]
     for _ in range(2, n_ch):
         ch.append(e_mul(ch[-1], c))
-    deep0 = torch.zeros(n * L, dtype=torch.int64, device=dev)
-    deep1 = torch.zeros(n * L, dtype=torch.int64, device=dev)
+    deep0 = torch.zeros(n * L_loc, dtype=torch.int64, device=dev)
+    deep1 = torch.zeros(n * L_loc, dtype=torch.int64, device=dev)
     ctx.quotening_operation_in_extension(deep0, deep1, sources, values_at_z, z, ch[:len(sources)])
     ctx.quotening_operation_in_extension(deep0, deep1, [(s2_cols[0], s2_cols[1])], values_at_z_omega, z_omega,
                                          ch[len(sources):len(sources) + 1])
@@ -248,27 +316,48 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
                                        sched, ctypes.byref(sl), ctypes.byref(fd)) == 0
     assert np_.value == 0, "PoW is not implemented (benches use NoPow)"
     schedule = list(sched[: sl.value])
-    fri = ctx.do_fri(tr, deep0, deep1, schedule, L, cap)
-    mono0, mono1 = fri.monomial_forms()
+    if comm:
+        fri = _ShardedFri(ctx, comm, tr, deep0, deep1, schedule, L, cap)
+        mono0, mono1 = fri.mono
+        fri_caps = fri.caps
+    else:
+        fri = ctx.do_fri(tr, deep0, deep1, schedule, L, cap)
+        mono0, mono1 = fri.monomial_forms()
+        fri_caps = [fri.get_cap(i) for i in range(fri.num_oracles())]
     mark("5_deep_fri", t0)
-    # ---- queries (prover.rs:2161-2266) ----
+    # ---- queries (prover.rs:2161-2266): a query is answered by the rank that owns the coset of its index ----
     t0 = time.perf_counter()
     max_bits = log_n + log_L
     idxs = [tr.get_index_bits(max_bits, max_bits) for _ in range(nq.value)]
     setup_cols = [setup.lde[c].reshape(-1) for c in range(setup.lde.shape[0])]
     oracles = [("witness_query", w_cols + ([m_col] if lk else []), w_tree), ("stage_2_query", s2_cols, s2_tree), ("quotient_query", qt_cols, qt_tree),
                ("setup_query", setup_cols, setup.tree)]
-    rows = {name: (ctx.query_leaf_elements(cols, idxs), ctx.merkle_paths(tree, idxs)) for name, cols, tree in oracles}
-    queries = []
-    for qi, idx in enumerate(idxs):
-        q = {name: {"leaf_elements": rows[name][0][qi].tolist(), "proof": rows[name][1][qi].tolist()} for name, _, _ in oracles}
-        fqs, sub = [], idx
+    mine = [(qi, idx) for qi, idx in enumerate(idxs) if local_leaf_index(idx, log_n, world)[0] == rank]
+    loc = [local_leaf_index(idx, log_n, world)[1] for _, idx in mine]
+    rows = {name: (ctx.query_leaf_elements(cols, loc), ctx.merkle_paths(tree, loc)) for name, cols, tree in oracles} if mine else {}
+    answered = {}
+    for pos, (qi, idx) in enumerate(mine):
+        q = {name: {"leaf_elements": rows[name][0][pos].tolist(), "proof": rows[name][1][pos].tolist()} for name, _, _ in oracles}
+        fqs, sub, log_len = [], idx, log_n
         for lvl, k in enumerate(schedule):
-            le, path = fri.query(lvl, sub >> k, k)
+            if comm:
+                c0_l, c1_l, tree_l, _ = fri.levels[lvl]
+                leaf = local_leaf_index(sub, log_len, world)[1] >> k
+                le = ctx.query_leaf_elements([c0_l, c1_l], [leaf], elems_per_leaf=1 << k)[0]
+                path = ctx.merkle_paths(tree_l, [leaf])[0]
+            else:
+                le, path = fri.query(lvl, sub >> k, k)
             fqs.append({"leaf_elements": le.tolist(), "proof": path.tolist()})
             sub >>= k
+            log_len -= k
         q["fri_queries"] = fqs
-        queries.append(q)
+        answered[qi] = q
+    if comm:
+        merged = {}
+        for part in comm.all_gather_host(answered):
+            merged.update(part)
+        answered = merged
+    queries = [answered[qi] for qi in range(len(idxs))]
     mark("6_queries", t0)
     return {
         "proof_config": cfg.to_dict(), "public_inputs": [],
@@ -276,7 +365,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
         "final_fri_monomials": [mono0.tolist(), mono1.tolist()],
         "values_at_z": [_ext_dict(v) for v in values_at_z], "values_at_z_omega": [_ext_dict(v) for v in values_at_z_omega],
         "values_at_0": [_ext_dict(v) for v in values_at_0],
-        "fri_base_oracle_cap": fri.get_cap(0).tolist(),
-        "fri_intermediate_oracles_caps": [fri.get_cap(i).tolist() for i in range(1, fri.num_oracles())],
+        "fri_base_oracle_cap": fri_caps[0].tolist(),
+        "fri_intermediate_oracles_caps": [c_.tolist() for c_ in fri_caps[1:]],
         "queries_per_fri_repetition": queries, "pow_challenge": 0, "_marker": None,
     }

@@ -52,6 +52,15 @@ BJ_API int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx);
 BJ_API int32_t bj_ctx_destroy(bj_ctx* ctx);
 BJ_API int32_t bj_ctx_set_stream(bj_ctx* ctx, void* stream);
 BJ_API int32_t bj_ctx_synchronize(bj_ctx* ctx);
+/* Multi-GPU proving (one process and one context per GPU): declare that this context is rank `rank` of `world` (a power
+ * of two, <= the LDE factor 2^log_lde of the proof).  Every buffer on the LDE domain then holds only the cosets j = rank (mod world), stored
+ * [local coset][row]: bj_lde produces just those cosets, and bj_quotient_copy_permutation,
+ * bj_quotient_divide_by_vanishing, bj_deep_quotient_group and bj_fri_fold take local buffers (sizes in their signatures
+ * stay the GLOBAL domain sizes) and use the domain points of the owned cosets.  Merkle trees are built per rank over the
+ * local leaves (a coset is a contiguous subtree: leaf index = coset * n + row, src/cs/implementations/proof.rs:89-91),
+ * so caps and query paths are gathered by the caller.  bj_barycentric_evaluate reads coset 0 and is valid on rank 0 only.
+ * The reference has no counterpart (its Worker is one machine's thread pool).  Default: rank 0 of 1. */
+BJ_API int32_t bj_ctx_set_coset_shard(bj_ctx* ctx, uint32_t rank, uint32_t world, uint32_t log_lde);
 BJ_API const char* bj_last_error(const bj_ctx* ctx);
 /* number of kernels this library launched through ctx so far (for launch accounting) */
 BJ_API uint64_t bj_launch_count(const bj_ctx* ctx);
