@@ -1,5 +1,6 @@
 """torchrun check on N GPUs: column-sharded iNTT -> NCCL all-gather of monomials -> coset-sharded LDE + Merkle subtrees
--> all-gather of caps equals the single-GPU commitment (bit-exact), plus timings.  Usage:
+-> all-gather of caps equals the single-GPU commitment (bit-exact), plus timings; then the coset-sharded prover
+(prover.prove with a TorchDistComm) must return the single-GPU proof on every rank.  Usage:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -46,4 +47,25 @@ if rank == 0:
     print({"world": world, "log_n": log_n, "cols": V, "bit_identical_to_single_gpu": bool(flag.item()),
            "commit_sharded_s": round(t_sharded, 4), "commit_single_gpu_s": round(t_single, 4),
            "speedup": round(t_single / t_sharded, 2)})
+del lde, tree, res, cols
+torch.cuda.empty_cache()
+
+# ---- coset-sharded PROVER over NCCL == single-GPU prover (same proof, bit for bit), and the oracle verifier accepts ----
+import json
+from era_boojum_b200 import prover, synthetic
+p_log_n = int(os.environ.get("PROVE_LOG_N", "16"))
+cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100)
+variables, sigmas, constants, gates, Q, lk = synthetic.generate(ctx, p_log_n, 60, seed=7, lookup=True)
+single = prover.prove(ctx, prover.Setup(ctx, sigmas, constants, gates, Q, cfg, lookup=lk), variables, multiplicities=lk["multiplicities"])
+sctx = bj.Context.on_current_stream(local)
+sctx.set_coset_shard(rank, world, 8)
+setup = prover.Setup(sctx, sigmas, constants, gates, Q, cfg, lookup=lk, comm=parallel.TorchDistComm(dist))
+sharded = prover.prove(sctx, setup, variables, multiplicities=lk["multiplicities"])
+same = json.dumps(single, sort_keys=True) == json.dumps(sharded, sort_keys=True)
+flag = torch.tensor([1 if same else 0], device="cuda:%d" % local)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    from oracle import verifier as OV
+    print({"world": world, "prove_log_n": p_log_n, "sharded_proof_equals_single_gpu_proof_on_every_rank": bool(flag.item()),
+           "oracle_verifier_accepts": bool(OV.verify(setup.vk(), sharded))})
 dist.destroy_process_group()
