@@ -25,8 +25,24 @@ __global__ void field_selftest_kernel(u64 n, u64 seed, unsigned long long* misma
   u64 a = next(st), b = next(st);
   if ((i & 7) == 0) a = edges[(i >> 3) % 12];
   if ((i & 15) < 2) b = edges[(i >> 4) % 12];
+  if ((i & 7) == 3) {
+    // structured operands that drive the rare wrap paths of the reduction: a = 2^s (+-1), b with all-zero / all-one
+    // 32-bit halves (e.g. 2^63 * (r << 33) leaves x = -r3: the borrow path; 2^32 * ~0 takes the carry path)
+    const u64 r = next(st);
+    a = (1ull << ((i >> 3) & 63)) + (((i >> 9) & 3) == 1 ? 1 : 0) - (((i >> 9) & 3) == 2 ? 1 : 0);
+    const unsigned sel = (unsigned)(i >> 11) & 7;
+    u64 lo = r & 0xffffffffull, hi = r >> 32;
+    if (sel & 1) lo = (sel & 4) ? 0xffffffffull : 0;
+    if (sel & 2) hi = (sel & 4) ? 0xffffffffull : 0;
+    b = (hi << 32) | lo;
+  }
+  if ((i & 63) == 5) {  // every pair of edge values
+    a = edges[(i >> 6) % 12];
+    b = edges[(i >> 6) / 12 % 12];
+  }
   unsigned bad = 0;
   if (gl::mul(a, b) != gl::mul_c(a, b)) bad++;
+  if (gl::canon(gl::mul_lazy(a, b)) != gl::mul_c(a, b)) bad++;
   const u64 bc = gl::canon(b);
   if (gl::canon(gl::add(a, bc)) != gl::canon(gl::add_c(a, bc))) bad++;
   if (gl::canon(gl::sub(a, bc)) != gl::canon(gl::sub_c(a, bc))) bad++;
@@ -96,6 +112,7 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
   if (ctx->ntt_max_tile_log > 14) ctx->ntt_max_tile_log = 14;
   ctx->ntt_pass1_w = env_int("BJ_NTT_PASS1_W", -1);
   ctx->ntt_use_v2 = env_int("BJ_NTT_V2", 1);
+  ctx->ntt_full_pow = env_int("BJ_NTT_FULL_POW", 1);
   int32_t st = poseidon2_init_constants(ctx);
   if (st != BJ_OK) {
     delete ctx;
@@ -114,6 +131,7 @@ int32_t bj_ctx_destroy(bj_ctx* ctx) {
   for (auto& e : ctx->pow_cache) {
     cudaFree(e.lo);
     cudaFree(e.hi);
+    if (e.full) cudaFree(e.full);
   }
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->ptr_table) cudaFree(ctx->ptr_table);

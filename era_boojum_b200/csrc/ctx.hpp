@@ -20,6 +20,7 @@ struct PowTab {
   int split;
   u64* lo;
   u64* hi;
+  u64* full;  // s * c^i for all i < 2^log_n, or nullptr (built while the per-context budget lasts)
 };
 
 // Coset shard of a multi-GPU prover: LDE-domain buffers of this context hold only the cosets j = first + k * 2^log_stride
@@ -53,6 +54,7 @@ struct bj_ctx {
   bj::u64* tw_inv = nullptr;
   int tw_log = 0;  // tables hold 2^(tw_log-1) entries
   std::vector<bj::PowTab> pow_cache;
+  size_t pow_full_bytes = 0;  // bytes held by the full power tables of pow_cache
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   void* ptr_table = nullptr;  // device copy of host pointer arrays (Merkle sources)
@@ -73,6 +75,7 @@ struct bj_ctx {
   int ntt_max_tile_log = 13;  // tunables (env BJ_NTT_*)
   int ntt_pass1_w = -1;
   int ntt_chunk_mb = 0;
+  int ntt_full_pow = 1;          // BJ_NTT_FULL_POW=0 keeps the two-level coset power tables only
   bj::CosetShard shard;  // bj_ctx_set_coset_shard; default = the whole domain
   uint32_t shard_log_lde = 0;  // LDE factor the shard was declared for (locates the coset bits of flat indices)
 };

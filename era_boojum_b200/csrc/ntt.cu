@@ -27,6 +27,7 @@ __device__ __forceinline__ int phys(int e) { return e + (e >> 4); }  // 1 pad wo
 
 __device__ __forceinline__ u64 scale_factor(const NttPass& p, u64 idx) {
   if (p.scale_mode == SCALE_CONST) return p.scale_const;
+  if (p.scale_mode == SCALE_FULL) return __ldg(p.pw_full + idx);
   u64 lo = __ldg(p.pw_lo + (idx & ((1ull << p.pw_split) - 1)));
   u64 hi = __ldg(p.pw_hi + (idx >> p.pw_split));
   return gl::mul(lo, hi);
@@ -279,7 +280,19 @@ int32_t ensure_twiddles(bj_ctx* ctx, int log_n) {
   return BJ_OK;
 }
 
-// c^i tables for i < 2^log_n: c^i = lo[i & mask] * hi[i >> split], hi pre-multiplied by `scale`
+// full[i] = lo[i & mask] * hi[i >> split]
+__global__ void __launch_bounds__(256) pow_full_kernel(u64* __restrict__ full, u64 n, const u64* __restrict__ lo,
+                                                        const u64* __restrict__ hi, int split) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  full[i] = gl::mul(__ldg(lo + (i & ((1ull << split) - 1))), __ldg(hi + (i >> split)));
+}
+
+// c^i tables for i < 2^log_n: c^i = lo[i & mask] * hi[i >> split], hi pre-multiplied by `scale`; plus the expanded table
+// `full` (one load + one multiplication per element in the pass kernels instead of two + two) while the context's
+// budget lasts - the pass kernels are ALU-bound and read HBM at < 20 % of its bandwidth, so 8 more bytes per element of
+// (mostly L2-resident, shared by all columns) traffic are cheaper than 25 more instructions.
+static constexpr size_t POW_FULL_BUDGET = (size_t)3 << 30;
 static int32_t get_pow_tables(bj_ctx* ctx, u64 c, int log_n, u64 scale, PowTab* out) {
   for (auto& e : ctx->pow_cache)
     if (e.coset == c && e.log_n == log_n && e.scale == scale) {
@@ -291,8 +304,10 @@ static int32_t get_pow_tables(bj_ctx* ctx, u64 c, int log_n, u64 scale, PowTab* 
     for (auto& e : ctx->pow_cache) {
       cudaFree(e.lo);
       cudaFree(e.hi);
+      if (e.full) cudaFree(e.full);
     }
     ctx->pow_cache.clear();
+    ctx->pow_full_bytes = 0;
   }
   PowTab pt;
   pt.coset = c;
@@ -308,6 +323,18 @@ static int32_t get_pow_tables(bj_ctx* ctx, u64 c, int log_n, u64 scale, PowTab* 
   pow_table_kernel<<<(nhi + 255) / 256, 256, 0, ctx->stream>>>(pt.hi, nhi, log_n - pt.split, make_squares(chi),
                                                                 gl::canon(scale));
   BJ_LAUNCH_CHECK(ctx);
+  pt.full = nullptr;
+  const size_t full_bytes = sizeof(u64) << log_n;
+  if (ctx->ntt_full_pow && log_n >= 8 && ctx->pow_full_bytes + full_bytes <= POW_FULL_BUDGET &&
+      cudaMalloc(&pt.full, full_bytes) == cudaSuccess) {
+    const u64 n = 1ull << log_n;
+    pow_full_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pt.full, n, pt.lo, pt.hi, pt.split);
+    BJ_LAUNCH_CHECK(ctx);
+    ctx->pow_full_bytes += full_bytes;
+  } else {
+    cudaGetLastError();
+    pt.full = nullptr;
+  }
   ctx->pow_cache.push_back(pt);
   *out = pt;
   return BJ_OK;
@@ -466,6 +493,8 @@ static int32_t run_transform(bj_ctx* ctx, const u64* src, u64 src_stride, u64* d
     p.pw_lo = pt.lo;
     p.pw_hi = pt.hi;
     p.pw_split = pt.split;
+    p.pw_full = pt.full;
+    if (p.scale_mode == SCALE_POW && pt.full) p.scale_mode = SCALE_FULL;
     p.canon_out = last ? 1 : 0;
     BJ_TRY(launch_pass(ctx, p, n_cols));
     cur_src = p.dst;

@@ -15,7 +15,7 @@ namespace bj {
 
 using gl::u64;
 
-enum NttScaleMode : int { SCALE_NONE = 0, SCALE_CONST = 1, SCALE_POW = 2 };
+enum NttScaleMode : int { SCALE_NONE = 0, SCALE_CONST = 1, SCALE_POW = 2, SCALE_FULL = 3 };
 enum NttPassKind : int { PASS_TILE = 0, PASS_TRANSPOSE_LAST = 1 };
 
 struct NttPass {
@@ -35,6 +35,7 @@ struct NttPass {
   const u64* pw_lo;    // SCALE_POW: c^x, x < 2^pw_split
   const u64* pw_hi;    // SCALE_POW: s * c^(y 2^pw_split)
   int pw_split;
+  const u64* pw_full;  // SCALE_FULL: s * c^i for every i < 2^log_n (one load, one multiplication per element)
   int canon_out;       // canonicalise values at the store (last pass)
 };
 

@@ -19,18 +19,35 @@ struct V2Cfg {
   static constexpr int RS0 = (T & 3) ? (T & 3) : 4;  // bits of the first (short) stage
   static constexpr int NSTAGES = (T + 3) / 4;
   static constexpr size_t SMEM = sizeof(u64) * (size_t)(E + (E >> 4) + 2);
+  // (12,0) is the only shape ptxas takes past 64 registers (66 -> 3 instead of 4 CTAs per SM); the others sit at 63-64
+  static constexpr bool CAP_REGS = (T == 12 && W == 0);
 };
 
 __device__ __forceinline__ int v2_phys(int e) { return e + (e >> 4); }
 
 __device__ __forceinline__ u64 v2_scale(const NttPass& p, u64 idx) {
   if (p.scale_mode == SCALE_CONST) return p.scale_const;
+  if (p.scale_mode == SCALE_FULL) return __ldg(p.pw_full + idx);
   const u64 lo = __ldg(p.pw_lo + (idx & ((1ull << p.pw_split) - 1)));
   const u64 hi = __ldg(p.pw_hi + (idx >> p.pw_split));
   return gl::mul(lo, hi);
 }
 
-template <int RS, int Q>
+// factors of the adjacent positions idx (even) and idx + 1
+__device__ __forceinline__ void v2_scale2(const NttPass& p, u64 idx, u64& s0, u64& s1) {
+  if (p.scale_mode == SCALE_FULL) {
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p.pw_full + idx));
+    s0 = v.x;
+    s1 = v.y;
+  } else {
+    s0 = v2_scale(p, idx);
+    s1 = v2_scale(p, idx + 1);
+  }
+}
+
+// FIRST: the stage starts the whole transform (no round done before it, prefix 0), so the twiddle of group 0 of every
+// round is tab[0] = 1 and 15 of the 32 multiplications of a radix-16 stage disappear.
+template <int RS, int Q, bool FIRST>
 __device__ __forceinline__ void v2_round(u64 (&x)[16], const u64* __restrict__ tab, u32 pfx) {
   constexpr int NG = 1 << Q;       // twiddles of this round
   constexpr int BIT = 1 << (3 - Q);
@@ -51,21 +68,23 @@ __device__ __forceinline__ void v2_round(u64 (&x)[16], const u64* __restrict__ t
   for (int j0 = 0; j0 < 16; j0++) {
     if (j0 & BIT) continue;
     const int j1 = j0 | BIT;
-    const u64 v = gl::mul(x[j1], tw[j0 >> (4 - Q)]);
+    u64 v;
+    if (FIRST && (j0 >> (4 - Q)) == 0) v = gl::canon(x[j1]);
+    else v = gl::mul(x[j1], tw[j0 >> (4 - Q)]);
     x[j1] = gl::sub(x[j0], v);
     x[j0] = gl::add(x[j0], v);
   }
 }
 
-template <int RS>
+template <int RS, bool FIRST>
 __device__ __forceinline__ void v2_stage_compute(u64 (&x)[16], const u64* __restrict__ tab, u32 pfx) {
-  v2_round<RS, 0>(x, tab, pfx);
-  if constexpr (RS > 1) v2_round<RS, 1>(x, tab, pfx);
-  if constexpr (RS > 2) v2_round<RS, 2>(x, tab, pfx);
-  if constexpr (RS > 3) v2_round<RS, 3>(x, tab, pfx);
+  v2_round<RS, 0, FIRST>(x, tab, pfx);
+  if constexpr (RS > 1) v2_round<RS, 1, FIRST>(x, tab, pfx);
+  if constexpr (RS > 2) v2_round<RS, 2, FIRST>(x, tab, pfx);
+  if constexpr (RS > 3) v2_round<RS, 3, FIRST>(x, tab, pfx);
 }
 
-template <int T, int W, int KIND, int STAGE>
+template <int T, int W, int KIND, int STAGE, bool FIRST = false>
 __device__ __forceinline__ void v2_stage(u64* __restrict__ sm, const u64* __restrict__ tab, int tid, u32 hi, u32 tile,
                                          int r0) {
   using C = V2Cfg<T, W>;
@@ -87,7 +106,7 @@ __device__ __forceinline__ void v2_stage(u64* __restrict__ sm, const u64* __rest
     u64 x[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) x[j] = base[(j << PP) + ((j << PP) >> 4)];
-    v2_stage_compute<RS>(x, tab, pfx);
+    v2_stage_compute<RS, FIRST>(x, tab, pfx);
 #pragma unroll
     for (int j = 0; j < 16; j++) base[(j << PP) + ((j << PP) >> 4)] = x[j];
   }
@@ -96,7 +115,7 @@ __device__ __forceinline__ void v2_stage(u64* __restrict__ sm, const u64* __rest
 }
 
 template <int T, int W, int KIND>
-__global__ void __launch_bounds__(V2Cfg<T, W>::THREADS) ntt_pass_v2_kernel(const NttPass p) {
+__device__ __forceinline__ void ntt_pass_v2_body(const NttPass& p) {
   using C = V2Cfg<T, W>;
   extern __shared__ u64 sm[];
   constexpr int WM = (1 << W) - 1;
@@ -131,8 +150,10 @@ __global__ void __launch_bounds__(V2Cfg<T, W>::THREADS) ntt_pass_v2_kernel(const
       }
       if (scale_load) {
         const u64 g0 = (W == 0) ? base + e : gi;
-        v.x = gl::mul(v.x, v2_scale(p, g0));
-        v.y = gl::mul(v.y, v2_scale(p, g0 + 1));
+        u64 s0, s1;
+        v2_scale2(p, g0, s0, s1);
+        v.x = gl::mul(v.x, s0);
+        v.y = gl::mul(v.y, s1);
       }
       const int pe = v2_phys(e);
       sm[pe] = v.x;
@@ -147,8 +168,10 @@ __global__ void __launch_bounds__(V2Cfg<T, W>::THREADS) ntt_pass_v2_kernel(const
       const u64 gi = ((u64)blk << T) + row;
       ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + gi);
       if (scale_load) {
-        v.x = gl::mul(v.x, v2_scale(p, gi));
-        v.y = gl::mul(v.y, v2_scale(p, gi + 1));
+        u64 s0, s1;
+        v2_scale2(p, gi, s0, s1);
+        v.x = gl::mul(v.x, s0);
+        v.y = gl::mul(v.y, s1);
       }
       sm[v2_phys((row << W) + col)] = v.x;
       sm[v2_phys(((row + 1) << W) + col)] = v.y;
@@ -156,7 +179,8 @@ __global__ void __launch_bounds__(V2Cfg<T, W>::THREADS) ntt_pass_v2_kernel(const
   }
   __syncthreads();
 
-  v2_stage<T, W, KIND, 0>(sm, p.tab, tid, hi, tile, r0);
+  if (r0 == 0) v2_stage<T, W, KIND, 0, true>(sm, p.tab, tid, hi, tile, r0);
+  else v2_stage<T, W, KIND, 0, false>(sm, p.tab, tid, hi, tile, r0);
 
   if constexpr (KIND == PASS_TILE) {
 #pragma unroll 4
@@ -169,8 +193,10 @@ __global__ void __launch_bounds__(V2Cfg<T, W>::THREADS) ntt_pass_v2_kernel(const
       v.x = sm[pe];
       v.y = sm[pe + 1];
       if (scale_store) {
-        v.x = gl::mul(v.x, v2_scale(p, gi));
-        v.y = gl::mul(v.y, v2_scale(p, gi + 1));
+        u64 s0, s1;
+        v2_scale2(p, gi, s0, s1);
+        v.x = gl::mul(v.x, s0);
+        v.y = gl::mul(v.y, s1);
       }
       if (p.canon_out) {
         v.x = gl::canon(v.x);
@@ -201,8 +227,10 @@ __global__ void __launch_bounds__(V2Cfg<T, W>::THREADS) ntt_pass_v2_kernel(const
       v.y = sm[pe + 1];
       const u64 go = ((u64)tile << W) + col + ((u64)kappa << r0);
       if (scale_store) {
-        v.x = gl::mul(v.x, v2_scale(p, go));
-        v.y = gl::mul(v.y, v2_scale(p, go + 1));
+        u64 s0, s1;
+        v2_scale2(p, go, s0, s1);
+        v.x = gl::mul(v.x, s0);
+        v.y = gl::mul(v.y, s1);
       }
       if (p.canon_out) {
         v.x = gl::canon(v.x);
@@ -213,11 +241,30 @@ __global__ void __launch_bounds__(V2Cfg<T, W>::THREADS) ntt_pass_v2_kernel(const
   }
 }
 
+template <int T, int W, int KIND>
+__global__ void __launch_bounds__(V2Cfg<T, W>::THREADS) ntt_pass_v2_kernel(const NttPass p) {
+  ntt_pass_v2_body<T, W, KIND>(p);
+}
+// 2^13-value tiles: shared memory admits 3 CTAs per SM, so up to 85 registers per thread cost no occupancy
+template <int T, int W, int KIND>
+__global__ void __launch_bounds__(V2Cfg<T, W>::THREADS, 3) ntt_pass_v2_kernel_r85(const NttPass p) {
+  ntt_pass_v2_body<T, W, KIND>(p);
+}
+// same body with the register cap that keeps 4 CTAs (of 256 threads) per SM
+template <int T, int W, int KIND>
+__global__ void __launch_bounds__(V2Cfg<T, W>::THREADS, 4) ntt_pass_v2_kernel_r64(const NttPass p) {
+  ntt_pass_v2_body<T, W, KIND>(p);
+}
+
 typedef void (*V2KernelPtr)(const NttPass);
 
 template <int T, int W, int KIND>
 struct V2Entry {
-  static V2KernelPtr get() { return ntt_pass_v2_kernel<T, W, KIND>; }
+  static V2KernelPtr get() {
+    if constexpr (V2Cfg<T, W>::CAP_REGS) return ntt_pass_v2_kernel_r64<T, W, KIND>;
+    else if constexpr (T + W == 13) return ntt_pass_v2_kernel_r85<T, W, KIND>;
+    else return ntt_pass_v2_kernel<T, W, KIND>;
+  }
 };
 
 struct V2Launch {

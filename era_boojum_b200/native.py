@@ -9,8 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libboojum_b200_portable.so" if os.environ.get("BJ_LIB_VARIANT") == "portable"
-                        else "libboojum_b200.so")
+_VARIANT = os.environ.get("BJ_LIB_VARIANT")   # debugging / A-B builds: libboojum_b200_<variant>.so
+LIB_PATH = os.path.join(_HERE, "libboojum_b200_%s.so" % _VARIANT if _VARIANT else "libboojum_b200.so")
 
 P = 0xFFFFFFFF00000001
 
