@@ -375,8 +375,23 @@ class Context:
         gates: list of dicts {relations: [(op, dst, (kind, value), (kind, value) | None)], writes: [(kind, value)],
         num_repetitions, variables_offset, witnesses_offset, constants_offset, constants_placement_offset,
         selector_path: [bool]} - the data of gpu_synthesizer::GPUDataCapture; columns: lists of flat CUDA tensors."""
+        keep, descs = self._gate_descs(gates)
+
+        def ptrs(cols):
+            return (ctypes.c_void_p * max(1, len(cols)))(*[c.data_ptr() for c in cols])
+
+        n_terms = len(alpha_powers)
+        al = (ctypes.c_uint64 * max(2, 2 * n_terms))(*[int(x) for a in alpha_powers for x in a])
+        self._check(lib.bj_quotient_gates_general_purpose(
+            self._h, descs, len(gates), ptrs(variables), len(variables), ptrs(witnesses), len(witnesses),
+            ptrs(constants), len(constants), al, n_terms, q_c0.numel(), self._ptr(q_c0), self._ptr(q_c1)))
+        return q_c0, q_c1
+
+    @staticmethod
+    def _gate_descs(gates):
+        """list of gate dicts -> (keep-alive list, ctypes array of bj_gate_desc)"""
         N = native
-        keep, descs = [], (N.GateDesc * len(gates))()
+        keep, descs = [], (N.GateDesc * max(1, len(gates)))()
         for d, g in zip(descs, gates):
             rels = (N.GateRelation * max(1, len(g["relations"])))()
             for r, (op, dst, a, b) in zip(rels, g["relations"]):
@@ -396,16 +411,13 @@ class Context:
             d.constants_offset = g.get("constants_offset", 0)
             d.constants_placement_offset = g["constants_placement_offset"]
             d.selector_path_len, d.selector_path = len(g["selector_path"]), path
+        return keep, descs
 
-        def ptrs(cols):
-            return (ctypes.c_void_p * max(1, len(cols)))(*[c.data_ptr() for c in cols])
-
-        n_terms = len(alpha_powers)
-        al = (ctypes.c_uint64 * max(2, 2 * n_terms))(*[int(x) for a in alpha_powers for x in a])
-        self._check(lib.bj_quotient_gates_general_purpose(
-            self._h, descs, len(gates), ptrs(variables), len(variables), ptrs(witnesses), len(witnesses),
-            ptrs(constants), len(constants), al, n_terms, q_c0.numel(), self._ptr(q_c0), self._ptr(q_c1)))
-        return q_c0, q_c1
+    # ---- native prover driver (bj_setup_create / bj_prove: host C++ inside the library) ----
+    def native_setup(self, sigmas, constants, gates, quotient_degree, config, lookup=None):
+        """bj_setup_create.  sigmas [V, n], constants [C, n], lookup["tables"] [width + 1, n]: contiguous int64 CUDA tensors
+        (borrowed by the setup: the returned object keeps them alive)."""
+        return NativeSetup(self, sigmas, constants, gates, quotient_degree, config, lookup)
 
     # ---- queries ----
     def query_leaf_elements(self, sources, indices, elems_per_leaf=1):
@@ -449,3 +461,65 @@ class Context:
         self._check(lib.bj_fri_fold(self._h, self._ptr(c0), self._ptr(c1), log_m, log_fold, al, ctypes.byref(ci),
                                     self._ptr(o0), self._ptr(o1)))
         return o0, o1, int(ci.value)
+
+
+class NativeSetup:
+    """bj_setup: setup LDE + setup tree + circuit description held by the library; prove() runs bj_prove (host C++)."""
+
+    def __init__(self, ctx, sigmas, constants, gates, quotient_degree, config, lookup=None):
+        import json as _json
+        self._json = _json
+        self.ctx = ctx
+        self._keep = [sigmas, constants, lookup["tables"] if lookup else None]
+        for t in self._keep:
+            assert t is None or (t.is_cuda and t.is_contiguous() and t.dtype == ctx._torch.int64)
+        keep, descs = ctx._gate_descs(gates)
+        c = native.Circuit()
+        c.log_n, c.num_variables, c.num_constants = sigmas.shape[1].bit_length() - 1, sigmas.shape[0], constants.shape[0]
+        c.quotient_degree, c.fri_lde_factor, c.merkle_tree_cap_size = quotient_degree, config.fri_lde_factor, config.merkle_tree_cap_size
+        c.security_level, c.pow_bits, c.gates, c.n_gates = config.security_level, config.pow_bits, descs, len(gates)
+        if lookup:
+            c.lookup_width, c.lookup_num_repetitions = lookup["width"], lookup["num_repetitions"]
+            c.lookup_variables_offset, c.lookup_table_id_column = lookup["variables_offset"], lookup["table_id_column"]
+        self.cap_size = config.merkle_tree_cap_size
+        h = ctypes.c_void_p()
+        ctx._check(lib.bj_setup_create(ctx._h, ctypes.byref(c), ctx._ptr(sigmas), ctx._ptr(constants),
+                                       ctx._ptr(lookup["tables"]) if lookup else None, ctypes.byref(h)))
+        self._h = h
+        del keep
+
+    def get_cap(self):
+        out = np.zeros((self.cap_size, 4), np.uint64)
+        assert lib.bj_setup_get_cap(self._h, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        return out
+
+    def prove(self, variables, multiplicities=None, timings=None, as_json=False):
+        """bj_prove -> the proof as a dict in the reference's serde shape (or the JSON text)."""
+        h = ctypes.c_void_p()
+        self.ctx._check(lib.bj_prove(self.ctx._h, self._h, self.ctx._ptr(variables),
+                                     self.ctx._ptr(multiplicities) if multiplicities is not None else None, ctypes.byref(h)))
+        try:
+            need = ctypes.c_size_t()
+            assert lib.bj_proof_to_json(h, None, 0, ctypes.byref(need)) == 0
+            buf = ctypes.create_string_buffer(need.value)
+            assert lib.bj_proof_to_json(h, buf, need.value, ctypes.byref(need)) == 0
+            if timings is not None:
+                st = (ctypes.c_double * 6)()
+                assert lib.bj_proof_stage_seconds(h, st) == 0
+                for k, v in zip(("1_witness_lde_commit", "2_stage2_products_lde_commit", "3_quotient", "4_openings", "5_deep_fri", "6_queries"), st):
+                    timings[k] = float(v)
+        finally:
+            lib.bj_proof_free(h)
+        text = buf.value.decode()
+        return text if as_json else self._json.loads(text)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.bj_setup_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

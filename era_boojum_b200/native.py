@@ -94,6 +94,13 @@ SIGNATURES = {
     "bj_fri_oracles_query": (_i32, [_vp, _u32, _u64, _vp, _vp, _vp]),
     "bj_query_leaf_elements": (_i32, [_vp, _vp, _u32, _u32, _vp, _u32, _vp]),
     "bj_merkle_paths": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _u32, _vp]),
+    "bj_setup_create": (_i32, [_vp, _vp, _vp, _vp, _vp, _pp]),
+    "bj_setup_free": (None, [_vp]),
+    "bj_setup_get_cap": (_i32, [_vp, _vp]),
+    "bj_prove": (_i32, [_vp, _vp, _vp, _vp, _pp]),
+    "bj_proof_free": (None, [_vp]),
+    "bj_proof_to_json": (_i32, [_vp, _vp, _sz, ctypes.POINTER(_sz)]),
+    "bj_proof_stage_seconds": (_i32, [_vp, _vp]),
     "bj_selftest_field": (_i32, [_vp, _u64, _u64, _vp]),
     "bj_host_gl_mul": (_u64, [_u64, _u64]),
     "bj_host_gl_add": (_u64, [_u64, _u64]),
@@ -133,3 +140,12 @@ class GateDesc(ctypes.Structure):
 
 IDX_VARIABLE, IDX_WITNESS, IDX_CONSTANT_POLY, IDX_TEMPORARY, IDX_CONSTANT_VALUE, IDX_CONSTANT_POLY_SHARED = range(6)
 REL_ADD, REL_DOUBLE, REL_SUB, REL_NEGATE, REL_MUL, REL_SQUARE, REL_INVERSE = range(7)
+
+
+class Circuit(ctypes.Structure):
+    """bj_circuit"""
+    _fields_ = [("log_n", ctypes.c_uint32), ("num_variables", ctypes.c_uint32), ("num_constants", ctypes.c_uint32),
+                ("quotient_degree", ctypes.c_uint32), ("fri_lde_factor", ctypes.c_uint32), ("merkle_tree_cap_size", ctypes.c_uint32),
+                ("security_level", ctypes.c_uint32), ("pow_bits", ctypes.c_uint32), ("gates", ctypes.POINTER(GateDesc)),
+                ("n_gates", ctypes.c_uint32), ("lookup_width", ctypes.c_uint32), ("lookup_num_repetitions", ctypes.c_uint32),
+                ("lookup_variables_offset", ctypes.c_uint32), ("lookup_table_id_column", ctypes.c_uint32)]

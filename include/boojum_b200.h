@@ -299,6 +299,43 @@ BJ_API int32_t bj_query_leaf_elements(bj_ctx* ctx, const uint64_t* const* h_sour
 BJ_API int32_t bj_merkle_paths(bj_ctx* ctx, const uint64_t* d_leaf_hashes, const uint64_t* d_nodes, uint64_t n_leaves,
                         uint32_t cap_size, const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out);
 
+/* ---- the prover entry point: CSReferenceAssembly::prove_cpu_basic (src/cs/implementations/prover.rs:153-2269) and the part of
+ *      the setup materialisation it depends on (setup.rs:1093-1255: sigma / constant / lookup-table columns -> LDE -> setup tree).
+ * Scope: gates on general-purpose columns (bj_gate_desc programs), copy permutation over all variable columns, optional
+ * log-derivative lookup over specialised columns with the table id in a constant column (lookup_width = 0: none), Poseidon2
+ * tree hasher and transcript, no public inputs, no proof of work.  Host C++ inside the library: transcript, schedule, query
+ * indices and proof assembly never leave the host; every heavy step is one of the entry points above.
+ * Column arguments are DEVICE arrays [column][2^log_n] in natural row order.  bj_setup BORROWS d_sigmas / d_constants /
+ * d_lookup_tables (stage 2 reads them again): they must outlive the setup.  The gate programs are copied.
+ * bj_prove returns BJ_ERR_INVALID_ARG for an unsatisfied circuit (the reference panics, prover.rs:1425-1438). */
+typedef struct bj_circuit {
+  uint32_t log_n;            /* trace length 2^log_n */
+  uint32_t num_variables;    /* columns under the copy permutation (general purpose + specialised lookup columns) */
+  uint32_t num_constants;
+  uint32_t quotient_degree;  /* power of two */
+  uint32_t fri_lde_factor, merkle_tree_cap_size, security_level, pow_bits; /* ProofConfig (prover.rs:55-73) */
+  const bj_gate_desc* gates;
+  uint32_t n_gates;
+  uint32_t lookup_width;            /* columns per lookup tuple without the table id; 0 = no lookup argument */
+  uint32_t lookup_num_repetitions;  /* sub-arguments */
+  uint32_t lookup_variables_offset; /* first lookup column among the variables */
+  uint32_t lookup_table_id_column;  /* constant column holding the table id */
+} bj_circuit;
+typedef struct bj_setup bj_setup;
+typedef struct bj_proof bj_proof;
+BJ_API int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* d_sigmas, const uint64_t* d_constants,
+                        const uint64_t* d_lookup_tables /* [lookup_width + 1][n] or NULL */, bj_setup** out);
+BJ_API void bj_setup_free(bj_setup* setup);
+BJ_API int32_t bj_setup_get_cap(const bj_setup* setup, uint64_t* h_cap /* 4 * cap_size u64: VerificationKey::setup_merkle_tree_cap */);
+BJ_API int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables, const uint64_t* d_multiplicities /* or NULL */,
+                 bj_proof** out);
+BJ_API void bj_proof_free(bj_proof* proof);
+/* the proof in the reference's serde_json shape (Proof<F, H, EXT>, src/cs/implementations/proof.rs:57-143).
+ * Call with buf == NULL to learn the size (incl. the terminating 0), then with a buffer of at least that size. */
+BJ_API int32_t bj_proof_to_json(const bj_proof* proof, char* buf, size_t capacity, size_t* needed);
+/* wall-clock seconds of the six stages (witness, stage 2, quotient, openings, DEEP+FRI, queries), device work included */
+BJ_API int32_t bj_proof_stage_seconds(const bj_proof* proof, double out[6]);
+
 /* device self-test: PTX field arithmetic vs the portable C versions on n pseudo-random + edge inputs */
 BJ_API int32_t bj_selftest_field(bj_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* h_mismatches);
 

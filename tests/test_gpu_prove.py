@@ -151,3 +151,36 @@ def test_local_comm_python_fri_equals_cxx_driver(env):
     a = prover.prove(ctx, prover.Setup(ctx, sigmas, constants, gates, Q, cfg), variables)
     b = prover.prove(ctx, prover.Setup(ctx, sigmas, constants, gates, Q, cfg, comm=parallel.LocalComm()), variables)
     assert json.dumps(a, sort_keys=True) == json.dumps(b, sort_keys=True)
+
+
+@pytest.mark.parametrize("log_n,lookup", [(9, False), (10, True)])
+def test_native_cxx_prover_equals_python_driver(env, log_n, lookup):
+    """bj_setup_create + bj_prove (host C++ inside the library, JSON in the reference's serde shape) produce the same proof
+    as the Python driver over the same entry points, and the oracle verifier accepts it."""
+    bj, ctx, prover, synthetic = env
+    gen = synthetic.generate(ctx, log_n, 60, seed=11, lookup=lookup)
+    lk = gen[5] if lookup else None
+    variables, sigmas, constants, gates, Q = gen[:5]
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100)
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg, lookup=lk)
+    ref = prover.prove(ctx, setup, variables, multiplicities=lk["multiplicities"] if lk else None)
+    nat = ctx.native_setup(sigmas.contiguous(), constants.contiguous(), gates, Q, cfg, lookup=lk)
+    assert np.array_equal(nat.get_cap(), setup.cap)
+    timings = {}
+    got = nat.prove(variables.contiguous(), lk["multiplicities"] if lk else None, timings=timings)
+    assert json.dumps(got, sort_keys=True) == json.dumps(ref, sort_keys=True)
+    assert OV.verify(setup.vk(), got)
+    assert len(timings) == 6 and all(v >= 0 for v in timings.values())
+    nat.close()
+
+
+def test_native_cxx_prover_rejects_unsatisfied_witness(env):
+    bj, ctx, prover, synthetic = env
+    variables, sigmas, constants, gates, Q = synthetic.generate(ctx, 8, 20, seed=2)
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100)
+    nat = ctx.native_setup(sigmas.contiguous(), constants.contiguous(), gates, Q, cfg)
+    bad = variables.clone()
+    bad[3, 5] += 1
+    with pytest.raises(bj.BoojumError):
+        nat.prove(bad.contiguous())
+    nat.prove(variables.contiguous())
