@@ -413,6 +413,25 @@ class Context:
             d.selector_path_len, d.selector_path = len(g["selector_path"]), path
         return keep, descs
 
+    # ---- setup / witness materialisation ----
+    def materialize_variables_polynomials_from_dense_hint(self, all_values, hint, log_n):
+        """witness.rs:325-385.  all_values: [n_values] CUDA tensor; hint: [n_cols, hint_rows] CUDA tensor of reference
+        `Variable`s (bit 63 = placeholder).  Returns [n_cols, 2^log_n]."""
+        torch = self._torch
+        assert hint.is_cuda and hint.is_contiguous() and hint.dim() == 2 and all_values.is_contiguous()
+        out = torch.empty((hint.shape[0], 1 << log_n), dtype=torch.int64, device=hint.device)
+        self._check(lib.bj_materialize_columns(self._h, self._ptr(all_values), all_values.numel(), self._ptr(hint), hint.shape[0],
+                                               hint.shape[1], log_n, self._ptr(out)))
+        return out
+
+    def create_permutation_polys(self, placement):
+        """setup.rs:419-502.  placement: [n_cols, n] CUDA tensor of `Variable`s (copy_permutation_data) -> sigma columns."""
+        assert placement.is_cuda and placement.is_contiguous() and placement.dim() == 2
+        out = self._torch.empty_like(placement)
+        self._check(lib.bj_create_permutation_polys(self._h, self._ptr(placement), placement.shape[0], placement.shape[1].bit_length() - 1,
+                                                    self._ptr(out)))
+        return out
+
     # ---- native prover driver (bj_setup_create / bj_prove: host C++ inside the library) ----
     def native_setup(self, sigmas, constants, gates, quotient_degree, config, lookup=None):
         """bj_setup_create.  sigmas [V, n], constants [C, n], lookup["tables"] [width + 1, n]: contiguous int64 CUDA tensors

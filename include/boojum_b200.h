@@ -299,6 +299,20 @@ BJ_API int32_t bj_query_leaf_elements(bj_ctx* ctx, const uint64_t* const* h_sour
 BJ_API int32_t bj_merkle_paths(bj_ctx* ctx, const uint64_t* d_leaf_hashes, const uint64_t* d_nodes, uint64_t n_leaves,
                         uint32_t cap_size, const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out);
 
+/* ---- setup / witness materialisation on the device (what feeds bj_setup_create and bj_prove) ----
+ * Variable encoding as in the reference (src/cs/mod.rs:44-47, :155-180): a u64 whose bit 63 marks a placeholder and whose
+ * low 48 bits are the variable index.
+ * bj_materialize_columns: materialize_variables_polynomials_from_dense_hint (src/cs/implementations/witness.rs:325-385):
+ *   d_out[c][row] = d_all_values[hint[c][row]] for row < hint_rows (hint laid out [n_cols][hint_rows]); placeholders and
+ *   the rows beyond the hint are zero.  Fails if a hint points past n_values.  Synchronises.
+ * bj_create_permutation_polys: create_permutation_polys (src/cs/implementations/setup.rs:419-502): d_placement is
+ *   copy_permutation_data, [n_cols][2^log_n] variables; d_sigmas [n_cols][2^log_n] receives the sigma columns (identity
+ *   k_c * w^row on cells that are never copied, one cycle per variable over its occurrences in column-major order). */
+BJ_API int32_t bj_materialize_columns(bj_ctx* ctx, const uint64_t* d_all_values, uint64_t n_values, const uint64_t* d_hint,
+                               uint32_t n_cols, uint64_t hint_rows, uint32_t log_n, uint64_t* d_out);
+BJ_API int32_t bj_create_permutation_polys(bj_ctx* ctx, const uint64_t* d_placement, uint32_t n_cols, uint32_t log_n,
+                                    uint64_t* d_sigmas);
+
 /* ---- the prover entry point: CSReferenceAssembly::prove_cpu_basic (src/cs/implementations/prover.rs:153-2269) and the part of
  *      the setup materialisation it depends on (setup.rs:1093-1255: sigma / constant / lookup-table columns -> LDE -> setup tree).
  * Scope: gates on general-purpose columns (bj_gate_desc programs), copy permutation over all variable columns, optional

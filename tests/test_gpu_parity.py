@@ -727,3 +727,33 @@ def test_blake2s_rfc7693_vector(bj, ctx):
     tree = ctx.merkle_tree_construct([bj.to_device(col)], 1, hasher="blake2s")
     assert bj.to_numpy(tree.leaf_hashes)[0].tobytes() == hashlib.blake2s(bytes(8), digest_size=32).digest()
     assert hashlib.blake2s(b"abc", digest_size=32).hexdigest() == "508c5e8c327c14e2e1a72ba34eeb452f37458b209ed63a294d999b4c86675982"
+
+
+# ---- setup / witness materialisation ----
+@pytest.mark.parametrize("log_n,n_cols,n_vars", [(4, 3, 10), (6, 5, 40), (8, 7, 3000), (10, 12, 200)])
+def test_materialize_columns_and_permutation_polys_match_reference_loops(bj, ctx, log_n, n_cols, n_vars):
+    from oracle import setup_oracle as SO
+    c = ctx
+    rng = np.random.default_rng(log_n * 100 + n_cols)
+    n = 1 << log_n
+    hint_rows = n - 3
+    place = rng.integers(0, n_vars, size=(n_cols, n), dtype=np.uint64)
+    place[rng.random((n_cols, n)) < 0.2] = SO.PLACEHOLDER_BIT          # unassigned cells
+    values = rng.integers(0, 2**64 - 1, size=n_vars, dtype=np.uint64)  # incl. non-canonical values
+    hint = np.ascontiguousarray(place[:, :hint_rows])
+    got = bj.to_numpy(c.materialize_variables_polynomials_from_dense_hint(bj.to_device(values), bj.to_device(hint), log_n))
+    want = SO.materialize_columns([int(v) for v in values], [[int(v) for v in col] for col in hint], n)
+    assert got.tolist() == want
+    sig = bj.to_numpy(c.create_permutation_polys(bj.to_device(place)))
+    want_sig = SO.create_permutation_polys([[int(v) for v in col] for col in place], n)
+    assert sig.tolist() == want_sig
+    # the sigma columns are a permutation of the identity columns k_c * w^row
+    ident = SO.create_permutation_polys([[SO.PLACEHOLDER_BIT] * n for _ in range(n_cols)], n)
+    assert sorted(v for col in sig.tolist() for v in col) == sorted(v for col in ident for v in col)
+
+
+def test_materialize_columns_rejects_out_of_range_hint(bj, ctx):
+    c = ctx
+    hint = bj.to_device(np.array([[0, 1, 5, 2]], dtype=np.uint64))
+    with pytest.raises(bj.BoojumError):
+        c.materialize_variables_polynomials_from_dense_hint(bj.to_device(np.arange(4, dtype=np.uint64)), hint, 2)
