@@ -433,10 +433,10 @@ class Context:
         return out
 
     # ---- native prover driver (bj_setup_create / bj_prove: host C++ inside the library) ----
-    def native_setup(self, sigmas, constants, gates, quotient_degree, config, lookup=None):
+    def native_setup(self, sigmas, constants, gates, quotient_degree, config, lookup=None, public_inputs=()):
         """bj_setup_create.  sigmas [V, n], constants [C, n], lookup["tables"] [width + 1, n]: contiguous int64 CUDA tensors
         (borrowed by the setup: the returned object keeps them alive)."""
-        return NativeSetup(self, sigmas, constants, gates, quotient_degree, config, lookup)
+        return NativeSetup(self, sigmas, constants, gates, quotient_degree, config, lookup, public_inputs)
 
     # ---- queries ----
     def query_leaf_elements(self, sources, indices, elems_per_leaf=1):
@@ -485,7 +485,7 @@ class Context:
 class NativeSetup:
     """bj_setup: setup LDE + setup tree + circuit description held by the library; prove() runs bj_prove (host C++)."""
 
-    def __init__(self, ctx, sigmas, constants, gates, quotient_degree, config, lookup=None):
+    def __init__(self, ctx, sigmas, constants, gates, quotient_degree, config, lookup=None, public_inputs=()):
         import json as _json
         self._json = _json
         self.ctx = ctx
@@ -500,6 +500,10 @@ class NativeSetup:
         if lookup:
             c.lookup_width, c.lookup_num_repetitions = lookup["width"], lookup["num_repetitions"]
             c.lookup_variables_offset, c.lookup_table_id_column = lookup["variables_offset"], lookup["table_id_column"]
+        pis = [(int(a), int(b)) for a, b in public_inputs]
+        pc = (ctypes.c_uint32 * max(1, len(pis)))(*[a for a, _ in pis])
+        pr = (ctypes.c_uint32 * max(1, len(pis)))(*[b for _, b in pis])
+        c.public_input_columns, c.public_input_rows, c.n_public_inputs = pc, pr, len(pis)
         self.cap_size = config.merkle_tree_cap_size
         h = ctypes.c_void_p()
         ctx._check(lib.bj_setup_create(ctx._h, ctypes.byref(c), ctx._ptr(sigmas), ctx._ptr(constants),

@@ -110,6 +110,7 @@ struct bj_setup {
   bj_circuit c{};
   std::vector<bj::GateCopy> gate_store;
   std::vector<bj_gate_desc> gates;
+  std::vector<uint32_t> pi_cols, pi_rows;
   const uint64_t *sigmas = nullptr, *constants = nullptr, *tables = nullptr;  // borrowed, natural row order
   uint32_t n_tables = 0;
   bj::DevMem lde;  // [V + C + T][L][n]
@@ -128,6 +129,7 @@ struct bj_proof {
   std::vector<std::vector<bj::u64>> fri_caps;
   std::vector<bj::u64> mono_c0, mono_c1;
   std::vector<gl::e2> values_at_z, values_at_z_omega, values_at_0;
+  std::vector<bj::u64> public_inputs;
   // queries[q][oracle]: witness, stage 2, quotient, setup, then one per FRI oracle
   std::vector<std::vector<bj::QueryAnswer>> queries;
   double stage_seconds[6] = {0, 0, 0, 0, 0, 0};
@@ -171,6 +173,16 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
     s->gates[g].selector_path = gc.path.data();
   }
   s->c.gates = s->gates.data();
+  if (circuit->n_public_inputs) {
+    if (!circuit->public_input_columns || !circuit->public_input_rows) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_setup_create: public input places missing");
+    s->pi_cols.assign(circuit->public_input_columns, circuit->public_input_columns + circuit->n_public_inputs);
+    s->pi_rows.assign(circuit->public_input_rows, circuit->public_input_rows + circuit->n_public_inputs);
+    for (uint32_t i = 0; i < circuit->n_public_inputs; i++)
+      if (s->pi_cols[i] >= circuit->num_variables || s->pi_rows[i] >= (1ull << circuit->log_n))
+        BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_setup_create: public input place out of range");
+  }
+  s->c.public_input_columns = s->pi_cols.data();
+  s->c.public_input_rows = s->pi_rows.data();
   s->sigmas = d_sigmas;
   s->constants = d_constants;
   s->tables = d_lookup_tables;
@@ -235,6 +247,18 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     return r;
   };
   bj_transcript_witness_merkle_tree_cap(tr, (const uint64_t*)setup->tree.cap.data(), cap);  // prover.rs:211
+  // public inputs: read from the witness, committed to before anything else (prover.rs:264-266)
+  const uint32_t n_pi = c.n_public_inputs;
+  pf->public_inputs.resize(n_pi);
+  for (uint32_t i = 0; i < n_pi; i++)
+    BJ_CUDA(ctx, cudaMemcpyAsync(&pf->public_inputs[i], d_variables + ((size_t)setup->pi_cols[i] << c.log_n) + setup->pi_rows[i], sizeof(u64),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_pi) BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (uint32_t i = 0; i < n_pi; i++) {
+    pf->public_inputs[i] = gl::canon(pf->public_inputs[i]);
+    const uint64_t v = pf->public_inputs[i];
+    bj_transcript_witness_field_elements(tr, &v, 1);
+  }
 
   // ---- round 1: witness commitment ----
   DevMem w_lde, m_lde;
@@ -432,8 +456,27 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   BJ_TRY(mark(3));
 
   // ---- round 5: DEEP combination + FRI ----
+  // public inputs grouped by opening point w^row in order of first appearance (prover.rs:1805-1821)
+  struct PiGroup {
+    u64 at;
+    std::vector<Src> srcs;
+    std::vector<gl::e2> vals;
+  };
+  std::vector<PiGroup> pi_groups;
+  for (uint32_t i = 0; i < n_pi; i++) {
+    const u64 at = gl::pow(gl::omega(log_n), setup->pi_rows[i]);
+    PiGroup* g = nullptr;
+    for (auto& e : pi_groups)
+      if (e.at == at) g = &e;
+    if (!g) {
+      pi_groups.push_back({at, {}, {}});
+      g = &pi_groups.back();
+    }
+    g->srcs.push_back({w_cols[setup->pi_cols[i]], nullptr});
+    g->vals.push_back({pf->public_inputs[i], 0});
+  }
   const gl::e2 ch0 = challenge2();
-  const size_t n_ch = pf->values_at_z.size() + 1 + pf->values_at_0.size();
+  const size_t n_ch = pf->values_at_z.size() + 1 + pf->values_at_0.size() + n_pi;
   std::vector<uint64_t> ch(2 * n_ch);
   {
     gl::e2 cur{1, 0};
@@ -463,6 +506,13 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   BJ_TRY(deep_group(sources, pf->values_at_z, z, ch.data()));
   BJ_TRY(deep_group(z_omega_sources, pf->values_at_z_omega, z_omega, ch.data() + 2 * sources.size()));
   BJ_TRY(deep_group(zero_sources, pf->values_at_0, gl::e2{0, 0}, ch.data() + 2 * (sources.size() + 1)));
+  {
+    size_t off = sources.size() + 1 + zero_sources.size();
+    for (const auto& g : pi_groups) {  // prover.rs:2010-2041
+      BJ_TRY(deep_group(g.srcs, g.vals, gl::e2{g.at, 0}, ch.data() + 2 * off));
+      off += g.srcs.size();
+    }
+  }
   uint32_t new_pow = 0, num_queries = 0, sched[32], sched_len = 0, final_degree = 0;
   BJ_TRY(bj_compute_fri_schedule(c.security_level, cap, c.pow_bits, log_l, log_n, &new_pow, &num_queries, sched, &sched_len, &final_degree));
   if (new_pow != 0) BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "bj_prove: proof-of-work is not implemented (the benches use NoPow)");
@@ -526,7 +576,9 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   s.reserve(1 << 20);
   s += "{\"proof_config\":{\"fri_lde_factor\":" + std::to_string(L) + ",\"merkle_tree_cap_size\":" + std::to_string(cap) +
        ",\"fri_folding_schedule\":null,\"security_level\":" + std::to_string(c.security_level) + ",\"pow_bits\":" + std::to_string(c.pow_bits) +
-       "},\"public_inputs\":[],\"witness_oracle_cap\":";
+       "},\"public_inputs\":";
+  json_u64_list(s, pf->public_inputs.data(), pf->public_inputs.size());
+  s += ",\"witness_oracle_cap\":";
   json_digests(s, pf->witness_cap.data(), cap);
   s += ",\"stage_2_oracle_cap\":";
   json_digests(s, pf->stage2_cap.data(), cap);

@@ -150,4 +150,6 @@ class Circuit(ctypes.Structure):
                 ("quotient_degree", ctypes.c_uint32), ("fri_lde_factor", ctypes.c_uint32), ("merkle_tree_cap_size", ctypes.c_uint32),
                 ("security_level", ctypes.c_uint32), ("pow_bits", ctypes.c_uint32), ("gates", ctypes.POINTER(GateDesc)),
                 ("n_gates", ctypes.c_uint32), ("lookup_width", ctypes.c_uint32), ("lookup_num_repetitions", ctypes.c_uint32),
-                ("lookup_variables_offset", ctypes.c_uint32), ("lookup_table_id_column", ctypes.c_uint32)]
+                ("lookup_variables_offset", ctypes.c_uint32), ("lookup_table_id_column", ctypes.c_uint32),
+                ("public_input_columns", ctypes.POINTER(ctypes.c_uint32)), ("public_input_rows", ctypes.POINTER(ctypes.c_uint32)),
+                ("n_public_inputs", ctypes.c_uint32)]

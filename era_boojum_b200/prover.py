@@ -1,6 +1,6 @@
 """Host driver of the five-round IOP over the B200 kernels, mirroring CSReferenceAssembly::prove_cpu_basic
-(src/cs/implementations/prover.rs:153-2269) for circuits whose gates live on general-purpose columns (no lookup argument,
-no specialised columns, no public inputs yet).  Every heavy step is a C-ABI call into libboojum_b200.so; the transcript,
+(src/cs/implementations/prover.rs:153-2269) for circuits whose gates live on general-purpose columns (optional lookup
+argument over specialised columns, optional public inputs; no gates over specialised columns).  Every heavy step is a C-ABI call into libboojum_b200.so; the transcript,
 the FRI schedule and the proof assembly stay on the host, as in the reference.  The proof is returned in the reference's
 serde shape (src/cs/implementations/proof.rs:57-143).
 
@@ -57,13 +57,14 @@ class Setup:
     """SetupStorage + setup Merkle tree + the fixed parameters of the VerificationKey (setup.rs:1093-1255,
     verifier.rs:31-79): sigma and constant columns, their LDEs, the tree over [sigmas | constants]."""
 
-    def __init__(self, ctx, sigmas, constants, gates, quotient_degree, config, lookup=None, comm=None):
+    def __init__(self, ctx, sigmas, constants, gates, quotient_degree, config, lookup=None, comm=None, public_inputs=()):
         """lookup: None or dict(width, num_repetitions, variables_offset, table_id_column (index into constants),
         tables=[width + 1, n] tensor of lookup-table setup columns, multiplicities are part of the witness).
         comm: None (one GPU) or a communicator of era_boojum_b200.parallel - every rank then keeps the LDE cosets
         j = rank (mod world) only and ctx must carry the matching coset shard (Context.set_coset_shard)."""
         torch = ctx._torch
         self.comm = comm
+        self.public_inputs = [(int(c), int(r)) for c, r in public_inputs]   # (column, row) places (CSReferenceAssembly::public_inputs)
         world = comm.world if comm else 1
         assert ctx.shard_world == world, "Context.set_coset_shard(rank, world, L) must match the communicator"
         assert world == 1 or config.merkle_tree_cap_size >= config.fri_lde_factor, "sharded proving needs cap_size >= LDE factor"
@@ -103,6 +104,7 @@ class Setup:
                 "quotient_degree": self.quotient_degree, "fri_lde_factor": self.config.fri_lde_factor,
                 "cap_size": self.config.merkle_tree_cap_size,
                 "gates": [(g["name"], g["num_repetitions"], list(g["selector_path"])) for g in self.gates],
+                "public_inputs_locations": [list(p) for p in self.public_inputs],
                 "setup_merkle_tree_cap": self.cap.tolist()}
 
 
@@ -177,6 +179,9 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     flat = lambda t: t.reshape(-1)
     tr = Transcript()
     tr.witness_merkle_tree_cap(setup.cap)                                   # prover.rs:211
+    public_values = [int(to_numpy(variables[c, r].reshape(1))[0]) % P for c, r in setup.public_inputs]
+    for v in public_values:                                                 # prover.rs:264-266
+        tr.witness_field_elements([v])
     # ---- round 1: witness commitment (prover.rs:313-353) ----
     t0 = time.perf_counter()
     lk = setup.lookup
@@ -296,8 +301,18 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     mark("4_openings", t0)
     # ---- round 5: DEEP + FRI (prover.rs:1828-2102) ----
     t0 = time.perf_counter()
+    # public inputs are enforced by quotening the variable columns at w^row, grouped by point (prover.rs:1805-1821, 2010-2041)
+    pi_groups = []
+    for (col, row), val in zip(setup.public_inputs, public_values):
+        at = pow(w_n, row, P)
+        for g in pi_groups:
+            if g[0] == at:
+                g[1].append((col, val))
+                break
+        else:
+            pi_groups.append((at, [(col, val)]))
     c = tr.get_multiple_challenges_fixed(2)
-    n_ch = len(values_at_z) + 1 + len(values_at_0)
+    n_ch = len(values_at_z) + 1 + len(values_at_0) + len(public_values)
     ch = [(1, 0), c]
     for _ in range(2, n_ch):
         ch.append(e_mul(ch[-1], c))
@@ -306,8 +321,14 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     ctx.quotening_operation_in_extension(deep0, deep1, sources, values_at_z, z, ch[:len(sources)])
     ctx.quotening_operation_in_extension(deep0, deep1, [(s2_cols[0], s2_cols[1])], values_at_z_omega, z_omega,
                                          ch[len(sources):len(sources) + 1])
+    off_ch = len(sources) + 1
     if lk:
-        ctx.quotening_operation_in_extension(deep0, deep1, zero_sources, values_at_0, (0, 0), ch[len(sources) + 1:])
+        ctx.quotening_operation_in_extension(deep0, deep1, zero_sources, values_at_0, (0, 0), ch[off_ch:off_ch + len(values_at_0)])
+        off_ch += len(values_at_0)
+    for at, members in pi_groups:
+        ctx.quotening_operation_in_extension(deep0, deep1, [(w_cols[col], None) for col, _ in members], [(val, 0) for _, val in members],
+                                             (at, 0), ch[off_ch:off_ch + len(members)])
+        off_ch += len(members)
     import ctypes
     from .native import lib
     np_, nq, sl, fd = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
@@ -360,7 +381,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     queries = [answered[qi] for qi in range(len(idxs))]
     mark("6_queries", t0)
     return {
-        "proof_config": cfg.to_dict(), "public_inputs": [],
+        "proof_config": cfg.to_dict(), "public_inputs": public_values,
         "witness_oracle_cap": w_cap.tolist(), "stage_2_oracle_cap": s2_cap.tolist(), "quotient_oracle_cap": qt_cap.tolist(),
         "final_fri_monomials": [mono0.tolist(), mono1.tolist()],
         "values_at_z": [_ext_dict(v) for v in values_at_z], "values_at_z_omega": [_ext_dict(v) for v in values_at_z_omega],

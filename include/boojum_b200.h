@@ -317,7 +317,7 @@ BJ_API int32_t bj_create_permutation_polys(bj_ctx* ctx, const uint64_t* d_placem
  *      the setup materialisation it depends on (setup.rs:1093-1255: sigma / constant / lookup-table columns -> LDE -> setup tree).
  * Scope: gates on general-purpose columns (bj_gate_desc programs), copy permutation over all variable columns, optional
  * log-derivative lookup over specialised columns with the table id in a constant column (lookup_width = 0: none), Poseidon2
- * tree hasher and transcript, no public inputs, no proof of work.  Host C++ inside the library: transcript, schedule, query
+ * tree hasher and transcript, public inputs, no proof of work.  Host C++ inside the library: transcript, schedule, query
  * indices and proof assembly never leave the host; every heavy step is one of the entry points above.
  * Column arguments are DEVICE arrays [column][2^log_n] in natural row order.  bj_setup BORROWS d_sigmas / d_constants /
  * d_lookup_tables (stage 2 reads them again): they must outlive the setup.  The gate programs are copied.
@@ -334,6 +334,11 @@ typedef struct bj_circuit {
   uint32_t lookup_num_repetitions;  /* sub-arguments */
   uint32_t lookup_variables_offset; /* first lookup column among the variables */
   uint32_t lookup_table_id_column;  /* constant column holding the table id */
+  /* public inputs: places (variable column, row) whose witness values are published (CSReferenceAssembly::public_inputs;
+   * prover.rs:264-266, 1805-1821, 2010-2041) */
+  const uint32_t* public_input_columns;
+  const uint32_t* public_input_rows;
+  uint32_t n_public_inputs;
 } bj_circuit;
 typedef struct bj_setup bj_setup;
 typedef struct bj_proof bj_proof;

@@ -1,6 +1,6 @@
 """ORACLE (test infrastructure): restatement of the reference verifier for circuits built from the bench's three gates
 over general-purpose columns, optionally with the bench's lookup argument over specialised columns (table id in a constant
-column), no public inputs (the acceptance oracle of the prove -> verify tests).
+column), optional public inputs (the acceptance oracle of the prove -> verify tests).
 
 Follows Verifier::verify (src/cs/implementations/verifier.rs:888-2510):
   transcript order :898-1068, alpha-power split :978-1023, quotient identity at z :1144-1828 (gates over general purpose
@@ -71,7 +71,10 @@ def verify(vk, proof):
 
     tr = R.Poseidon2Transcript()
     tr.witness_merkle_tree_cap(vk["setup_merkle_tree_cap"])
-    assert proof["public_inputs"] == []
+    pi_locations = vk.get("public_inputs_locations", [])
+    assert len(proof["public_inputs"]) == len(pi_locations)
+    for v in proof["public_inputs"]:                      # verifier.rs: public inputs enter right after the setup cap
+        tr.witness_field_elements([v])
     tr.witness_merkle_tree_cap(proof["witness_oracle_cap"])
     beta = tr.get_ext_challenge()
     gamma = tr.get_ext_challenge()
@@ -170,8 +173,19 @@ def verify(vk, proof):
     assert t_acc == R.e_mul(t_chunks, vanishing), "Invalid quotient at Z"
 
     # ---- DEEP + FRI ----
+    # public inputs grouped by opening point w^row, in order of first appearance (verifier.rs:1074-1108)
+    w_n = R.omega(log_n)
+    pi_groups = []
+    for (col, row), val in zip(pi_locations, proof["public_inputs"]):
+        at = pow(w_n, row, R.P)
+        for g in pi_groups:
+            if g[0] == at:
+                g[1].append((col, val))
+                break
+        else:
+            pi_groups.append((at, [(col, val)]))
     c = tr.get_ext_challenge()
-    ch = R.ext_powers(c, len(vals_z) + len(vals_zw) + len(vals_0))
+    ch = R.ext_powers(c, len(vals_z) + len(vals_zw) + len(vals_0) + sum(len(g[1]) for g in pi_groups))
     new_pow, num_queries, schedule, final_degree = R.compute_fri_schedule(
         proof["proof_config"]["security_level"], cap_size, proof["proof_config"]["pow_bits"], log_L, log_n)
     assert new_pow == 0 and num_queries == len(proof["queries_per_fri_repetition"])
@@ -215,8 +229,14 @@ def verify(vk, proof):
         x_q = R.fmul(x, 7)
         acc = O.deep_point((0, 0), src, vals_z, ch[:len(src)], x_q, z)
         acc = O.deep_point(acc, ext(sq[0:2]), vals_zw, ch[len(src):len(src) + 1], x_q, z_omega)
+        off_ch = len(src) + 1
         if lk:
-            acc = O.deep_point(acc, ext(sq[off_a:]), vals_0, ch[len(src) + 1:], x_q, (0, 0))
+            acc = O.deep_point(acc, ext(sq[off_a:]), vals_0, ch[off_ch:off_ch + len(vals_0)], x_q, (0, 0))
+            off_ch += len(vals_0)
+        for at, members in pi_groups:                     # (w_col(x) - value) / (x - w^row)
+            acc = O.deep_point(acc, base([wq[col] for col, _ in members]), [(val, 0) for _, val in members],
+                               ch[off_ch:off_ch + len(members)], x_q, (at, 0))
+            off_ch += len(members)
         fqs = [(fq["leaf_elements"], fq["proof"]) for fq in q["fri_queries"]]
         R.verify_fri_query(idx, log_n, log_L, schedule, cap_size, fri_caps, fri_ch, (mono[0], mono[1]), fqs, start_value=acc)
     return True

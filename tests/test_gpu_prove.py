@@ -184,3 +184,51 @@ def test_native_cxx_prover_rejects_unsatisfied_witness(env):
     with pytest.raises(bj.BoojumError):
         nat.prove(bad.contiguous())
     nat.prove(variables.contiguous())
+
+
+@pytest.mark.parametrize("lookup", [False, True])
+def test_public_inputs_python_and_native_drivers(env, lookup):
+    """public inputs (places in the variable columns): committed to first, enforced by quotening at w^row
+    (prover.rs:264-266, 1805-1821, 2010-2041); two of the three share a row, so two opening points."""
+    bj, ctx, prover, synthetic = env
+    gen = synthetic.generate(ctx, 9, 60, seed=21, lookup=lookup)
+    lk = gen[5] if lookup else None
+    variables, sigmas, constants, gates, Q = gen[:5]
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100)
+    places = [(3, 17), (40, 17), (7, 300)]
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg, lookup=lk, public_inputs=places)
+    m = lk["multiplicities"] if lk else None
+    proof = prover.prove(ctx, setup, variables, multiplicities=m)
+    vk = setup.vk()
+    assert proof["public_inputs"] == [int(bj.to_numpy(variables[c, r].reshape(1))[0]) for c, r in places]
+    assert OV.verify(vk, proof)
+    nat = ctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk, public_inputs=places)
+    assert json.dumps(nat.prove(variables, m), sort_keys=True) == json.dumps(proof, sort_keys=True)
+    bad = copy.deepcopy(proof)
+    bad["public_inputs"][1] = (bad["public_inputs"][1] + 1) % bj.P
+    with pytest.raises(AssertionError):
+        OV.verify(vk, bad)
+    # sharded prover agrees as well
+    res = None
+    if not lookup:
+        import threading
+        from era_boojum_b200 import parallel
+        shared, outs, errs = parallel.ThreadComm(2), [None, None], []
+
+        def run(rank):
+            try:
+                c2 = bj.Context(0)
+                c2.set_coset_shard(rank, 2, 8)
+                s2 = prover.Setup(c2, sigmas, constants, gates, Q, cfg, comm=shared.rank_view(rank), public_inputs=places)
+                outs[rank] = prover.prove(c2, s2, variables)
+                c2.synchronize()
+                c2.close()
+            except BaseException as e:
+                errs.append(e)
+                shared._barrier.abort()
+
+        ts = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs, errs
+        assert all(json.dumps(o, sort_keys=True) == json.dumps(proof, sort_keys=True) for o in outs)
