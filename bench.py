@@ -221,6 +221,33 @@ def main():
         sweep["2^%d" % m] = {"cols": cols[m], "ms": round(t_ms, 4), "gelem_s": round(el / t_ms / 1e6, 3),
                              "algo_gbs": round(16 * el / t_ms / 1e6, 1)}
 
+    # the rest of the NTT family at 2^22 (SURVEY 8d cfg 2): inverse (natural -> natural, coset 7) and LDE to 2 / 4 / 8 cosets
+    family = {}
+    if not args.no_e2e:
+        m = 22
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.ifft_natural_to_natural(data[m], COSET)
+        a0.record()
+        for _ in range(3):
+            ctx.ifft_natural_to_natural(data[m], COSET)
+        a1.record()
+        torch.cuda.synchronize()
+        t_ms = a0.elapsed_time(a1) / 3
+        family["inverse_2^22"] = {"cols": cols[m], "ms": round(t_ms, 4), "gelem_s": round((cols[m] << m) / t_ms / 1e6, 3)}
+        src = data[m][:8]
+        for lde in (2, 4, 8):
+            out_l = torch.empty((8, lde, 1 << m), dtype=torch.int64, device=dev)
+            ctx.transform_raw_storages_to_lde(src, lde, out=out_l)
+            a0.record()
+            for _ in range(3):
+                ctx.transform_raw_storages_to_lde(src, lde, out=out_l)
+            a1.record()
+            torch.cuda.synchronize()
+            t_ms = a0.elapsed_time(a1) / 3
+            family["lde%d_2^22" % lde] = {"cols": 8, "ms": round(t_ms, 4), "in_gelem_s": round((8 << m) / t_ms / 1e6, 3),
+                                           "algo_gbs": round(8 * (1 + lde) * (8 << m) / t_ms / 1e6, 1)}
+            del out_l
+
     peak, peak_kind = load_peaks()
     launches_per_step = launches / max(1, args.steps)
     algo_bytes_step = 16.0 * elems_per_step
@@ -270,7 +297,7 @@ def main():
         "config": {"workload": "ntt_forward_sweep_2^20..2^24_coset7", "sizes_log2": SIZES,
                    "columns_per_size": [cols[m] for m in SIZES], "resident_bytes_per_gpu": 8 * elems_per_step,
                    "l2": "inputs (5 GiB) larger than L2, no flush", "parallelism": "columns sharded x%d, no collective" % world},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "sweep": sweep, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "sweep": sweep, "ntt_family": family, "e2e": e2e,
     }
     # BASELINE configs[2]: Poseidon2 Merkle tree over 2^22 leaves x 100 columns (cap 16), device-resident columns
     if world == 1 and args.prove_log_n > 0:

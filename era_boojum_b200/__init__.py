@@ -91,10 +91,13 @@ class FriOracles:
             raise BoojumError(st, "bj_fri_oracles_query")
         return le, path[: plen.value]
 
-    def __del__(self):
+    def close(self):
         if getattr(self, "_h", None):
             lib.bj_fri_oracles_free(self._h)
             self._h = None
+
+    def __del__(self):
+        self.close()
 
 
 def to_device(a, device="cuda:0"):
@@ -155,6 +158,8 @@ class Context:
             raise BoojumError(st, lib.bj_status_string(st).decode())
         self._h = handle
         self._stream = stream
+        import weakref
+        self._children = weakref.WeakSet()   # library objects that hold device memory of this context (freed before it)
 
     @classmethod
     def on_current_stream(cls, device=0):
@@ -164,6 +169,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                child.close()
             lib.bj_ctx_destroy(self._h)
             self._h = None
 
@@ -436,7 +443,9 @@ class Context:
     def native_setup(self, sigmas, constants, gates, quotient_degree, config, lookup=None, public_inputs=()):
         """bj_setup_create.  sigmas [V, n], constants [C, n], lookup["tables"] [width + 1, n]: contiguous int64 CUDA tensors
         (borrowed by the setup: the returned object keeps them alive)."""
-        return NativeSetup(self, sigmas, constants, gates, quotient_degree, config, lookup, public_inputs)
+        ns = NativeSetup(self, sigmas, constants, gates, quotient_degree, config, lookup, public_inputs)
+        self._children.add(ns)
+        return ns
 
     # ---- queries ----
     def query_leaf_elements(self, sources, indices, elems_per_leaf=1):
@@ -466,7 +475,9 @@ class Context:
         h = ctypes.c_void_p()
         self._check(lib.bj_do_fri(self._h, transcript._h, self._ptr(c0), self._ptr(c1), log_full, sched, len(schedule),
                                   lde_degree.bit_length() - 1, cap_size, ctypes.byref(h)))
-        return FriOracles(h, cap_size, (c0, c1))
+        fo = FriOracles(h, cap_size, (c0, c1))
+        self._children.add(fo)
+        return fo
 
     def fri_fold(self, c0, c1, log_fold, alpha, coset_inv):
         """One oracle step (log_fold folds).  Returns (out_c0, out_c1, new_coset_inv)."""

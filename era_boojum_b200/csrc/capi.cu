@@ -113,6 +113,22 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
   ctx->ntt_pass1_w = env_int("BJ_NTT_PASS1_W", -1);
   ctx->ntt_use_v2 = env_int("BJ_NTT_V2", 1);
   ctx->ntt_full_pow = env_int("BJ_NTT_FULL_POW", 1);
+  {
+    // the prover driver allocates tens of GB per proof: a private pool that never trims keeps the second and later
+    // proofs free of cudaMalloc / page-mapping cost (the default pool returns memory to the OS at every synchronisation)
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      cudaGetLastError();
+      ctx->pool = nullptr;
+    }
+  }
   int32_t st = poseidon2_init_constants(ctx);
   if (st != BJ_OK) {
     delete ctx;
@@ -133,6 +149,7 @@ int32_t bj_ctx_destroy(bj_ctx* ctx) {
     cudaFree(e.hi);
     if (e.full) cudaFree(e.full);
   }
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->ptr_table) cudaFree(ctx->ptr_table);
   if (ctx->param_arena) cudaFree(ctx->param_arena);

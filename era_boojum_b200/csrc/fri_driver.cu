@@ -42,13 +42,19 @@ __global__ void gather_paths_kernel(const u64* __restrict__ leaf_hashes, const u
   out[i] = gl::canon(layer[4 * (pos ^ 1) + k]);
 }
 
+// device buffer from the context's stream-ordered pool (no device-wide synchronisation on allocation or release)
 struct DevBuf {
   void* p = nullptr;
+  bj_ctx* owner = nullptr;
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (!p) return;
+    if (owner && owner->pool) cudaFreeAsync(p, owner->stream);
+    else cudaFree(p);
   }
   int32_t alloc(bj_ctx* ctx, size_t bytes) {
-    if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) {
+    owner = ctx;
+    const cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync(&p, bytes ? bytes : 8, ctx->pool, ctx->stream) : cudaMalloc(&p, bytes ? bytes : 8);
+    if (e != cudaSuccess) {
       cudaGetLastError();
       p = nullptr;
       BJ_FAIL(ctx, BJ_ERR_OOM, "FRI: device allocation failed");

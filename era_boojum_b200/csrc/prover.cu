@@ -34,7 +34,9 @@ struct DevMem {
   int32_t alloc(bj_ctx* c, size_t n_u64) {
     release();
     ctx = c;
-    if (cudaMallocAsync((void**)&p, sizeof(u64) * (n_u64 ? n_u64 : 1), c->stream) != cudaSuccess) {
+    const size_t bytes = sizeof(u64) * (n_u64 ? n_u64 : 1);
+    const cudaError_t e = c->pool ? cudaMallocFromPoolAsync((void**)&p, bytes, c->pool, c->stream) : cudaMallocAsync((void**)&p, bytes, c->stream);
+    if (e != cudaSuccess) {
       cudaGetLastError();
       p = nullptr;
       BJ_FAIL(c, BJ_ERR_OOM, "prover: device allocation failed");

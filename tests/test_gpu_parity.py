@@ -560,6 +560,30 @@ def test_query_helpers_match_oracle(bj, ctx):
         assert O.merkle_verify(O.poseidon2_hash_leaf(rows[q]), paths[q], capd, i)
 
 
+def test_merkle_full_size_config3_paths_verify_against_cap(bj, ctx):
+    """BASELINE config 3 (2^22 leaves x 100 columns, cap 16): the oracle cannot rebuild the tree in seconds, so the full-size
+    check is the size-independent one - 192 random leaves are re-hashed by the oracle from the opened rows and their paths
+    must lead to the cap the GPU produced (a wrong node anywhere on those paths, or a wrong leaf hash, breaks it)."""
+    import torch
+    log_leaves, n_cols, cap = 22, 100, 16
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(7)
+    d_cols = [torch.randint(0, 2**63 - 1, (1 << log_leaves,), dtype=torch.int64, device="cuda:0", generator=gen) for _ in range(n_cols)]
+    tree = ctx.merkle_tree_construct(d_cols, cap)
+    capd = tree.get_cap()
+    assert capd.shape == (cap, 4) and len({tuple(r) for r in capd.tolist()}) == cap
+    idx = [0, (1 << log_leaves) - 1] + [int(v) for v in rng(5).integers(0, 1 << log_leaves, 190)]
+    rows = ctx.query_leaf_elements(d_cols, idx)
+    paths = ctx.merkle_paths(tree, idx)
+    assert paths.shape[1] == log_leaves - 4
+    for q, i in enumerate(idx):
+        assert O.merkle_verify(O.poseidon2_hash_leaf(rows[q]), paths[q], capd, i), i
+    # a flipped bit in an opened row must not verify
+    bad = rows[0].copy()
+    bad[37] ^= 1
+    assert not O.merkle_verify(O.poseidon2_hash_leaf(bad), paths[0], capd, idx[0])
+
+
 # ------------------------------------------------------------------------------------ stage 2 (copy permutation) -----
 def _satisfying_copy_permutation(r, n_cols, log_n):
     """variable columns with repeated values and sigma columns encoding the cycles of equal cells
