@@ -418,6 +418,7 @@ class Context:
             d.constants_offset = g.get("constants_offset", 0)
             d.constants_placement_offset = g["constants_placement_offset"]
             d.selector_path_len, d.selector_path = len(g["selector_path"]), path
+            d.variables_initial_offset, d.witnesses_initial_offset = g.get("variables_initial_offset", 0), g.get("witnesses_initial_offset", 0)
         return keep, descs
 
     # ---- setup / witness materialisation ----

@@ -1,4 +1,4 @@
-// Per-row gate / quotient evaluator over general-purpose columns.
+// Per-row gate / quotient evaluator over general-purpose columns and over specialised columns.
 //
 // Reference semantics (what is computed, bit-exact):
 //   * a gate's constraint terms come from GateConstraintEvaluator::evaluate_once (src/cs/traits/evaluator.rs:145-152),
@@ -11,6 +11,9 @@
 //     (compute_selector_subpath, src/cs/implementations/prover.rs:2775-2916); the gate's own constants start at column
 //     `path length` (constant_placement_offset, prover.rs:1000-1013);
 //   * driver: the row loop of prove_cpu_basic (prover.rs:1031-1080) over the first Q cosets of the LDE.
+//   * gates placed on SPECIALISED columns (GatePlacementStrategy::UseSpecializedColumns, prover.rs:653-801) own a fixed range
+//     of columns: no selector, the first repetition starts at the gate's initial offset, constants start behind those of
+//     the general-purpose gates (shared by the repetitions when share_constants); their terms precede the general-purpose ones.
 // The gate itself is data: the SSA program the reference's own GPU hook records (gpu_synthesizer::GPUDataCapture,
 // src/gpu_synthesizer/mod.rs:115-133, 354-443) - Index::{VariablePoly, WitnessPoly, ConstantPoly, TemporaryValue,
 // ConstantValue} and Relation::{Add, Double, Sub, Negate, Mul, Square, Inverse} - so any evaluator the reference can
@@ -38,10 +41,10 @@ struct DevGate {
   u32 writes_begin, n_writes;
   u32 num_repetitions;
   u32 var_offset, wit_offset, const_offset;  // PerChunkOffset
+  u32 var_base, wit_base;                     // first column of repetition 0 (specialised placement; 0 for general purpose)
   u32 const_placement;                        // first constant column of the gate (= selector path length)
   u32 path_len;
   u32 path_bits;  // bit i = path[i]
-  u32 pad;
 };
 
 struct GateEvalParams {
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(128) gate_eval_kernel(const GateEvalParams p) 
     const DevGate gate = p.gates[g];
     gl::e2 acc = {0, 0};
     for (u32 rep = 0; rep < gate.num_repetitions; rep++) {
-      const u32 vbase = rep * gate.var_offset, wbase = rep * gate.wit_offset;
+      const u32 vbase = gate.var_base + rep * gate.var_offset, wbase = gate.wit_base + rep * gate.wit_offset;
       const u32 cshared = gate.const_placement, cbase = cshared + rep * gate.const_offset;
       for (u32 i = 0; i < gate.n_ops; i++) {
         const DevOp op = p.ops[gate.ops_begin + i];
@@ -137,10 +140,10 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     const uint32_t reps = g.num_repetitions ? g.num_repetitions - 1 : 0;
     switch (ix.kind) {
       case BJ_IDX_VARIABLE:
-        if (ix.value + (uint64_t)reps * g.variables_offset >= n_variables) return false;
+        if (g.variables_initial_offset + ix.value + (uint64_t)reps * g.variables_offset >= n_variables) return false;
         break;
       case BJ_IDX_WITNESS:
-        if (ix.value + (uint64_t)reps * g.witnesses_offset >= n_witnesses) return false;
+        if (g.witnesses_initial_offset + ix.value + (uint64_t)reps * g.witnesses_offset >= n_witnesses) return false;
         break;
       case BJ_IDX_CONSTANT_POLY:
         if (g.constants_placement_offset + ix.value + (uint64_t)reps * g.constants_offset >= n_constants) return false;
@@ -172,6 +175,8 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     d.num_repetitions = g.num_repetitions;
     d.var_offset = g.variables_offset;
     d.wit_offset = g.witnesses_offset;
+    d.var_base = g.variables_initial_offset;
+    d.wit_base = g.witnesses_initial_offset;
     d.const_offset = g.constants_offset;
     d.const_placement = g.constants_placement_offset;
     d.path_len = g.selector_path_len;

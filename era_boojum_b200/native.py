@@ -137,7 +137,8 @@ class GateDesc(ctypes.Structure):
                 ("writes", ctypes.POINTER(GateIndex)), ("num_repetitions", ctypes.c_uint32),
                 ("variables_offset", ctypes.c_uint32), ("witnesses_offset", ctypes.c_uint32),
                 ("constants_offset", ctypes.c_uint32), ("constants_placement_offset", ctypes.c_uint32),
-                ("selector_path_len", ctypes.c_uint32), ("selector_path", ctypes.POINTER(ctypes.c_uint8))]
+                ("selector_path_len", ctypes.c_uint32), ("selector_path", ctypes.POINTER(ctypes.c_uint8)),
+                ("variables_initial_offset", ctypes.c_uint32), ("witnesses_initial_offset", ctypes.c_uint32)]
 
 
 IDX_VARIABLE, IDX_WITNESS, IDX_CONSTANT_POLY, IDX_TEMPORARY, IDX_CONSTANT_VALUE, IDX_CONSTANT_POLY_SHARED = range(6)

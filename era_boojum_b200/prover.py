@@ -103,7 +103,8 @@ class Setup:
         return {"lookup": lk, "domain_size": 1 << self.log_n, "num_variables": self.num_variables, "num_constants": self.num_constants,
                 "quotient_degree": self.quotient_degree, "fri_lde_factor": self.config.fri_lde_factor,
                 "cap_size": self.config.merkle_tree_cap_size,
-                "gates": [(g["name"], g["num_repetitions"], list(g["selector_path"])) for g in self.gates],
+                "gates": [(g["name"], g["num_repetitions"], list(g["selector_path"]), g.get("variables_initial_offset", 0),
+                           g["constants_placement_offset"]) for g in self.gates],
                 "public_inputs_locations": [list(p) for p in self.public_inputs],
                 "setup_merkle_tree_cap": self.cap.tolist()}
 

@@ -136,3 +136,31 @@ def generate(ctx, log_n, num_variables=60, seed=0, lookup=False):
     lk = dict(width=width, num_repetitions=nsub, variables_offset=n_gp, table_id_column=6, tables=tables.contiguous(),
               multiplicities=mult.contiguous())
     return variables.contiguous(), sigmas.contiguous(), constants.contiguous(), gates, 4, lk
+
+
+def add_specialized_fma(ctx, variables, sigmas, constants, gates, repetitions=2, seed=0):
+    """Places `repetitions` FMA gates on SPECIALISED columns (GatePlacementStrategy::UseSpecializedColumns with
+    share_constants = true, src/cs/implementations/prover.rs:653-801): 4 * repetitions extra variable columns that satisfy
+    d = c0 * a * b + c1 * c on EVERY row (no selector), two extra constant columns shared by the repetitions.  The gate is
+    put first in the gate list, as the reference orders the quotient terms (specialised before general purpose)."""
+    torch = ctx._torch
+    V0, n = variables.shape
+    C0 = constants.shape[0]
+    dev = variables.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1000 + seed)
+    rnd = lambda shape, hi: torch.randint(0, hi, shape, dtype=torch.int64, device=dev, generator=gen)
+    c0, c1 = rnd((n,), 1 << 10) + 1, rnd((n,), 1 << 10)
+    cols = rnd((4 * repetitions, n), 1 << 20)
+    for k in range(repetitions):
+        cols[4 * k + 3] = c0 * cols[4 * k] * cols[4 * k + 1] + c1 * cols[4 * k + 2]
+    Vt = V0 + 4 * repetitions
+    ks = ctx.non_residues_for_copy_permutation(n, Vt)
+    mono = torch.zeros((Vt, n), dtype=torch.int64, device=dev)
+    mono[:, 1 if n > 1 else 0] = torch.from_numpy(ks.view(np.int64)).to(dev)
+    ctx.fft_natural_to_bitreversed(mono, 1)
+    ctx.bitreverse_enumeration_inplace(mono)
+    g = dict(FMA)
+    g.update(name="fma", num_repetitions=repetitions, constants_placement_offset=C0, selector_path=[], variables_initial_offset=V0)
+    return (torch.cat([variables, cols]).contiguous(), torch.cat([sigmas, mono[V0:]]).contiguous(),
+            torch.cat([constants, torch.stack([c0, c1])]).contiguous(), [g] + list(gates))

@@ -182,7 +182,7 @@ BJ_API int32_t bj_quotient_lookup_specialized(bj_ctx* ctx, const uint64_t* const
                                        const uint64_t* h_alphas, uint64_t n_points, uint64_t* d_q_c0, uint64_t* d_q_c1);
 
 /* ---- gate / quotient evaluator over general-purpose columns: the row loop of prove_cpu_basic
- *      (src/cs/implementations/prover.rs:1031-1080) with GateConstraintEvaluator::evaluate_once (src/cs/traits/evaluator.rs:145-152)
+ *      (src/cs/implementations/prover.rs:1031-1080; gates over specialised columns, :653-801, use the same call) with GateConstraintEvaluator::evaluate_once (src/cs/traits/evaluator.rs:145-152)
  *      supplied as DATA: the SSA program recorded by the reference's own GPU hook, gpu_synthesizer::GPUDataCapture
  *      (src/gpu_synthesizer/mod.rs:115-133 Index / Relation, :354-443 capture). */
 enum { /* Index<F> (gpu_synthesizer/mod.rs:115-121); SHARED = a ConstantPoly listed in row_shared_constants_set */
@@ -214,6 +214,12 @@ typedef struct bj_gate_desc {
   uint32_t constants_placement_offset; /* first constant column of the gate = selector path length (prover.rs:1000-1013) */
   uint32_t selector_path_len;          /* TreeNode path of the gate; 0 = no selector */
   const uint8_t* selector_path;        /* path[i] != 0: factor const_i, else (1 - const_i) (prover.rs:2775-2916) */
+  /* gates on SPECIALISED columns (GatePlacementStrategy::UseSpecializedColumns, prover.rs:653-801): first column of
+   * repetition 0 among the variable / witness columns (initial_offset of offsets_for_specialized_evaluators); 0 for
+   * general-purpose gates.  Such a gate has selector_path_len = 0, constants_placement_offset = (constants of the
+   * general-purpose gates) + initial constants offset, and constants_offset = 0 when share_constants. */
+  uint32_t variables_initial_offset;
+  uint32_t witnesses_initial_offset;
 } bj_gate_desc;
 /* For every point t < n_points (= Q * n, the first Q cosets of the LDE, flat coset-major):
  *   q[t] += sum_g selector_g(t) * sum_k alpha_pow[k] * term_k(t),  k running over the terms of all gates in order

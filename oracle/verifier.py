@@ -83,7 +83,7 @@ def verify(vk, proof):
         lookup_gamma = tr.get_ext_challenge()
     tr.witness_merkle_tree_cap(proof["stage_2_oracle_cap"])
     alpha = tr.get_ext_challenge()
-    n_gate_terms = sum(reps for _, reps, _ in gates)  # one term per repetition for the three bench gates
+    n_gate_terms = sum(g[1] for g in gates)  # one term per repetition for the three bench gates
     total_terms = n_lk_terms + n_gate_terms + 1 + 1 + n_partial
     powers = [(1, 0)]
     for _ in range(1, total_terms):
@@ -137,15 +137,20 @@ def verify(vk, proof):
             d = R.e_add(d, R.e_mul(gp[j], table_v[j]))
         t_acc = R.e_add(t_acc, R.e_mul(R.e_sub(R.e_mul(b_v[0], d), mult_v[0]), lk_ch[nsub]))
     k = 0
-    for name, reps, path in gates:
+    for g in gates:
+        # (name, repetitions, selector path[, first variable column, first constant column]); the optional pair places a
+        # gate on specialised columns (prover.rs:653-801): no selector, terms listed before the general-purpose gates
+        name, reps, path = g[0], g[1], g[2]
+        var0 = g[3] if len(g) > 3 else 0
+        const0 = g[4] if len(g) > 4 else len(path)
         fn, width, (voff, coff) = GATES[name]
         sel = (1, 0)
         for i, bit in enumerate(path):
             sel = R.e_mul(sel, const_v[i] if bit else R.e_sub((1, 0), const_v[i]))
         acc = (0, 0)
         for rep in range(reps):
-            v = var_v[rep * voff: rep * voff + width]
-            c = const_v[len(path) + rep * coff:]
+            v = var_v[var0 + rep * voff: var0 + rep * voff + width]
+            c = const_v[const0 + rep * coff:]
             for term in fn(v, c):
                 acc = R.e_add(acc, R.e_mul(term, gp_ch[k]))
                 k += 1

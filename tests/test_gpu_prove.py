@@ -232,3 +232,25 @@ def test_public_inputs_python_and_native_drivers(env, lookup):
         [t.join() for t in ts]
         assert not errs, errs
         assert all(json.dumps(o, sort_keys=True) == json.dumps(proof, sort_keys=True) for o in outs)
+
+
+@pytest.mark.parametrize("lookup", [False, True])
+def test_gates_over_specialized_columns(env, lookup):
+    """an FMA gate placed on specialised columns (no selector, shared constants, terms ahead of the general-purpose gates;
+    prover.rs:653-801) next to the selector-tree gates: prove (Python driver and native C++ driver) -> verify."""
+    bj, ctx, prover, synthetic = env
+    gen = synthetic.generate(ctx, 9, 60, seed=31, lookup=lookup)
+    lk = gen[5] if lookup else None
+    variables, sigmas, constants, gates, Q = gen[:5]
+    variables, sigmas, constants, gates = synthetic.add_specialized_fma(ctx, variables, sigmas, constants, gates, repetitions=3, seed=1)
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100)
+    m = lk["multiplicities"] if lk else None
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg, lookup=lk)
+    proof = prover.prove(ctx, setup, variables, multiplicities=m)
+    assert OV.verify(setup.vk(), proof)
+    nat = ctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk)
+    assert json.dumps(nat.prove(variables, m), sort_keys=True) == json.dumps(proof, sort_keys=True)
+    bad = variables.clone()
+    bad[variables.shape[0] - 1, 9] += 1            # break the last specialised repetition on one row
+    with pytest.raises(ValueError):
+        prover.prove(ctx, setup, bad, multiplicities=m)
