@@ -29,8 +29,10 @@ __all__ = ["Context", "MerkleTreeWithCap", "Transcript", "FriOracles", "BoojumEr
 class Transcript:
     """GoldilocksPoisedon2Transcript (cs/implementations/transcript.rs:62-129, 140-151) - host side."""
 
-    def __init__(self):
-        self._h = ctypes.c_void_p(lib.bj_transcript_new())
+    def __init__(self, kind="poseidon2"):
+        """kind: "poseidon2" (GoldilocksPoisedon2Transcript) or "blake2s" (Blake2sTranscript, transcript.rs:155-260)."""
+        self.kind = kind
+        self._h = ctypes.c_void_p(lib.bj_transcript_new_blake2s() if kind == "blake2s" else lib.bj_transcript_new())
 
     def witness_field_elements(self, els):
         a = np.ascontiguousarray(np.array([int(e) for e in els], dtype=np.uint64))
@@ -469,13 +471,13 @@ class Context:
         return out[:, :depth, :]
 
     # ---- FRI ----
-    def do_fri(self, transcript, c0, c1, schedule, lde_degree, cap_size):
+    def do_fri(self, transcript, c0, c1, schedule, lde_degree, cap_size, hasher="poseidon2"):
         """do_fri (cs/implementations/fri/mod.rs:49-357): commit phase driven from the host transcript."""
         log_full = c0.numel().bit_length() - 1
         sched = (ctypes.c_uint32 * len(schedule))(*schedule)
         h = ctypes.c_void_p()
-        self._check(lib.bj_do_fri(self._h, transcript._h, self._ptr(c0), self._ptr(c1), log_full, sched, len(schedule),
-                                  lde_degree.bit_length() - 1, cap_size, ctypes.byref(h)))
+        self._check(lib.bj_do_fri_with_hasher(self._h, transcript._h, self._ptr(c0), self._ptr(c1), log_full, sched, len(schedule),
+                                              lde_degree.bit_length() - 1, cap_size, {"poseidon2": 0, "blake2s": 1}[hasher], ctypes.byref(h)))
         fo = FriOracles(h, cap_size, (c0, c1))
         self._children.add(fo)
         return fo
@@ -516,6 +518,8 @@ class NativeSetup:
         pc = (ctypes.c_uint32 * max(1, len(pis)))(*[a for a, _ in pis])
         pr = (ctypes.c_uint32 * max(1, len(pis)))(*[b for _, b in pis])
         c.public_input_columns, c.public_input_rows, c.n_public_inputs = pc, pr, len(pis)
+        c.tree_hasher = {"poseidon2": 0, "blake2s": 1}[getattr(config, "hasher", "poseidon2")]
+        c.transcript = {"poseidon2": 0, "blake2s": 1}[getattr(config, "transcript", "poseidon2")]
         self.cap_size = config.merkle_tree_cap_size
         h = ctypes.c_void_p()
         ctx._check(lib.bj_setup_create(ctx._h, ctypes.byref(c), ctx._ptr(sigmas), ctx._ptr(constants),

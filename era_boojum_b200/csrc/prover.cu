@@ -54,14 +54,14 @@ struct Oracle {
   std::vector<u64> cap;  // host, 4 * cap_size
 };
 
-static int32_t oracle_build(bj_ctx* ctx, Oracle& o, u64 n_leaves, u32 cap_size) {
+static int32_t oracle_build(bj_ctx* ctx, Oracle& o, u64 n_leaves, u32 cap_size, u32 hasher) {
   o.n_leaves = n_leaves;
   o.cap_size = cap_size;
   if (n_leaves < cap_size) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "prover: oracle smaller than the cap");
   BJ_TRY(o.leaf_hashes.alloc(ctx, 4 * n_leaves));
   BJ_TRY(o.nodes.alloc(ctx, 4 * (n_leaves - cap_size)));
-  BJ_TRY(bj_merkle_build_poseidon2(ctx, o.cols.data(), (u32)o.cols.size(), n_leaves, 1, cap_size, (uint64_t*)o.leaf_hashes.p,
-                                   (uint64_t*)o.nodes.p));
+  BJ_TRY((hasher == BJ_HASHER_BLAKE2S ? bj_merkle_build_blake2s : bj_merkle_build_poseidon2)(
+      ctx, o.cols.data(), (u32)o.cols.size(), n_leaves, 1, cap_size, (uint64_t*)o.leaf_hashes.p, (uint64_t*)o.nodes.p));
   o.cap.resize(4 * (size_t)cap_size);
   const u64* src = n_leaves == cap_size ? o.leaf_hashes.p : o.nodes.p + 4 * (n_leaves - 2 * (u64)cap_size);
   BJ_CUDA(ctx, cudaMemcpyAsync(o.cap.data(), src, sizeof(u64) * 4 * cap_size, cudaMemcpyDeviceToHost, ctx->stream));
@@ -149,7 +149,7 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
   if (!ctx || !circuit || !d_sigmas || !out || circuit->num_variables == 0 || circuit->log_n == 0 || circuit->log_n > 28 ||
       !is_pow2(circuit->fri_lde_factor) || !is_pow2(circuit->merkle_tree_cap_size) || !is_pow2(circuit->quotient_degree) ||
       circuit->quotient_degree > circuit->fri_lde_factor || (circuit->num_constants && !d_constants) ||
-      (circuit->n_gates && !circuit->gates))
+      (circuit->n_gates && !circuit->gates) || circuit->tree_hasher > BJ_HASHER_BLAKE2S || circuit->transcript > 1)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_setup_create: bad argument");
   if (circuit->lookup_width && (!d_lookup_tables || circuit->lookup_table_id_column >= circuit->num_constants ||
                                 circuit->lookup_variables_offset + circuit->lookup_width * circuit->lookup_num_repetitions >
@@ -197,7 +197,7 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
   if (C) BJ_TRY(bj_lde(ctx, d_constants, n, (uint64_t*)s->lde.p + ((size_t)V << (log_n + log_l)), log_n, log_l, C, 0));
   if (T) BJ_TRY(bj_lde(ctx, d_lookup_tables, n, (uint64_t*)s->lde.p + ((size_t)(V + C) << (log_n + log_l)), log_n, log_l, T, 0));
   for (uint32_t j = 0; j < V + C + T; j++) s->tree.cols.push_back(s->col(j));
-  BJ_TRY(oracle_build(ctx, s->tree, n << log_l, circuit->merkle_tree_cap_size));
+  BJ_TRY(oracle_build(ctx, s->tree, n << log_l, circuit->merkle_tree_cap_size, circuit->tree_hasher));
   *out = s.release();
   return BJ_OK;
 }
@@ -240,7 +240,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   struct TrGuard {
     bj_transcript* t;
     ~TrGuard() { bj_transcript_free(t); }
-  } trg{bj_transcript_new()};
+  } trg{c.transcript == 1 ? bj_transcript_new_blake2s() : bj_transcript_new()};
   bj_transcript* tr = trg.t;
   auto challenge2 = [&]() {
     gl::e2 r;
@@ -275,7 +275,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     BJ_TRY(bj_lde(ctx, d_multiplicities, n, (uint64_t*)m_lde.p, log_n, log_l, 1, 0));
     w_or.cols.push_back((const uint64_t*)m_lde.p);  // variables | witness (none) | multiplicities
   }
-  BJ_TRY(oracle_build(ctx, w_or, nL, cap));
+  BJ_TRY(oracle_build(ctx, w_or, nL, cap, c.tree_hasher));
   pf->witness_cap = w_or.cap;
   bj_transcript_witness_merkle_tree_cap(tr, (const uint64_t*)w_or.cap.data(), cap);
   BJ_TRY(mark(0));
@@ -318,7 +318,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   for (uint32_t j = 0; j < n_s2; j++) s2_cols[j] = (const uint64_t*)s2_lde.p + (size_t)j * nL;
   Oracle s2_or;
   s2_or.cols = s2_cols;
-  BJ_TRY(oracle_build(ctx, s2_or, nL, cap));
+  BJ_TRY(oracle_build(ctx, s2_or, nL, cap, c.tree_hasher));
   pf->stage2_cap = s2_or.cap;
   bj_transcript_witness_merkle_tree_cap(tr, (const uint64_t*)s2_or.cap.data(), cap);
   const uint32_t a_off = 2 + 2 * n_partial;
@@ -394,7 +394,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   for (uint32_t j = 0; j < 2 * Q; j++) qt_cols[j] = (const uint64_t*)qt_lde.p + (size_t)j * nL;
   Oracle qt_or;
   qt_or.cols = qt_cols;
-  BJ_TRY(oracle_build(ctx, qt_or, nL, cap));
+  BJ_TRY(oracle_build(ctx, qt_or, nL, cap, c.tree_hasher));
   pf->quotient_cap = qt_or.cap;
   bj_transcript_witness_merkle_tree_cap(tr, (const uint64_t*)qt_or.cap.data(), cap);
   BJ_TRY(mark(2));
@@ -519,7 +519,8 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   BJ_TRY(bj_compute_fri_schedule(c.security_level, cap, c.pow_bits, log_l, log_n, &new_pow, &num_queries, sched, &sched_len, &final_degree));
   if (new_pow != 0) BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "bj_prove: proof-of-work is not implemented (the benches use NoPow)");
   bj_fri_oracles* fri = nullptr;
-  BJ_TRY(bj_do_fri(ctx, tr, (const uint64_t*)deep.p, (const uint64_t*)deep.p + nL, log_n + log_l, sched, sched_len, log_l, cap, &fri));
+  BJ_TRY(bj_do_fri_with_hasher(ctx, tr, (const uint64_t*)deep.p, (const uint64_t*)deep.p + nL, log_n + log_l, sched, sched_len, log_l, cap,
+                               c.tree_hasher, &fri));
   struct FriGuard {
     bj_fri_oracles* f;
     ~FriGuard() { bj_fri_oracles_free(f); }

@@ -78,6 +78,7 @@ SIGNATURES = {
     "bj_ntt_natural_to_bitreversed_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
     "bj_intt_natural_to_natural_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
     "bj_transcript_new": (_vp, []),
+    "bj_transcript_new_blake2s": (_vp, []),
     "bj_transcript_free": (None, [_vp]),
     "bj_transcript_witness_field_elements": (None, [_vp, _vp, _sz]),
     "bj_transcript_witness_merkle_tree_cap": (None, [_vp, _vp, _sz]),
@@ -85,6 +86,7 @@ SIGNATURES = {
     "bj_transcript_get_index_bits": (_u64, [_vp, _u32, _u32]),
     "bj_compute_fri_schedule": (_i32, [_u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "bj_do_fri": (_i32, [_vp, _vp, _vp, _vp, _u32, _vp, _u32, _u32, _u32, _pp]),
+    "bj_do_fri_with_hasher": (_i32, [_vp, _vp, _vp, _vp, _u32, _vp, _u32, _u32, _u32, _u32, _pp]),
     "bj_fri_oracles_free": (None, [_vp]),
     "bj_fri_oracles_num_oracles": (_u32, [_vp]),
     "bj_fri_oracles_num_monomials": (_u32, [_vp]),
@@ -153,4 +155,4 @@ class Circuit(ctypes.Structure):
                 ("n_gates", ctypes.c_uint32), ("lookup_width", ctypes.c_uint32), ("lookup_num_repetitions", ctypes.c_uint32),
                 ("lookup_variables_offset", ctypes.c_uint32), ("lookup_table_id_column", ctypes.c_uint32),
                 ("public_input_columns", ctypes.POINTER(ctypes.c_uint32)), ("public_input_rows", ctypes.POINTER(ctypes.c_uint32)),
-                ("n_public_inputs", ctypes.c_uint32)]
+                ("n_public_inputs", ctypes.c_uint32), ("tree_hasher", ctypes.c_uint32), ("transcript", ctypes.c_uint32)]

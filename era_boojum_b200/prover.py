@@ -44,9 +44,14 @@ def _combine_ext(a, b):
 class ProofConfig:
     """ProofConfig (prover.rs:55-73)."""
 
-    def __init__(self, fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, pow_bits=0):
+    def __init__(self, fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, pow_bits=0, hasher="poseidon2",
+                 transcript="poseidon2"):
+        """hasher / transcript: the H and TR type parameters of prove_cpu_basic - "poseidon2" for both is the recursive-mode
+        bench (GoldilocksPoseidon2Sponge + GoldilocksPoisedon2Transcript), "blake2s" for both is sha256_bench_non_recursive
+        (Blake2s256 + Blake2sTranscript, src/gadgets/sha256/mod.rs:527)."""
         self.fri_lde_factor, self.merkle_tree_cap_size = fri_lde_factor, merkle_tree_cap_size
         self.security_level, self.pow_bits = security_level, pow_bits
+        self.hasher, self.transcript = hasher, transcript
 
     def to_dict(self):
         return {"fri_lde_factor": self.fri_lde_factor, "merkle_tree_cap_size": self.merkle_tree_cap_size,
@@ -82,7 +87,7 @@ class Setup:
         cols = torch.cat(parts, dim=0).contiguous()
         self.lde = ctx.transform_raw_storages_to_lde(cols, L)      # [V + C, L / world, n]
         self.tree = ctx.merkle_tree_construct([self.lde[c].reshape(-1) for c in range(cols.shape[0])],
-                                              config.merkle_tree_cap_size // world)
+                                              config.merkle_tree_cap_size // world, hasher=config.hasher)
         self.cap = self.tree.get_cap()
         if comm:
             self.cap = assemble_cap(comm, self.cap, L, config.merkle_tree_cap_size)
@@ -106,13 +111,14 @@ class Setup:
                 "gates": [(g["name"], g["num_repetitions"], list(g["selector_path"]), g.get("variables_initial_offset", 0),
                            g["constants_placement_offset"]) for g in self.gates],
                 "public_inputs_locations": [list(p) for p in self.public_inputs],
+                "hasher": self.config.hasher, "transcript": self.config.transcript,
                 "setup_merkle_tree_cap": self.cap.tolist()}
 
 
-def _commit(ctx, comm, cols, L, cap):
+def _commit(ctx, comm, cols, L, cap, hasher="poseidon2"):
     """Merkle oracle over LDE columns: local tree (this rank's cosets) + the global cap."""
     world = comm.world if comm else 1
-    tree = ctx.merkle_tree_construct(cols, cap // world)
+    tree = ctx.merkle_tree_construct(cols, cap // world, hasher=hasher)
     local_cap = tree.get_cap()
     return tree, (assemble_cap(comm, local_cap, L, cap) if comm else local_cap)
 
@@ -122,13 +128,13 @@ class _ShardedFri:
     2^k neighbours never leaves a coset), every oracle cap is gathered so that all ranks draw the same challenges, the last
     codeword (a few hundred elements) is gathered and interpolated by every rank."""
 
-    def __init__(self, ctx, comm, tr, c0, c1, schedule, L, cap):
+    def __init__(self, ctx, comm, tr, c0, c1, schedule, L, cap, hasher="poseidon2"):
         torch = ctx._torch
         self.levels, self.caps, self.schedule = [], [], list(schedule)
         kappa = pow(7, P - 2, P)                                              # coset_inverse (fri/mod.rs:194)
         cur0, cur1 = c0, c1
         for k in schedule:
-            tree = ctx.merkle_tree_construct([cur0, cur1], cap // comm.world, elems_per_leaf=1 << k)
+            tree = ctx.merkle_tree_construct([cur0, cur1], cap // comm.world, elems_per_leaf=1 << k, hasher=hasher)
             gcap = assemble_cap(comm, tree.get_cap(), L, cap)
             tr.witness_merkle_tree_cap(gcap)
             alpha = tr.get_multiple_challenges_fixed(2)
@@ -178,7 +184,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
             tm[name] = tm.get(name, 0.0) + time.perf_counter() - t0
 
     flat = lambda t: t.reshape(-1)
-    tr = Transcript()
+    tr = Transcript(cfg.transcript)
     tr.witness_merkle_tree_cap(setup.cap)                                   # prover.rs:211
     public_values = [int(to_numpy(variables[c, r].reshape(1))[0]) % P for c, r in setup.public_inputs]
     for v in public_values:                                                 # prover.rs:264-266
@@ -192,7 +198,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     if lk:
         m_lde = ctx.transform_raw_storages_to_lde(multiplicities.reshape(1, -1).contiguous(), L)
         m_col = flat(m_lde[0])
-    w_tree, w_cap = _commit(ctx, comm, w_cols + ([m_col] if lk else []), L, cap)   # variables | witness (none) | multiplicities
+    w_tree, w_cap = _commit(ctx, comm, w_cols + ([m_col] if lk else []), L, cap, cfg.hasher)   # variables | witness (none) | multiplicities
     tr.witness_merkle_tree_cap(w_cap)
     mark("1_witness_lde_commit", t0)
     # ---- round 2: copy-permutation products (prover.rs:360-554); the trace-domain part is replicated on every rank ----
@@ -214,7 +220,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     st2 = torch.stack([z0, z1] + [t for pr in partials for t in pr] + lk_polys).contiguous()
     s2_lde = ctx.transform_raw_storages_to_lde(st2, L)
     s2_cols = [flat(s2_lde[c]) for c in range(st2.shape[0])]
-    s2_tree, s2_cap = _commit(ctx, comm, s2_cols, L, cap)
+    s2_tree, s2_cap = _commit(ctx, comm, s2_cols, L, cap, cfg.hasher)
     tr.witness_merkle_tree_cap(s2_cap)
     n_partial = len(partials)
     mark("2_stage2_products_lde_commit", t0)
@@ -264,7 +270,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     chunks = torch.stack([qq[k][j * n:(j + 1) * n] for j in range(Q) for k in (0, 1)]).contiguous()   # c0,c1 of chunk 0, ...
     qt_lde = ctx.transform_raw_storages_to_lde(chunks, L, from_monomials=True)
     qt_cols = [flat(qt_lde[c]) for c in range(2 * Q)]
-    qt_tree, qt_cap = _commit(ctx, comm, qt_cols, L, cap)
+    qt_tree, qt_cap = _commit(ctx, comm, qt_cols, L, cap, cfg.hasher)
     tr.witness_merkle_tree_cap(qt_cap)
     mark("3_quotient", t0)
     # ---- round 4: openings (prover.rs:1501-1802) ----
@@ -339,11 +345,11 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     assert np_.value == 0, "PoW is not implemented (benches use NoPow)"
     schedule = list(sched[: sl.value])
     if comm:
-        fri = _ShardedFri(ctx, comm, tr, deep0, deep1, schedule, L, cap)
+        fri = _ShardedFri(ctx, comm, tr, deep0, deep1, schedule, L, cap, cfg.hasher)
         mono0, mono1 = fri.mono
         fri_caps = fri.caps
     else:
-        fri = ctx.do_fri(tr, deep0, deep1, schedule, L, cap)
+        fri = ctx.do_fri(tr, deep0, deep1, schedule, L, cap, hasher=cfg.hasher)
         mono0, mono1 = fri.monomial_forms()
         fri_caps = [fri.get_cap(i) for i in range(fri.num_oracles())]
     mark("5_deep_fri", t0)

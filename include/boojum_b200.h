@@ -265,7 +265,11 @@ BJ_API int32_t bj_intt_natural_to_natural_host(bj_ctx* ctx, uint64_t* h_data, ui
  * (src/cs/implementations/transcript.rs:62-129), BoolsBuffer::get_bits (:369-417), compute_fri_schedule
  * (src/cs/implementations/prover.rs:2281-2372). */
 typedef struct bj_transcript bj_transcript;
-BJ_API bj_transcript* bj_transcript_new(void);
+BJ_API bj_transcript* bj_transcript_new(void);          /* GoldilocksPoisedon2Transcript */
+/* Blake2sTranscript (transcript.rs:155-260; the transcript of sha256_bench_non_recursive): field elements enter as the
+ * 8 LE bytes of their reduced value, caps as raw 32-byte digests; a challenge is 8 output bytes reduced mod p; query bits
+ * take all 64 bits of 8 challenge bytes (BoolsBuffer, non-algebraic branch). */
+BJ_API bj_transcript* bj_transcript_new_blake2s(void);
 BJ_API void bj_transcript_free(bj_transcript* t);
 BJ_API void bj_transcript_witness_field_elements(bj_transcript* t, const uint64_t* els, size_t n);
 BJ_API void bj_transcript_witness_merkle_tree_cap(bj_transcript* t, const uint64_t* cap_digests, size_t n_digests);
@@ -288,6 +292,12 @@ typedef struct bj_fri_oracles bj_fri_oracles;
 BJ_API int32_t bj_do_fri(bj_ctx* ctx, bj_transcript* transcript, const uint64_t* d_c0, const uint64_t* d_c1,
                   uint32_t log_full_size, const uint32_t* schedule, uint32_t n_schedule, uint32_t log_lde,
                   uint32_t cap_size, bj_fri_oracles** out);
+#define BJ_HASHER_POSEIDON2 0u
+#define BJ_HASHER_BLAKE2S 1u
+/* same with the tree hasher chosen (BJ_HASHER_*: GoldilocksPoseidon2Sponge or Blake2s256, src/cs/oracle/mod.rs:114-245) */
+BJ_API int32_t bj_do_fri_with_hasher(bj_ctx* ctx, bj_transcript* transcript, const uint64_t* d_c0, const uint64_t* d_c1,
+                              uint32_t log_full_size, const uint32_t* schedule, uint32_t n_schedule, uint32_t log_lde,
+                              uint32_t cap_size, uint32_t hasher, bj_fri_oracles** out);
 BJ_API void bj_fri_oracles_free(bj_fri_oracles* o);
 BJ_API uint32_t bj_fri_oracles_num_oracles(const bj_fri_oracles* o);
 BJ_API uint32_t bj_fri_oracles_num_monomials(const bj_fri_oracles* o);
@@ -345,6 +355,8 @@ typedef struct bj_circuit {
   const uint32_t* public_input_columns;
   const uint32_t* public_input_rows;
   uint32_t n_public_inputs;
+  uint32_t tree_hasher; /* BJ_HASHER_POSEIDON2 (recursive-mode bench) or BJ_HASHER_BLAKE2S (sha256_bench_non_recursive) */
+  uint32_t transcript;  /* 0: Poseidon2 sponge transcript, 1: Blake2sTranscript */
 } bj_circuit;
 typedef struct bj_setup bj_setup;
 typedef struct bj_proof bj_proof;

@@ -104,6 +104,86 @@ class Poseidon2Transcript:
         return (c0, c1)
 
 
+class Blake2sTranscript:
+    """Blake2sTranscript (src/cs/implementations/transcript.rs:155-260): the byte buffer is hashed into a running
+    Blake2s-256 whose state is re-seeded with every 32-byte output; challenges are 8 output bytes, little endian, reduced
+    mod p.  Caps are raw 32-byte digests (given here as 4 little-endian u64 each)."""
+    IS_ALGEBRAIC = False
+
+    def __init__(self):
+        import hashlib
+        self._new = lambda: hashlib.blake2s(digest_size=32)
+        self.inner = self._new()
+        self.buffer = b""
+        self.available = b""
+
+    def witness_field_elements(self, els):
+        for e in els:
+            self.buffer += (int(e) % P).to_bytes(8, "little")
+
+    def witness_merkle_tree_cap(self, cap):
+        for digest in cap:
+            for w in digest:
+                self.buffer += int(w).to_bytes(8, "little")
+
+    def _reseed(self):
+        out = self.inner.digest()
+        self.inner = self._new()
+        self.inner.update(out)
+        return out
+
+    def _absorb(self):
+        if self.buffer:
+            self.inner.update(self.buffer)
+            self.buffer = b""
+            self.available = self._reseed()
+
+    def get_challenge_bytes(self, num_bytes):
+        self._absorb()
+        while len(self.available) < num_bytes:
+            self.available += self._reseed()
+        out, self.available = self.available[:num_bytes], self.available[num_bytes:]
+        return out
+
+    def get_challenge(self):
+        return int.from_bytes(self.get_challenge_bytes(8), "little") % P
+
+    def get_ext_challenge(self):
+        c0 = self.get_challenge()
+        c1 = self.get_challenge()
+        return (c0, c1)
+
+
+def blake2s_leaf_hash(elements):
+    """impl TreeHasher for Blake2s256 (src/cs/oracle/mod.rs:179-245): digest over the LE bytes of the reduced elements,
+    returned as 4 little-endian u64 (byte-identical to [u8; 32])."""
+    import hashlib
+    h = hashlib.blake2s(b"".join((int(e) % P).to_bytes(8, "little") for e in elements), digest_size=32).digest()
+    return np.frombuffer(h, dtype="<u8").copy()
+
+
+def blake2s_node_hash(left, right):
+    import hashlib
+    h = hashlib.blake2s(np.asarray(left, dtype="<u8").tobytes() + np.asarray(right, dtype="<u8").tobytes(), digest_size=32).digest()
+    return np.frombuffer(h, dtype="<u8").copy()
+
+
+def merkle_verify_generic(leaf_hash, path, cap, idx, node_hash):
+    cur = np.asarray(leaf_hash, dtype=np.uint64)
+    for sib in np.asarray(path, dtype=np.uint64).reshape(-1, 4):
+        cur = node_hash(cur, sib) if idx & 1 == 0 else node_hash(sib, cur)
+        idx >>= 1
+    return bool(np.array_equal(cur, np.asarray(cap, dtype=np.uint64).reshape(-1, 4)[idx]))
+
+
+def hasher_functions(name):
+    """(leaf hash, path verifier) of a tree hasher."""
+    if name == "blake2s":
+        return blake2s_leaf_hash, (lambda leaf, path, cap, idx: merkle_verify_generic(leaf, path, cap, idx, blake2s_node_hash))
+    return (lambda els: O.poseidon2_hash_leaf(np.array(els, dtype=np.uint64))), \
+           (lambda leaf, path, cap, idx: O.merkle_verify(leaf, np.asarray(path, dtype=np.uint64).reshape(-1, 4), np.array(cap, dtype=np.uint64), idx))
+
+
 class BoolsBuffer:
     def __init__(self, max_needed):
         self.available = []
@@ -111,6 +191,11 @@ class BoolsBuffer:
 
     def get_bits(self, transcript, num_bits):
         while len(self.available) < num_bits:
+            if not getattr(transcript, "IS_ALGEBRAIC", True):      # transcript.rs:401-413: 8 uniform bytes, all 64 bits
+                el = int.from_bytes(transcript.get_challenge_bytes(8), "little")
+                for b in range(64):
+                    self.available.append((el >> b) & 1)
+                continue
             el = transcript.get_challenge()
             for b in range(64 - self.max_needed):
                 self.available.append((el >> b) & 1)
@@ -402,7 +487,8 @@ def do_fri_oracle(c0, c1, transcript, schedule, log_lde, cap_size):
     return dict(caps=caps, challenges=chals, levels=levels, trees=trees, monomials=(m0[:final_degree], m1[:final_degree]))
 
 
-def verify_fri_query(idx, log_n, log_lde, schedule, cap_size, caps, fri_challenges, monomials, queries, start_value=None):
+def verify_fri_query(idx, log_n, log_lde, schedule, cap_size, caps, fri_challenges, monomials, queries, start_value=None,
+                     hasher="poseidon2"):
     """Verifier-side FRI chain for one base-tree index (src/cs/implementations/verifier.rs:2386-2510).
     queries: per oracle (leaf_elements, path).  Returns the value expected in the first leaf if start_value is None."""
     max_bits = log_n + log_lde
@@ -432,10 +518,11 @@ def verify_fri_query(idx, log_n, log_lde, schedule, cap_size, caps, fri_challeng
         le = [int(v) for v in le]
         if cur is not None:
             assert (le[sub_in_leaf], le[deg + sub_in_leaf]) == cur, ("fold chain broken at level", lvl)
-        leaf = O.poseidon2_hash_leaf(np.array(le, dtype=np.uint64))
+        leaf_fn, path_ok = hasher_functions(hasher)
+        leaf = leaf_fn(le)
         path = np.array(path, dtype=np.uint64).reshape(-1, 4)
         assert path.shape[0] == depth
-        assert O.merkle_verify(leaf, path, np.array(caps[lvl], dtype=np.uint64), tree_idx), ("path", lvl)
+        assert path_ok(leaf, path, caps[lvl], tree_idx), ("path", lvl)
         els = [(le[i], le[deg + i]) for i in range(deg)]
         base_pow = power_chunks[lvl]
         a = fri_challenges[lvl]

@@ -69,7 +69,9 @@ def verify(vk, proof):
     n_mult = 1 if lk else 0
     n_tables = wdt + 1 if lk else 0
 
-    tr = R.Poseidon2Transcript()
+    hasher = vk.get("hasher", "poseidon2")                # tree hasher and transcript of the proof system instance
+    tr = R.Blake2sTranscript() if vk.get("transcript", "poseidon2") == "blake2s" else R.Poseidon2Transcript()
+    leaf_fn, path_ok = R.hasher_functions(hasher)
     tr.witness_merkle_tree_cap(vk["setup_merkle_tree_cap"])
     pi_locations = vk.get("public_inputs_locations", [])
     assert len(proof["public_inputs"]) == len(pi_locations)
@@ -214,10 +216,10 @@ def verify(vk, proof):
         idx = sum(b << i for i, b in enumerate(bits))
         for name, cap in (("witness_query", proof["witness_oracle_cap"]), ("stage_2_query", proof["stage_2_oracle_cap"]),
                           ("quotient_query", proof["quotient_oracle_cap"]), ("setup_query", vk["setup_merkle_tree_cap"])):
-            leaf = O.poseidon2_hash_leaf(np.array(q[name]["leaf_elements"], dtype=np.uint64))
+            leaf = leaf_fn(q[name]["leaf_elements"])
             path = np.array(q[name]["proof"], dtype=np.uint64).reshape(-1, 4)
             assert path.shape[0] == depth
-            assert O.merkle_verify(leaf, path, np.array(cap, dtype=np.uint64), idx), (name, idx)
+            assert path_ok(leaf, path, cap, idx), (name, idx)
         wq, sq = q["witness_query"]["leaf_elements"], q["stage_2_query"]["leaf_elements"]
         qq, uq = q["quotient_query"]["leaf_elements"], q["setup_query"]["leaf_elements"]
         assert len(wq) == V + n_mult and len(sq) == 2 * (1 + n_partial + n_lk_terms) and len(qq) == 2 * Q
@@ -243,5 +245,5 @@ def verify(vk, proof):
                                ch[off_ch:off_ch + len(members)], x_q, (at, 0))
             off_ch += len(members)
         fqs = [(fq["leaf_elements"], fq["proof"]) for fq in q["fri_queries"]]
-        R.verify_fri_query(idx, log_n, log_L, schedule, cap_size, fri_caps, fri_ch, (mono[0], mono[1]), fqs, start_value=acc)
+        R.verify_fri_query(idx, log_n, log_L, schedule, cap_size, fri_caps, fri_ch, (mono[0], mono[1]), fqs, start_value=acc, hasher=hasher)
     return True

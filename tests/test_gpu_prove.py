@@ -254,3 +254,47 @@ def test_gates_over_specialized_columns(env, lookup):
     bad[variables.shape[0] - 1, 9] += 1            # break the last specialised repetition on one row
     with pytest.raises(ValueError):
         prover.prove(ctx, setup, bad, multiplicities=m)
+
+
+@pytest.mark.parametrize("lookup,world", [(False, 1), (True, 1), (False, 2)])
+def test_blake2s_hasher_and_transcript_non_recursive_config(env, lookup, world):
+    """H = Blake2s256, TR = Blake2sTranscript - the type parameters of sha256_bench_non_recursive
+    (src/gadgets/sha256/mod.rs:527): Python driver, native C++ driver and the coset-sharded prover agree, the oracle verifier
+    (hashlib Blake2s) accepts, a Poseidon2-configured verifier does not."""
+    bj, ctx, prover, synthetic = env
+    gen = synthetic.generate(ctx, 9, 60, seed=41, lookup=lookup)
+    lk = gen[5] if lookup else None
+    variables, sigmas, constants, gates, Q = gen[:5]
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher="blake2s", transcript="blake2s")
+    m = lk["multiplicities"] if lk else None
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg, lookup=lk, public_inputs=[(2, 5)])
+    proof = prover.prove(ctx, setup, variables, multiplicities=m)
+    vk = setup.vk()
+    assert vk["hasher"] == "blake2s" and OV.verify(vk, proof)
+    wrong = dict(vk, transcript="poseidon2")
+    with pytest.raises(AssertionError):
+        OV.verify(wrong, proof)
+    nat = ctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk, public_inputs=[(2, 5)])
+    assert json.dumps(nat.prove(variables, m), sort_keys=True) == json.dumps(proof, sort_keys=True)
+    if world > 1:
+        import threading
+        from era_boojum_b200 import parallel
+        shared, outs, errs = parallel.ThreadComm(world), [None] * world, []
+
+        def run(rank):
+            try:
+                c2 = bj.Context(0)
+                c2.set_coset_shard(rank, world, 8)
+                s2 = prover.Setup(c2, sigmas, constants, gates, Q, cfg, comm=shared.rank_view(rank), public_inputs=[(2, 5)])
+                outs[rank] = prover.prove(c2, s2, variables)
+                c2.synchronize()
+                c2.close()
+            except BaseException as e:
+                errs.append(e)
+                shared._barrier.abort()
+
+        ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs, errs
+        assert all(json.dumps(o, sort_keys=True) == json.dumps(proof, sort_keys=True) for o in outs)

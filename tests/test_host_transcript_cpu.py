@@ -100,3 +100,45 @@ def test_fri_schedule_matches_oracle():
         assert st == 0
         w_np, w_nq, w_s, w_fd = replay.compute_fri_schedule(*args)
         assert (np_.value, nq.value, list(sched[: sl.value]), fd.value) == (w_np, w_nq, w_s, w_fd)
+
+
+def test_blake2s_transcript_matches_oracle_random_script():
+    """Blake2sTranscript (transcript.rs:155-260) in the library's host C++ (own Blake2s) against the hashlib restatement:
+    random interleavings of absorbing elements / caps (message lengths crossing the 64-byte block in every way), drawing
+    challenges and drawing query-index bits (non-algebraic BoolsBuffer branch)."""
+    lib = _lib()
+    r = np.random.default_rng(3)
+    for trial in range(20):
+        h = ctypes.c_void_p(lib.bj_transcript_new_blake2s())
+        o = replay.Blake2sTranscript()
+        bools = replay.BoolsBuffer(25)
+        for step in range(60):
+            op = r.integers(0, 4)
+            if op == 0:
+                els = r.integers(0, 2**64 - 1, size=int(r.integers(0, 20)), dtype=np.uint64)   # incl. non-canonical values
+                lib.bj_transcript_witness_field_elements(h, els.ctypes.data_as(ctypes.c_void_p), len(els))
+                o.witness_field_elements([int(e) for e in els])
+            elif op == 1:
+                cap = r.integers(0, 2**64 - 1, size=(int(r.integers(1, 5)), 4), dtype=np.uint64)  # raw digests: NOT reduced
+                lib.bj_transcript_witness_merkle_tree_cap(h, cap.ctypes.data_as(ctypes.c_void_p), cap.shape[0])
+                o.witness_merkle_tree_cap(cap.tolist())
+            elif op == 2:
+                for _ in range(int(r.integers(1, 7))):
+                    assert int(lib.bj_transcript_get_challenge(h)) == o.get_challenge()
+            else:
+                bits = bools.get_bits(o, 25)
+                assert int(lib.bj_transcript_get_index_bits(h, 25, 25)) == sum(b << i for i, b in enumerate(bits))
+        lib.bj_transcript_free(h)
+
+
+def test_blake2s_transcript_known_answer():
+    """first challenge after absorbing nothing but one element = first 8 bytes of Blake2s-256 of its 8 LE bytes."""
+    import hashlib
+    lib = _lib()
+    h = ctypes.c_void_p(lib.bj_transcript_new_blake2s())
+    el = np.array([0x0123456789ABCDEF], dtype=np.uint64)
+    lib.bj_transcript_witness_field_elements(h, el.ctypes.data_as(ctypes.c_void_p), 1)
+    d = hashlib.blake2s(int(el[0]).to_bytes(8, "little"), digest_size=32).digest()
+    assert int(lib.bj_transcript_get_challenge(h)) == int.from_bytes(d[:8], "little") % replay.P
+    assert int(lib.bj_transcript_get_challenge(h)) == int.from_bytes(d[8:16], "little") % replay.P
+    lib.bj_transcript_free(h)
