@@ -333,33 +333,46 @@ def main():
             pctx.set_coset_shard(rank, world, 8)
             comm = parallel.TorchDistComm(dist)
         variables, sigmas, constants, gates, Q, lk = synthetic.generate(pctx, args.prove_log_n, 60, seed=42, lookup=True)
-        cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100)
-        if world == 1:
-            # one GPU: the host driver is the library's own C++ (bj_setup_create / bj_prove), proof returned as serde JSON
-            setup = pctx.native_setup(sigmas.contiguous(), constants.contiguous(), gates, Q, cfg, lookup=lk)
-            run_prove = lambda tm: setup.prove(variables, lk["multiplicities"], timings=tm)
-        else:
-            setup = prover.Setup(pctx, sigmas, constants, gates, Q, cfg, lookup=lk, comm=comm)
-            run_prove = lambda tm: prover.prove(pctx, setup, variables, timings=tm, multiplicities=lk["multiplicities"])
-        run_prove(None)  # warm-up (tables, allocator)
-        barrier()
-        stages = {}
-        t0 = time.perf_counter()
-        proof = run_prove(stages)
-        torch.cuda.synchronize()
-        secs = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([secs] + [stages[k] for k in sorted(stages)], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            secs = float(t[0].item())
-            stages = {k: float(v) for k, v in zip(sorted(stages), t[1:].tolist())}
-        out["prove"] = {"circuit": "synthetic sha256-bench-shaped: 60 gp columns + 8 lookup sub-arguments of width 4 (92 copy-permutation columns, 1 multiplicity column), ConstantsAllocator/Fma/Reduction<4>, Q=4, L=8, cap 16, Poseidon2 tree + transcript",
-                        "rows_log2": args.prove_log_n, "seconds": round(secs, 4), "queries": len(proof["queries_per_fri_repetition"]),
-                        "n_gpus": world, "scaling": "strong (one proof, LDE cosets sharded over the GPUs)" if world > 1 else "single GPU",
-                        "driver": "python + torch.distributed over the C-ABI (era_boojum_b200/prover.py)" if world > 1 else "bj_prove (host C++ in libboojum_b200.so), JSON proof parsed inside the timed region",
-                        "stages_s": {k: round(v, 4) for k, v in stages.items()},
-                        "note": "H2D of the witness not included (trace generated on the device); accepted by the oracle verifier in tests/test_gpu_prove.py; wall clock, max over ranks"}
-        del proof, setup, variables, sigmas, constants, lk
+
+        def prove_once(hasher):
+            """one timed proof of the synthetic SHA-shaped circuit with the given tree hasher + matching transcript"""
+            cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher=hasher, transcript=hasher)
+            if world == 1:
+                # one GPU: the host driver is the library's own C++ (bj_setup_create / bj_prove), proof returned as serde JSON
+                setup = pctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk)
+                run_prove = lambda tm: setup.prove(variables, lk["multiplicities"], timings=tm)
+            else:
+                setup = prover.Setup(pctx, sigmas, constants, gates, Q, cfg, lookup=lk, comm=comm)
+                run_prove = lambda tm: prover.prove(pctx, setup, variables, timings=tm, multiplicities=lk["multiplicities"])
+            run_prove(None)  # warm-up (tables, allocator)
+            barrier()
+            stages = {}
+            t0 = time.perf_counter()
+            proof = run_prove(stages)
+            torch.cuda.synchronize()
+            secs = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([secs] + [stages[k] for k in sorted(stages)], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                secs = float(t[0].item())
+                stages = {k: float(v) for k, v in zip(sorted(stages), t[1:].tolist())}
+            res = {"rows_log2": args.prove_log_n, "seconds": round(secs, 4), "queries": len(proof["queries_per_fri_repetition"]),
+                   "n_gpus": world, "tree_hasher_and_transcript": hasher,
+                   "stages_s": {k: round(v, 4) for k, v in stages.items()}}
+            if hasattr(setup, "close"):
+                setup.close()
+            del setup, proof
+            torch.cuda.empty_cache()
+            return res
+
+        common = {"circuit": "synthetic sha256-bench-shaped: 60 gp columns + 8 lookup sub-arguments of width 4 (92 copy-permutation columns, 1 multiplicity column), ConstantsAllocator/Fma/Reduction<4>, Q=4, L=8, cap 16",
+                  "scaling": "strong (one proof, LDE cosets sharded over the GPUs)" if world > 1 else "single GPU",
+                  "driver": "python + torch.distributed over the C-ABI (era_boojum_b200/prover.py)" if world > 1 else "bj_prove (host C++ in libboojum_b200.so), JSON proof parsed inside the timed region",
+                  "note": "H2D of the witness not included (trace generated on the device); accepted by the oracle verifier in tests/test_gpu_prove.py; wall clock, max over ranks"}
+        # BASELINE configs[4] (recursive mode: Poseidon2 tree + transcript) and configs[3] (non-recursive: Blake2s tree + transcript)
+        out["prove"] = dict(common, **prove_once("poseidon2"))
+        out["prove_non_recursive"] = dict(common, **prove_once("blake2s"))
+        del variables, sigmas, constants, lk
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_sample()
     if rank == 0:
