@@ -256,6 +256,15 @@ def main():
                 "peak_source": peak_kind + " hbm copy", "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "algo_bytes_per_launch": algo_bytes_step / max(1.0, launches_per_step),
                 "avg_launch_ms": ms / max(1.0, launches_per_step), "traffic": None}
+    try:
+        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (not measured in this run):
+        # bytes per element per launch of the capture x the elements one launch of this run processes
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr_ = json.load(f)
+        roofline["traffic"] = round(tr_["dram_bytes_per_element_per_launch"] * elems_per_step / max(1.0, launches_per_step))
+        roofline["traffic_source"] = "profiles/ncu_traffic.json"
+    except Exception:
+        pass
 
     # end to end: pinned host buffers -> H2D -> NTT -> D2H through the host-buffer C-ABI entry point
     e2e = None
