@@ -163,6 +163,22 @@ def main():
     from era_boojum_b200 import native
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    numa = "unchanged"
+    if world > 1:
+        # keep this rank's host threads (and, by first touch, its pinned staging buffers) on the CPU socket next to its GPU:
+        # the end-to-end path moves 10 GiB per step per GPU through host memory
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h_ = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h_, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+            cpus &= set(os.sched_getaffinity(0))
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = "bound to the %d CPUs local to GPU %d" % (len(cpus), local_rank)
+        except Exception as e:  # affinity is an optimisation only
+            numa = "unchanged (%s)" % type(e).__name__
     torch.cuda.set_device(local_rank)
     dev = "cuda:%d" % local_rank
     if world > 1:
@@ -296,7 +312,7 @@ def main():
             e_ms = float(t.item())
         e2e = {"value": round(world * elems_per_step / (e_ms * 1e-3) / 1e9, 4), "unit": "Gelem/s",
                "h2d_bytes_per_step": 8 * elems_per_step, "d2h_bytes_per_step": 8 * elems_per_step,
-               "ms_per_step": round(e_ms, 3), "steps": k}
+               "ms_per_step": round(e_ms, 3), "steps": k, "host_affinity": numa}
         del host
 
     out = {
