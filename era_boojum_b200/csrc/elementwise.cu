@@ -103,11 +103,16 @@ __global__ void __launch_bounds__(256) batch_inverse_ext_kernel(u64* __restrict_
 // Each thread owns DEEP_R rows strided by the grid; the Fp2 denominators of its rows share one inversion.
 constexpr int DEEP_R = 4;
 
+// one base-field column of the DEEP sum with its two coefficients: acc.c0 += k0 * f, acc.c1 += k1 * f.  An Fp2 polynomial
+// (f0, f1) with challenge (c0, c1) is two such columns: f0 with (c0, c1) and f1 with (7 c1, c0)   (u^2 = 7).
+struct DeepColumn {
+  const u64* f;
+  u64 k0, k1;
+};
+
 struct DeepParams {
-  const u64* const* src_c0;  // n_src device pointers
-  const u64* const* src_c1;  // n_src device pointers, NULL entry = base-field column
-  const u64* ch;             // n_src (c0, c1) challenge coefficients
-  u32 n_src;
+  const DeepColumn* cols;
+  u32 n_cols;
   u64 n_rows;                // n * (local cosets)
   int log_n;                 // coset length (locates the coset bits when the context holds a coset shard)
   CosetShard shard;
@@ -118,37 +123,68 @@ struct DeepParams {
   u64* acc_c1;
 };
 
+// Unreduced accumulator for sums of 64x64-bit products: 128 bits + an overflow word (exact for < 2^32 terms).  One
+// reduction per accumulator at the end instead of one per product: the DEEP sum has ~270 terms per row.
+struct Acc160 {
+  u64 lo, hi;
+  u32 ov;
+};
+__device__ __forceinline__ void acc_mad(Acc160& a, u64 x, u64 y) {
+  const u64 pl = x * y, ph = __umul64hi(x, y);
+  asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(a.lo), "+l"(a.hi), "+r"(a.ov) : "l"(pl), "l"(ph));
+}
+__device__ __forceinline__ u64 acc_reduce(const Acc160& a) {
+  // lo + 2^64 hi + 2^128 ov,  2^128 = -2^32 (mod p)
+  const u64 r = gl::reduce128(a.lo, a.hi);
+  return gl::canon(gl::sub(r, gl::mul((u64)a.ov, 1ull << 32)));
+}
+
+constexpr int DEEP_U = 4;  // columns whose loads are issued together (memory-level parallelism: the kernel streams ~70 GB)
+
 __global__ void __launch_bounds__(256) deep_group_kernel(const DeepParams p) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   const u64 t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  gl::e2 s[DEEP_R];
+  Acc160 a0[DEEP_R], a1[DEEP_R];
 #pragma unroll
-  for (int r = 0; r < DEEP_R; r++) s[r] = {0, 0};
-  for (u32 i = 0; i < p.n_src; i++) {
-    const u64* __restrict__ f0 = p.src_c0[i];
-    const u64* __restrict__ f1 = p.src_c1[i];
-    const gl::e2 ch = {__ldg(p.ch + 2 * i), __ldg(p.ch + 2 * i + 1)};
-    if (f1 == nullptr) {
+  for (int r = 0; r < DEEP_R; r++) a0[r] = a1[r] = {0, 0, 0};
+  u32 i = 0;
+  for (; i + DEEP_U <= p.n_cols; i += DEEP_U) {
+    DeepColumn c[DEEP_U];
+    u64 v[DEEP_U][DEEP_R];
 #pragma unroll
-      for (int r = 0; r < DEEP_R; r++) {
-        const u64 t = t0 + r * stride;
-        if (t < p.n_rows) {
-          const u64 v = f0[t];
-          s[r].c0 = gl::add(s[r].c0, gl::mul(ch.c0, v));
-          s[r].c1 = gl::add(s[r].c1, gl::mul(ch.c1, v));
-        }
-      }
-    } else {
+    for (int u = 0; u < DEEP_U; u++) {
+      c[u].f = p.cols[i + u].f;
+      c[u].k0 = __ldg(&p.cols[i + u].k0);
+      c[u].k1 = __ldg(&p.cols[i + u].k1);
+    }
+#pragma unroll
+    for (int u = 0; u < DEEP_U; u++)
 #pragma unroll
       for (int r = 0; r < DEEP_R; r++) {
         const u64 t = t0 + r * stride;
-        if (t < p.n_rows) {
-          const gl::e2 m = gl::e2_mul(ch, {f0[t], f1[t]});
-          s[r] = gl::e2_add(s[r], m);
-        }
+        v[u][r] = t < p.n_rows ? __ldcs(c[u].f + t) : 0;  // streamed once: evict first
       }
+#pragma unroll
+    for (int u = 0; u < DEEP_U; u++)
+#pragma unroll
+      for (int r = 0; r < DEEP_R; r++) {
+        acc_mad(a0[r], c[u].k0, v[u][r]);
+        acc_mad(a1[r], c[u].k1, v[u][r]);
+      }
+  }
+  for (; i < p.n_cols; i++) {
+    const DeepColumn c = p.cols[i];
+#pragma unroll
+    for (int r = 0; r < DEEP_R; r++) {
+      const u64 t = t0 + r * stride;
+      const u64 v = t < p.n_rows ? __ldcs(c.f + t) : 0;
+      acc_mad(a0[r], c.k0, v);
+      acc_mad(a1[r], c.k1, v);
     }
   }
+  gl::e2 s[DEEP_R];
+#pragma unroll
+  for (int r = 0; r < DEEP_R; r++) s[r] = {acc_reduce(a0[r]), acc_reduce(a1[r])};
   // denominators x - at for the thread's rows, inverted together
   gl::e2 den[DEEP_R], pre[DEEP_R];
   gl::e2 acc = {1, 0};
@@ -232,25 +268,23 @@ int32_t bj_deep_quotient_group(bj_ctx* ctx, const uint64_t* const* h_src_c0, con
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_deep_quotient_group: bad argument");
   BJ_TRY(ensure_twiddles(ctx, (int)log_rows));
   DeepParams p;
-  void *d0, *d1, *dch;
-  BJ_TRY(param_upload(ctx, h_src_c0, sizeof(u64*) * n_src, &d0));
-  BJ_TRY(param_upload(ctx, h_src_c1, sizeof(u64*) * n_src, &d1));
-  // canonical challenges, and K = sum ch_i * v_i on the host
-  std::vector<u64> ch(2 * (size_t)n_src);
+  // canonical challenges, K = sum ch_i * v_i on the host, and the flattened column list
+  std::vector<DeepColumn> cols;
+  cols.reserve(2 * (size_t)n_src);
   gl::e2 k = {0, 0};
   for (uint32_t i = 0; i < n_src; i++) {
     const gl::e2 c = {gl::canon(h_challenges[2 * i]), gl::canon(h_challenges[2 * i + 1])};
     const gl::e2 v = {gl::canon(h_values_at[2 * i]), gl::canon(h_values_at[2 * i + 1])};
-    ch[2 * i] = c.c0;
-    ch[2 * i + 1] = c.c1;
+    if (!h_src_c0[i]) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_deep_quotient_group: NULL source column");
+    cols.push_back({(const u64*)h_src_c0[i], c.c0, c.c1});
+    if (h_src_c1[i]) cols.push_back({(const u64*)h_src_c1[i], gl::mul7(c.c1), c.c0});
     const gl::e2 m = gl::e2_mul(c, v);
     k = {gl::canon(gl::add(k.c0, m.c0)), gl::canon(gl::add(k.c1, m.c1))};
   }
-  BJ_TRY(param_upload(ctx, ch.data(), sizeof(u64) * ch.size(), &dch));
-  p.src_c0 = (const u64* const*)d0;
-  p.src_c1 = (const u64* const*)d1;
-  p.ch = (const u64*)dch;
-  p.n_src = n_src;
+  void* dcols;
+  BJ_TRY(param_upload(ctx, cols.data(), sizeof(DeepColumn) * cols.size(), &dcols));
+  p.cols = (const DeepColumn*)dcols;
+  p.n_cols = (u32)cols.size();
   p.n_rows = 1ull << log_rows;
   p.log_n = (int)log_rows;
   p.shard = ctx->shard;

@@ -781,3 +781,43 @@ def test_materialize_columns_rejects_out_of_range_hint(bj, ctx):
     hint = bj.to_device(np.array([[0, 1, 5, 2]], dtype=np.uint64))
     with pytest.raises(bj.BoojumError):
         c.materialize_variables_polynomials_from_dense_hint(bj.to_device(np.arange(4, dtype=np.uint64)), hint, 2)
+
+
+# ---- error behaviour of the C-ABI: every misuse is a status + message, never an abort (the reference panics instead) ----
+def test_c_abi_rejects_misuse_with_status_codes(bj, ctx):
+    import ctypes
+    import torch
+    from era_boojum_b200 import native
+    lib, h = native.lib, ctx._h
+    dev = "cuda:0"
+    t = torch.zeros(64, dtype=torch.int64, device=dev)
+    p = ctypes.c_void_p(t.data_ptr())
+    INV = native.BJ_ERR_INVALID_ARG
+    # NULL pointers / impossible sizes
+    assert lib.bj_ntt_natural_to_bitreversed(h, None, 4, 1, 16, 1) == INV
+    assert lib.bj_ntt_natural_to_bitreversed(h, p, 33, 1, 1 << 33, 1) == INV           # beyond the 2-adicity of the field
+    assert lib.bj_intt_natural_to_natural(h, p, 4, 2, 8, 1) == INV                      # column stride smaller than the column
+    assert lib.bj_lde(h, p, 4, p, 4, 1, 1, 0) == INV                                    # in_col_stride < n
+    srcs = (ctypes.c_void_p * 1)(t.data_ptr())
+    assert lib.bj_merkle_build_poseidon2(h, srcs, 1, 48, 1, 4, p, p) == INV            # leaves not a power of two
+    assert lib.bj_merkle_build_poseidon2(h, srcs, 1, 16, 1, 32, p, p) == INV           # cap larger than the tree
+    assert lib.bj_merkle_build_blake2s(h, srcs, 1, 16, 3, 4, p, p) == INV              # elems per leaf not a power of two
+    al = (ctypes.c_uint64 * 2)(1, 0)
+    ci = ctypes.c_uint64(1)
+    assert lib.bj_fri_fold(h, p, p, 4, 4, al, ctypes.byref(ci), p, p) == INV           # fold by 16
+    assert lib.bj_fri_fold(h, p, p, 2, 3, al, ctypes.byref(ci), p, p) == INV           # fold deeper than the vector
+    assert lib.bj_ctx_set_coset_shard(h, 3, 2, 3) == INV                                # rank >= world
+    assert lib.bj_ctx_set_coset_shard(h, 0, 16, 3) == INV                               # more shards than cosets
+    assert lib.bj_ctx_set_coset_shard(h, 0, 3, 3) == INV                                # world not a power of two
+    assert b"coset" in lib.bj_last_error(h) or b"world" in lib.bj_last_error(h)
+    sched = (ctypes.c_uint32 * 2)(3, 4)
+    out = ctypes.c_void_p()
+    tr = ctypes.c_void_p(lib.bj_transcript_new())
+    assert lib.bj_do_fri(h, tr, p, p, 6, sched, 2, 1, 4, ctypes.byref(out)) == INV      # fold of 4 in the schedule
+    sched = (ctypes.c_uint32 * 2)(3, 3)
+    assert lib.bj_do_fri(h, tr, p, p, 6, sched, 2, 1, 4, ctypes.byref(out)) == INV      # final degree would be zero
+    assert lib.bj_do_fri_with_hasher(h, tr, p, p, 6, sched, 1, 1, 4, 7, ctypes.byref(out)) == INV   # unknown hasher
+    lib.bj_transcript_free(tr)
+    # the context stays usable afterwards
+    x = O.random_field(rng(1), (1, 16))
+    assert np.array_equal(bj.to_numpy(ctx.fft_natural_to_bitreversed(bj.to_device(x), 1)), O.ntt_n2b(x, 1))
