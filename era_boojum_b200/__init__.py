@@ -423,6 +423,14 @@ class Context:
             d.variables_initial_offset, d.witnesses_initial_offset = g.get("variables_initial_offset", 0), g.get("witnesses_initial_offset", 0)
         return keep, descs
 
+    # ---- proof of work ----
+    def pow_blake2s(self, seed_bytes, pow_bits):
+        """impl PoWRunner for Blake2s256 (cs/implementations/pow.rs:52-147)."""
+        seed = (ctypes.c_uint8 * max(1, len(seed_bytes)))(*seed_bytes)
+        out = ctypes.c_uint64()
+        self._check(lib.bj_pow_blake2s(self._h, seed, len(seed_bytes), pow_bits, ctypes.byref(out)))
+        return int(out.value)
+
     # ---- setup / witness materialisation ----
     def materialize_variables_polynomials_from_dense_hint(self, all_values, hint, log_n):
         """witness.rs:325-385.  all_values: [n_values] CUDA tensor; hint: [n_cols, hint_rows] CUDA tensor of reference

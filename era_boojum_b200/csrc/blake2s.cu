@@ -3,6 +3,7 @@
 // unkeyed, 32-byte digest; crate blake2 = "0.10", Cargo.toml:33) over the little-endian bytes of the REDUCED u64 of every
 // element in preimage order; a node is Blake2s-256(left || right).  Digests are 32 bytes, stored here as 4 little-endian
 // u64 so that trees share the [n][4] u64 layout of the Poseidon2 trees (byte-identical to [u8; 32]).
+#include <cstring>
 #include "ctx.hpp"
 
 namespace bj {
@@ -140,5 +141,74 @@ extern "C" int32_t bj_merkle_build_blake2s(bj_ctx* ctx, const uint64_t* const* h
     written += next;
     cnt = next;
   }
+  return BJ_OK;
+}
+
+// ---- proof of work: impl PoWRunner for Blake2s256 (src/cs/implementations/pow.rs:52-147): find a u64 `challenge` such that
+// the first 8 bytes (LE) of Blake2s-256(seed || challenge.to_le_bytes()) have >= pow_bits trailing zero bits.  One thread per
+// candidate, 2^24 candidates per launch, the smallest hit of the first successful batch is returned (the reference's serial
+// search for <= 16 bits returns the smallest overall; its parallel search returns whichever worker wins).
+namespace bj {
+
+__global__ void __launch_bounds__(256) blake2s_pow_kernel(const u32* __restrict__ seed_words, u32 seed_len, u64 base, u32 pow_bits,
+                                                           unsigned long long* __restrict__ best) {
+  const u64 nonce = base + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  // message = seed (seed_len <= 56 bytes, zero padded in seed_words) || nonce: always one 64-byte block
+  u32 m[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) m[i] = seed_words[i];
+  const u32 off = seed_len;  // byte offset of the nonce
+  const u64 lo_shift = (off & 3) * 8;
+  // place the 8 nonce bytes at byte offset `off` (unaligned in general)
+  u32 w = off >> 2;
+  u64 carry = nonce;
+  if (lo_shift == 0) {
+    m[w] = (u32)carry;
+    m[w + 1] = (u32)(carry >> 32);
+  } else {
+    m[w] |= (u32)(carry << lo_shift);
+    m[w + 1] = (u32)(carry >> (32 - lo_shift));
+    m[w + 2] |= (u32)(carry >> (64 - lo_shift));
+  }
+  u32 h[8];
+  blake2s_init(h);
+  blake2s_compress(h, m, seed_len + 8, 0u, true);
+  const u64 first = (u64)h[0] | ((u64)h[1] << 32);
+  const bool ok = pow_bits == 0 || (first << (64 - pow_bits)) == 0;  // trailing_zeros >= pow_bits (pow_bits <= 32)
+  if (ok) atomicMin(best, (unsigned long long)nonce);
+}
+
+}  // namespace bj
+
+extern "C" int32_t bj_pow_blake2s(bj_ctx* ctx, const uint8_t* h_seed, uint32_t seed_len, uint32_t pow_bits, uint64_t* h_challenge) {
+  if (!ctx || (!h_seed && seed_len) || !h_challenge || pow_bits > 32 || seed_len > 52)
+    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_pow_blake2s: bad argument (pow_bits <= 32, seed <= 52 bytes)");
+  u32 words[16] = {0};
+  memcpy(words, h_seed, seed_len);
+  void* d_seed;
+  BJ_TRY(param_upload(ctx, words, sizeof(words), &d_seed));
+  unsigned long long* d_best = nullptr;
+  BJ_CUDA(ctx, cudaMalloc(&d_best, sizeof(unsigned long long)));
+  const unsigned long long none = ~0ull;
+  const u64 batch = 1ull << 24;
+  int32_t st = BJ_OK;
+  unsigned long long best = none;
+  for (u64 base = 0; best == none; base += batch) {
+    if (base >= (1ull << 40)) {  // 2^40 candidates without a hit for <= 32 bits does not happen; do not spin forever
+      st = BJ_ERR_UNSUPPORTED;
+      break;
+    }
+    if (cudaMemcpyAsync(d_best, &none, sizeof(none), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = BJ_ERR_CUDA;
+    blake2s_pow_kernel<<<(unsigned)(batch / 256), 256, 0, ctx->stream>>>((const u32*)d_seed, seed_len, base, pow_bits, d_best);
+    ctx->launches++;
+    if (cudaMemcpyAsync(&best, d_best, sizeof(best), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+      st = BJ_ERR_CUDA;
+    if (st != BJ_OK) break;
+  }
+  cudaFree(d_best);
+  if (st == BJ_ERR_CUDA) BJ_FAIL(ctx, BJ_ERR_CUDA, "bj_pow_blake2s: CUDA error");
+  if (st != BJ_OK) BJ_FAIL(ctx, st, "bj_pow_blake2s: no solution found");
+  *h_challenge = best;
   return BJ_OK;
 }

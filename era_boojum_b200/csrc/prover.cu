@@ -132,6 +132,7 @@ struct bj_proof {
   std::vector<bj::u64> mono_c0, mono_c1;
   std::vector<gl::e2> values_at_z, values_at_z_omega, values_at_0;
   std::vector<bj::u64> public_inputs;
+  uint64_t pow_challenge = 0;
   // queries[q][oracle]: witness, stage 2, quotient, setup, then one per FRI oracle
   std::vector<std::vector<bj::QueryAnswer>> queries;
   double stage_seconds[6] = {0, 0, 0, 0, 0, 0};
@@ -517,7 +518,6 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   }
   uint32_t new_pow = 0, num_queries = 0, sched[32], sched_len = 0, final_degree = 0;
   BJ_TRY(bj_compute_fri_schedule(c.security_level, cap, c.pow_bits, log_l, log_n, &new_pow, &num_queries, sched, &sched_len, &final_degree));
-  if (new_pow != 0) BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "bj_prove: proof-of-work is not implemented (the benches use NoPow)");
   bj_fri_oracles* fri = nullptr;
   BJ_TRY(bj_do_fri_with_hasher(ctx, tr, (const uint64_t*)deep.p, (const uint64_t*)deep.p + nL, log_n + log_l, sched, sched_len, log_l, cap,
                                c.tree_hasher, &fri));
@@ -535,6 +535,18 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   pf->mono_c0.resize(n_mono);
   pf->mono_c1.resize(n_mono);
   BJ_TRY(bj_fri_oracles_get_monomials(fri, (uint64_t*)pf->mono_c0.data(), (uint64_t*)pf->mono_c1.data()));
+  if (new_pow) {  // prover.rs:2109-2132 with POW = Blake2s256: 5 challenges seed the search, the nonce re-enters the transcript
+    uint8_t seed[40];
+    for (int i = 0; i < 5; i++) {
+      const uint64_t e = bj_transcript_get_challenge(tr);
+      for (int k = 0; k < 8; k++) seed[8 * i + k] = (uint8_t)(e >> (8 * k));
+    }
+    uint64_t nonce = 0;
+    BJ_TRY(bj_pow_blake2s(ctx, seed, 40, new_pow, &nonce));
+    pf->pow_challenge = nonce;
+    const uint64_t lh[2] = {nonce & 0xffffffffull, nonce >> 32};
+    bj_transcript_witness_field_elements(tr, lh, 2);
+  }
   BJ_TRY(mark(4));
 
   // ---- queries ----
@@ -628,7 +640,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     }
     s += "]}";
   }
-  s += "],\"pow_challenge\":0,\"_marker\":null}";
+  s += "],\"pow_challenge\":" + std::to_string(pf->pow_challenge) + ",\"_marker\":null}";
   *out = pf.release();
   return BJ_OK;
 }

@@ -342,7 +342,6 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     sched = (ctypes.c_uint32 * 32)()
     assert lib.bj_compute_fri_schedule(cfg.security_level, cap, cfg.pow_bits, log_L, log_n, ctypes.byref(np_), ctypes.byref(nq),
                                        sched, ctypes.byref(sl), ctypes.byref(fd)) == 0
-    assert np_.value == 0, "PoW is not implemented (benches use NoPow)"
     schedule = list(sched[: sl.value])
     if comm:
         fri = _ShardedFri(ctx, comm, tr, deep0, deep1, schedule, L, cap, cfg.hasher)
@@ -352,6 +351,12 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
         fri = ctx.do_fri(tr, deep0, deep1, schedule, L, cap, hasher=cfg.hasher)
         mono0, mono1 = fri.monomial_forms()
         fri_caps = [fri.get_cap(i) for i in range(fri.num_oracles())]
+    # proof of work (prover.rs:2109-2132; POW = Blake2s256): seeded by 5 challenges, the nonce goes back into the transcript
+    pow_challenge = 0
+    if np_.value:
+        seed = b"".join(int(tr.get_challenge()).to_bytes(8, "little") for _ in range(5))
+        pow_challenge = ctx.pow_blake2s(seed, np_.value)      # every rank of a sharded prover finds the same nonce
+        tr.witness_field_elements([pow_challenge & 0xFFFFFFFF, pow_challenge >> 32])
     mark("5_deep_fri", t0)
     # ---- queries (prover.rs:2161-2266): a query is answered by the rank that owns the coset of its index ----
     t0 = time.perf_counter()
@@ -395,5 +400,5 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
         "values_at_0": [_ext_dict(v) for v in values_at_0],
         "fri_base_oracle_cap": fri_caps[0].tolist(),
         "fri_intermediate_oracles_caps": [c_.tolist() for c_ in fri_caps[1:]],
-        "queries_per_fri_repetition": queries, "pow_challenge": 0, "_marker": None,
+        "queries_per_fri_repetition": queries, "pow_challenge": pow_challenge, "_marker": None,
     }

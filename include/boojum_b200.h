@@ -315,6 +315,13 @@ BJ_API int32_t bj_query_leaf_elements(bj_ctx* ctx, const uint64_t* const* h_sour
 BJ_API int32_t bj_merkle_paths(bj_ctx* ctx, const uint64_t* d_leaf_hashes, const uint64_t* d_nodes, uint64_t n_leaves,
                         uint32_t cap_size, const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out);
 
+/* ---- proof of work: impl PoWRunner for Blake2s256 (src/cs/implementations/pow.rs:52-147).  Returns the smallest u64
+ * `challenge` of the first successful 2^24-candidate batch for which the first 8 bytes (little endian) of
+ * Blake2s-256(seed || challenge.to_le_bytes()) have at least pow_bits (<= 32) trailing zero bits.  The seed is the byte
+ * string of run_from_field_elements (the LE bytes of the reduced field elements; 5 challenges = 40 bytes in
+ * prove_cpu_basic, prover.rs:2109-2126).  Synchronises. */
+BJ_API int32_t bj_pow_blake2s(bj_ctx* ctx, const uint8_t* h_seed, uint32_t seed_len, uint32_t pow_bits, uint64_t* h_challenge);
+
 /* ---- setup / witness materialisation on the device (what feeds bj_setup_create and bj_prove) ----
  * Variable encoding as in the reference (src/cs/mod.rs:44-47, :155-180): a u64 whose bit 63 marks a placeholder and whose
  * low 48 bits are the variable index.
@@ -333,7 +340,7 @@ BJ_API int32_t bj_create_permutation_polys(bj_ctx* ctx, const uint64_t* d_placem
  *      the setup materialisation it depends on (setup.rs:1093-1255: sigma / constant / lookup-table columns -> LDE -> setup tree).
  * Scope: gates on general-purpose columns (bj_gate_desc programs), copy permutation over all variable columns, optional
  * log-derivative lookup over specialised columns with the table id in a constant column (lookup_width = 0: none), Poseidon2
- * tree hasher and transcript, public inputs, no proof of work.  Host C++ inside the library: transcript, schedule, query
+ * or Blake2s tree hasher and transcript, public inputs, Blake2s proof of work (pow_bits > 0).  Host C++ inside the library: transcript, schedule, query
  * indices and proof assembly never leave the host; every heavy step is one of the entry points above.
  * Column arguments are DEVICE arrays [column][2^log_n] in natural row order.  bj_setup BORROWS d_sigmas / d_constants /
  * d_lookup_tables (stage 2 reads them again): they must outlive the setup.  The gate programs are copied.

@@ -195,7 +195,7 @@ def verify(vk, proof):
     ch = R.ext_powers(c, len(vals_z) + len(vals_zw) + len(vals_0) + sum(len(g[1]) for g in pi_groups))
     new_pow, num_queries, schedule, final_degree = R.compute_fri_schedule(
         proof["proof_config"]["security_level"], cap_size, proof["proof_config"]["pow_bits"], log_L, log_n)
-    assert new_pow == 0 and num_queries == len(proof["queries_per_fri_repetition"])
+    assert num_queries == len(proof["queries_per_fri_repetition"])
     fri_caps = [proof["fri_base_oracle_cap"]] + list(proof["fri_intermediate_oracles_caps"])
     assert len(fri_caps) == len(schedule)
     fri_ch = []
@@ -206,6 +206,16 @@ def verify(vk, proof):
     assert len(mono[0]) == final_degree == len(mono[1])
     tr.witness_field_elements(mono[0])
     tr.witness_field_elements(mono[1])
+    if new_pow:
+        # PoWRunner for Blake2s256 (pow.rs:135-146, verifier.rs: the same 5 challenges seed the check)
+        import hashlib
+        seed = b"".join(int(tr.get_challenge()).to_bytes(8, "little") for _ in range(5))
+        nonce = int(proof["pow_challenge"])
+        first = int.from_bytes(hashlib.blake2s(seed + nonce.to_bytes(8, "little"), digest_size=32).digest()[:8], "little")
+        assert first & ((1 << new_pow) - 1) == 0, "proof of work is invalid"
+        tr.witness_field_elements([nonce & 0xFFFFFFFF, nonce >> 32])
+    else:
+        assert proof["pow_challenge"] == 0
     max_bits = log_n + log_L
     bools = R.BoolsBuffer(max_bits)
     w_n = R.omega(log_n)

@@ -298,3 +298,30 @@ def test_blake2s_hasher_and_transcript_non_recursive_config(env, lookup, world):
         [t.join() for t in ts]
         assert not errs, errs
         assert all(json.dumps(o, sort_keys=True) == json.dumps(proof, sort_keys=True) for o in outs)
+
+
+def test_pow_blake2s_kernel_and_proof_with_pow_bits(env):
+    """PoWRunner for Blake2s256 (pow.rs:52-147) on the GPU, then a proof with pow_bits = 20 (ProofConfig default,
+    prover.rs:70): 98/3 -> fewer queries, nonce checked by the oracle verifier, both drivers agree."""
+    import hashlib
+    bj, ctx, prover, synthetic = env
+    for seed, bits in ((b"", 1), (bytes(range(40)), 12), (bytes(range(7)), 20), (bytes(range(52)), 9), (b"abc", 0)):
+        nonce = ctx.pow_blake2s(seed, bits)
+        first = int.from_bytes(hashlib.blake2s(seed + nonce.to_bytes(8, "little"), digest_size=32).digest()[:8], "little")
+        assert first & ((1 << bits) - 1) == 0
+        if bits <= 16:   # the serial search of the reference returns the smallest solution (pow.rs:60-73)
+            for c in range(nonce):
+                f = int.from_bytes(hashlib.blake2s(seed + c.to_bytes(8, "little"), digest_size=32).digest()[:8], "little")
+                assert f & ((1 << bits) - 1) != 0
+    variables, sigmas, constants, gates, Q = synthetic.generate(ctx, 9, 60, seed=51)
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, pow_bits=20)
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg)
+    proof = prover.prove(ctx, setup, variables)
+    assert proof["pow_challenge"] != 0 and len(proof["queries_per_fri_repetition"]) < 34
+    assert OV.verify(setup.vk(), proof)
+    nat = ctx.native_setup(sigmas, constants, gates, Q, cfg)
+    assert json.dumps(nat.prove(variables), sort_keys=True) == json.dumps(proof, sort_keys=True)
+    bad = copy.deepcopy(proof)
+    bad["pow_challenge"] += 1
+    with pytest.raises(AssertionError):
+        OV.verify(setup.vk(), bad)
