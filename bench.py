@@ -267,8 +267,8 @@ def main():
     peak, peak_kind = load_peaks()
     launches_per_step = launches / max(1, args.steps)
     algo_bytes_step = 16.0 * elems_per_step
-    achieved = algo_bytes_step / (ms * 1e-3) / 1e9  # the step is ntt_pass_kernel launches only
-    roofline = {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": round(achieved, 1), "peak": peak,
+    achieved = algo_bytes_step / (ms * 1e-3) / 1e9  # the step is ntt_pass_v2_kernel launches only
+    roofline = {"bound": "hbm", "kernel": "ntt_pass_v2_kernel", "achieved": round(achieved, 1), "peak": peak,
                 "peak_source": peak_kind + " hbm copy", "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "algo_bytes_per_launch": algo_bytes_step / max(1.0, launches_per_step),
                 "avg_launch_ms": ms / max(1.0, launches_per_step), "traffic": None}
