@@ -2,16 +2,19 @@
 """bench.py - headline measurement for the Boojum polynomial-commitment hot path on B200.
 
 metric  : Goldilocks NTT G-elements/s (BASELINE.json metric, first half).  The second half, proof-generation seconds
-          at 2^22 rows, is reported in the extra "prove" object on a synthetic SHA-256-bench-shaped circuit (the real
-          circuit needs the Rust synthesiser); "merkle" reports BASELINE configs[2].
+          at 2^22 rows at N GPUs, is reported in the extra objects "prove" (Poseidon2 tree + transcript: configs[4]) and
+          "prove_non_recursive" (Blake2s tree + transcript: configs[3]) on a synthetic SHA-256-bench-shaped circuit (the
+          real circuit needs the Rust synthesiser); one GPU runs the library's C++ driver bj_prove, several GPUs the
+          coset-sharded prover over NCCL.  "merkle" reports configs[2]; "ntt_family" the inverse / LDE figures of configs[1].
 workload: BASELINE.json configs[1] "2^20-2^24 Goldilocks NTT/LDE sweep on 1xB200": one step = forward
           natural->bit-reversed NTT on coset 7 (benches/benchmarks.rs:541 uses coset 7) of five resident batches,
           n = 2^20..2^24 with 128/64/32/16/8 columns (1 GiB each, SURVEY.md 8(d) cfg 2), in place, through the
           C-ABI (bj_ntt_natural_to_bitreversed).  5 GiB of inputs >> 126 MB L2, so no L2 flush is needed.
 value   : elements transformed per second, all ranks (columns shard across GPUs with no collective -> weak scaling).
 e2e     : the same sweep through bj_ntt_natural_to_bitreversed_host: pinned HOST buffers, H2D + NTT + D2H per step.
-roofline: dominant kernel ntt_pass_kernel; algorithmic bytes = 16 B per element per transform (read once, write
-          once) / measured HBM copy peak (MEASURED_PEAKS.json, burst figure).
+roofline: dominant kernel ntt_pass_v2_kernel; algorithmic bytes = 16 B per element per transform (read once, write
+          once) / measured HBM copy peak (MEASURED_PEAKS.json, burst figure); `traffic` = DRAM bytes per launch
+          from the committed ncu capture (profiles/ncu_traffic.json).
 cpu_baseline / --impl reference: the oracle's restatement of the reference CPU algorithm (one serial NTT per column,
           columns spread over all host threads, src/cs/implementations/utils.rs:295-304) on a bounded sample.
 """
