@@ -59,3 +59,64 @@ def test_sharding_maps():
     res = parallel.commit_sharded(parallel.OracleBackend(), None, torch.from_numpy(cols.view(np.int64)), 3, 4, 4)
     want = O.lde(cols, 2)
     assert np.array_equal(res["cap"].numpy().view(np.uint64), O.merkle_tree([want[c].reshape(-1) for c in range(3)], 4)[2])
+
+
+# ---- communicators and index maps of the coset-sharded PROVER (era_boojum_b200/prover.py with comm=...) ----
+def _comm_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from era_boojum_b200 import parallel
+    comm = parallel.TorchDistComm(dist)
+    assert (comm.rank, comm.world) == (rank, world)
+    got = comm.all_gather_host({"rank": rank, "a": np.arange(3) + rank})
+    assert [g["rank"] for g in got] == list(range(world)) and np.array_equal(got[1]["a"], np.arange(3) + 1)
+    assert comm.broadcast_host("from0" if rank == 0 else None, 0) == "from0"
+    # the quotient exchange: every rank fills only its own cosets, the integer sum recombines them exactly
+    L, Q, n = 8, 4, 16
+    qq = torch.zeros((2, Q, n), dtype=torch.int64)
+    full = torch.from_numpy(O.random_field(np.random.default_rng(5), (2, Q, n)).view(np.int64))
+    for k in range(Q // world):
+        qq[:, k * world + rank] = full[:, k * world + rank]
+    comm.all_reduce_sum_(qq)
+    assert torch.equal(qq, full)
+    # cap assembly: local trees over the owned cosets [k][row] -> the cap of the tree over all cosets [j][row]
+    cap = 16
+    cols = O.random_field(np.random.default_rng(9), (3, L * n)).reshape(3, L, n)
+    mine = parallel.owned_cosets(rank, world, L)
+    _, _, local_cap = O.merkle_tree([np.ascontiguousarray(cols[c][mine].reshape(-1)) for c in range(3)], cap // world)
+    _, _, want_cap = O.merkle_tree([cols[c].reshape(-1) for c in range(3)], cap)
+    assert np.array_equal(parallel.assemble_cap(comm, local_cap, L, cap), want_cap)
+    out[rank] = 1
+    dist.destroy_process_group()
+
+
+def test_prover_communicator_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_comm_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {0: 1, 1: 1}
+
+
+def test_local_leaf_index_and_thread_comm():
+    import threading
+    from era_boojum_b200 import parallel
+    log_n, world = 5, 4
+    seen = set()
+    for t in range(8 << log_n):                      # every global leaf has exactly one (owner, local index)
+        owner, loc = parallel.local_leaf_index(t, log_n, world)
+        assert owner == (t >> log_n) % world and (loc & 31) == (t & 31) and (loc >> log_n) == (t >> log_n) // world
+        seen.add((owner, loc))
+    assert len(seen) == 8 << log_n
+    assert parallel.LocalComm().all_gather_host(3) == [3]
+    shared, res = parallel.ThreadComm(3), [None] * 3
+
+    def run(r):
+        c = shared.rank_view(r)
+        res[r] = (c.all_gather_host(r * 10), c.broadcast_host("x" if r == 2 else None, 2))
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(3)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert res == [([0, 10, 20], "x")] * 3
