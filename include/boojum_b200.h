@@ -14,7 +14,9 @@
  *   - Fp2 elements are (c0, c1) pairs; Fp2 vectors are two separate u64 columns (SoA), as in the reference;
  *   - Poseidon2 digests are 4 x u64;
  *   - pointers named d_* are DEVICE pointers (cudaMalloc / bj_alloc / torch tensor data_ptr); h_* are host.
- *   - there is no CPU fallback: without a CUDA device bj_ctx_create fails with BJ_ERR_NO_DEVICE.
+ *   - there is no CPU fallback: without a CUDA device bj_ctx_create fails with BJ_ERR_NO_DEVICE;
+ *   - objects created through a context (bj_fri_oracles, bj_setup) hold device memory from that context's private
+ *     stream-ordered pool: free them before bj_ctx_destroy.  A bj_proof is host memory only.
  */
 #ifndef BOOJUM_B200_H
 #define BOOJUM_B200_H
