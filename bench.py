@@ -348,7 +348,7 @@ def main():
                          "algo_gbs": round(((8 * m_cols + 32) * (1 << m_log) + 96 * ((1 << m_log) - 16)) / m_ms / 1e6, 1)}
         del srcs, tree
     # second half of BASELINE.json's metric: proof generation seconds on the SHA-256-bench-shaped circuit (synthetic trace,
-    # 60 general-purpose columns, 3 gate types, quotient degree 4, LDE 8, cap 16, ~100-bit security; no lookup argument yet)
+    # 60 general-purpose columns + 8 lookup sub-arguments of width 4, 3 gate types, quotient degree 4, LDE 8, cap 16, ~100-bit security)
     if args.prove_log_n > 0:
         data = None
         torch.cuda.empty_cache()

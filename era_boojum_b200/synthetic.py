@@ -3,8 +3,9 @@ to synthesise the real circuit).
 
 Geometry of the reference bench (src/gadgets/sha256/mod.rs:307-373): 60 general-purpose columns under copy permutation,
 gates ConstantsAllocator (4 repetitions), FmaGateInBaseFieldWithoutConstant (15) and ReductionGate<4> (12) selected per
-row through a binary selector tree in the first constant columns, quotient degree 4.  (The lookup argument of the real
-bench is not part of this synthetic circuit.)  Every row satisfies the gate its selector picks, and neighbouring
+row through a binary selector tree in the first constant columns, quotient degree 4; with lookup=True also the bench's 8
+lookup sub-arguments of width 4 over specialised columns (table id in a constant column), and add_specialized_fma() places
+extra gates on specialised columns.  Every row satisfies the gate its selector picks, and neighbouring
 repetitions of a row are tied by copy constraints (the output of repetition k-1 is an input of repetition k), so the
 sigma polynomials are a non-trivial permutation.  All values are kept small enough that plain 64-bit integer arithmetic
 is exact, so the trace can be generated with torch on the GPU without field multiplications; the identity permutation
