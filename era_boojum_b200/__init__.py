@@ -30,9 +30,11 @@ class Transcript:
     """GoldilocksPoisedon2Transcript (cs/implementations/transcript.rs:62-129, 140-151) - host side."""
 
     def __init__(self, kind="poseidon2"):
-        """kind: "poseidon2" (GoldilocksPoisedon2Transcript) or "blake2s" (Blake2sTranscript, transcript.rs:155-260)."""
+        """kind: "poseidon2" (GoldilocksPoisedon2Transcript), "blake2s" (Blake2sTranscript, transcript.rs:155-260) or "keccak256"
+        (Keccak256Transcript, :262-367)."""
         self.kind = kind
-        self._h = ctypes.c_void_p(lib.bj_transcript_new_blake2s() if kind == "blake2s" else lib.bj_transcript_new())
+        new = {"poseidon2": lib.bj_transcript_new, "blake2s": lib.bj_transcript_new_blake2s, "keccak256": lib.bj_transcript_new_keccak256}
+        self._h = ctypes.c_void_p(new[kind]())
 
     def witness_field_elements(self, els):
         a = np.ascontiguousarray(np.array([int(e) for e in els], dtype=np.uint64))
@@ -254,7 +256,8 @@ class Context:
         dev = sources[0].device
         leaf_hashes = torch.empty((n_leaves, 4), dtype=torch.int64, device=dev)
         nodes = torch.empty((max(n_leaves - cap_size, 1), 4), dtype=torch.int64, device=dev)
-        build = {"poseidon2": lib.bj_merkle_build_poseidon2, "blake2s": lib.bj_merkle_build_blake2s}[hasher]
+        build = {"poseidon2": lib.bj_merkle_build_poseidon2, "blake2s": lib.bj_merkle_build_blake2s,
+                 "keccak256": lib.bj_merkle_build_keccak256}[hasher]
         self._check(build(self._h, ptrs, len(sources), n_leaves, elems_per_leaf, cap_size, self._ptr(leaf_hashes), self._ptr(nodes)))
         return MerkleTreeWithCap(cap_size, leaf_hashes, nodes[:max(n_leaves - cap_size, 0)])
 
@@ -485,7 +488,7 @@ class Context:
         sched = (ctypes.c_uint32 * len(schedule))(*schedule)
         h = ctypes.c_void_p()
         self._check(lib.bj_do_fri_with_hasher(self._h, transcript._h, self._ptr(c0), self._ptr(c1), log_full, sched, len(schedule),
-                                              lde_degree.bit_length() - 1, cap_size, {"poseidon2": 0, "blake2s": 1}[hasher], ctypes.byref(h)))
+                                              lde_degree.bit_length() - 1, cap_size, {"poseidon2": 0, "blake2s": 1, "keccak256": 2}[hasher], ctypes.byref(h)))
         fo = FriOracles(h, cap_size, (c0, c1))
         self._children.add(fo)
         return fo
@@ -526,8 +529,8 @@ class NativeSetup:
         pc = (ctypes.c_uint32 * max(1, len(pis)))(*[a for a, _ in pis])
         pr = (ctypes.c_uint32 * max(1, len(pis)))(*[b for _, b in pis])
         c.public_input_columns, c.public_input_rows, c.n_public_inputs = pc, pr, len(pis)
-        c.tree_hasher = {"poseidon2": 0, "blake2s": 1}[getattr(config, "hasher", "poseidon2")]
-        c.transcript = {"poseidon2": 0, "blake2s": 1}[getattr(config, "transcript", "poseidon2")]
+        c.tree_hasher = {"poseidon2": 0, "blake2s": 1, "keccak256": 2}[getattr(config, "hasher", "poseidon2")]
+        c.transcript = {"poseidon2": 0, "blake2s": 1, "keccak256": 2}[getattr(config, "transcript", "poseidon2")]
         self.cap_size = config.merkle_tree_cap_size
         h = ctypes.c_void_p()
         ctx._check(lib.bj_setup_create(ctx._h, ctypes.byref(c), ctx._ptr(sigmas), ctx._ptr(constants),

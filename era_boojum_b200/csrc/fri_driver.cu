@@ -142,7 +142,7 @@ int32_t bj_do_fri(bj_ctx* ctx, bj_transcript* transcript, const uint64_t* d_c0, 
 int32_t bj_do_fri_with_hasher(bj_ctx* ctx, bj_transcript* transcript, const uint64_t* d_c0, const uint64_t* d_c1, uint32_t log_full_size,
                               const uint32_t* schedule, uint32_t n_schedule, uint32_t log_lde, uint32_t cap_size, uint32_t hasher,
                               bj_fri_oracles** out) {
-  if (hasher != BJ_HASHER_POSEIDON2 && hasher != BJ_HASHER_BLAKE2S) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_do_fri: unknown tree hasher");
+  if (hasher > BJ_HASHER_KECCAK256) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_do_fri: unknown tree hasher");
   if (!ctx || !transcript || !d_c0 || !d_c1 || !schedule || n_schedule == 0 || !out || cap_size == 0 ||
       (cap_size & (cap_size - 1)) || log_full_size > 32 || log_lde > log_full_size)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_do_fri: bad argument");
@@ -176,7 +176,7 @@ int32_t bj_do_fri_with_hasher(bj_ctx* ctx, bj_transcript* transcript, const uint
     BJ_TRY(lv.leaf_hashes->alloc(ctx, sizeof(u64) * 4 * n_leaves));
     BJ_TRY(lv.nodes->alloc(ctx, sizeof(u64) * 4 * (n_leaves - cap_size)));
     const uint64_t* srcs[2] = {(const uint64_t*)cur0, (const uint64_t*)cur1};
-    BJ_TRY((hasher == BJ_HASHER_BLAKE2S ? bj_merkle_build_blake2s : bj_merkle_build_poseidon2)(
+    BJ_TRY((hasher == BJ_HASHER_BLAKE2S ? bj_merkle_build_blake2s : hasher == BJ_HASHER_KECCAK256 ? bj_merkle_build_keccak256 : bj_merkle_build_poseidon2)(
         ctx, srcs, 2, n_leaves, 1u << k, cap_size, (uint64_t*)lv.leaf_hashes->p, (uint64_t*)lv.nodes->p));
     lv.cap.resize(4 * (size_t)cap_size);
     const u64* cap_src = n_leaves == cap_size ? lv.leaf_hashes->u() : lv.nodes->u() + 4 * (n_leaves - 2 * (u64)cap_size);

@@ -9,6 +9,7 @@
 #include <vector>
 #include "ctx.hpp"
 #include "poseidon2.cuh"
+#include "keccak.cuh"
 
 namespace bj {
 // Streaming Blake2s-256 on the host (RFC 7693, unkeyed, 32-byte digest) for Blake2sTranscript.
@@ -93,8 +94,9 @@ struct HostBlake2s {
 }  // namespace bj
 
 struct bj_transcript {
-  int kind = 0;  // 0: Poseidon2 sponge transcript, 1: Blake2sTranscript (src/cs/implementations/transcript.rs:155-260)
+  int kind = 0;  // 0: Poseidon2 sponge, 1: Blake2sTranscript (transcript.rs:155-260), 2: Keccak256Transcript (:262-367)
   bj::HostBlake2s b2s;
+  bj::HostKeccak256 keccak;
   std::vector<uint8_t> byte_buffer, byte_available;
   size_t byte_pos = 0;
   std::vector<bj::u64> buffer;
@@ -108,10 +110,15 @@ struct bj_transcript {
 
 namespace bj {
 // Blake2sTranscript: absorb the pending bytes, re-seed the hasher with its own output, expose the 32 output bytes
+static void byte_hash_update(bj_transcript* t, const uint8_t* d, size_t n) {
+  if (t->kind == 2) t->keccak.update(d, n);
+  else t->b2s.update(d, n);
+}
 static void b2s_reseed(bj_transcript* t, bool keep_leftover) {
   uint8_t out[32];
-  t->b2s.finalize_reset(out);
-  t->b2s.update(out, 32);
+  if (t->kind == 2) t->keccak.finalize_reset(out);
+  else t->b2s.finalize_reset(out);
+  byte_hash_update(t, out, 32);
   if (!keep_leftover) {
     t->byte_available.clear();
     t->byte_pos = 0;
@@ -120,7 +127,7 @@ static void b2s_reseed(bj_transcript* t, bool keep_leftover) {
 }
 static void b2s_challenge_bytes(bj_transcript* t, size_t num, uint8_t* dst) {
   if (!t->byte_buffer.empty()) {
-    t->b2s.update(t->byte_buffer.data(), t->byte_buffer.size());
+    byte_hash_update(t, t->byte_buffer.data(), t->byte_buffer.size());
     t->byte_buffer.clear();
     b2s_reseed(t, false);
   }
@@ -155,11 +162,16 @@ bj_transcript* bj_transcript_new_blake2s(void) {
   t->kind = 1;
   return t;
 }
+bj_transcript* bj_transcript_new_keccak256(void) {
+  bj_transcript* t = new bj_transcript();
+  t->kind = 2;
+  return t;
+}
 void bj_transcript_free(bj_transcript* t) { delete t; }
 
 void bj_transcript_witness_field_elements(bj_transcript* t, const uint64_t* els, size_t n) {
   if (!t || (!els && n)) return;
-  if (t->kind == 1) {  // el.as_u64_reduced().to_le_bytes()
+  if (t->kind != 0) {  // el.as_u64_reduced().to_le_bytes()
     for (size_t i = 0; i < n; i++) {
       const u64 v = gl::canon(els[i]);
       for (int k = 0; k < 8; k++) t->byte_buffer.push_back((uint8_t)(v >> (8 * k)));
@@ -170,7 +182,7 @@ void bj_transcript_witness_field_elements(bj_transcript* t, const uint64_t* els,
 }
 
 void bj_transcript_witness_merkle_tree_cap(bj_transcript* t, const uint64_t* cap, size_t n_digests) {
-  if (t && t->kind == 1) {  // caps are raw 32-byte digests (4 little-endian u64 each), not field elements
+  if (t && t->kind != 0) {  // caps are raw 32-byte digests (4 little-endian u64 each), not field elements
     if (!cap && n_digests) return;
     for (size_t i = 0; i < 4 * n_digests; i++)
       for (int k = 0; k < 8; k++) t->byte_buffer.push_back((uint8_t)(cap[i] >> (8 * k)));
@@ -181,7 +193,7 @@ void bj_transcript_witness_merkle_tree_cap(bj_transcript* t, const uint64_t* cap
 
 uint64_t bj_transcript_get_challenge(bj_transcript* t) {
   if (!t) return 0;
-  if (t->kind == 1) {  // 8 challenge bytes, little endian, reduced (from_u64_with_reduction)
+  if (t->kind != 0) {  // 8 challenge bytes, little endian, reduced (from_u64_with_reduction)
     uint8_t b[8];
     b2s_challenge_bytes(t, 8, b);
     return gl::canon(le64(b));
@@ -209,7 +221,7 @@ uint64_t bj_transcript_get_challenge(bj_transcript* t) {
 uint64_t bj_transcript_get_index_bits(bj_transcript* t, uint32_t num_bits, uint32_t max_needed) {
   if (!t || num_bits > 64 || max_needed >= 64) return 0;
   while (t->bits.size() - t->bits_pos < num_bits) {
-    if (t->kind == 1) {  // non-algebraic transcript: 8 uniform bytes, all 64 bits (transcript.rs:401-413)
+    if (t->kind != 0) {  // non-algebraic transcript: 8 uniform bytes, all 64 bits (transcript.rs:401-413)
       uint8_t bb[8];
       b2s_challenge_bytes(t, 8, bb);
       const u64 el = le64(bb);

@@ -60,7 +60,7 @@ static int32_t oracle_build(bj_ctx* ctx, Oracle& o, u64 n_leaves, u32 cap_size, 
   if (n_leaves < cap_size) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "prover: oracle smaller than the cap");
   BJ_TRY(o.leaf_hashes.alloc(ctx, 4 * n_leaves));
   BJ_TRY(o.nodes.alloc(ctx, 4 * (n_leaves - cap_size)));
-  BJ_TRY((hasher == BJ_HASHER_BLAKE2S ? bj_merkle_build_blake2s : bj_merkle_build_poseidon2)(
+  BJ_TRY((hasher == BJ_HASHER_BLAKE2S ? bj_merkle_build_blake2s : hasher == BJ_HASHER_KECCAK256 ? bj_merkle_build_keccak256 : bj_merkle_build_poseidon2)(
       ctx, o.cols.data(), (u32)o.cols.size(), n_leaves, 1, cap_size, (uint64_t*)o.leaf_hashes.p, (uint64_t*)o.nodes.p));
   o.cap.resize(4 * (size_t)cap_size);
   const u64* src = n_leaves == cap_size ? o.leaf_hashes.p : o.nodes.p + 4 * (n_leaves - 2 * (u64)cap_size);
@@ -150,7 +150,7 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
   if (!ctx || !circuit || !d_sigmas || !out || circuit->num_variables == 0 || circuit->log_n == 0 || circuit->log_n > 28 ||
       !is_pow2(circuit->fri_lde_factor) || !is_pow2(circuit->merkle_tree_cap_size) || !is_pow2(circuit->quotient_degree) ||
       circuit->quotient_degree > circuit->fri_lde_factor || (circuit->num_constants && !d_constants) ||
-      (circuit->n_gates && !circuit->gates) || circuit->tree_hasher > BJ_HASHER_BLAKE2S || circuit->transcript > 1)
+      (circuit->n_gates && !circuit->gates) || circuit->tree_hasher > BJ_HASHER_KECCAK256 || circuit->transcript > 2)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_setup_create: bad argument");
   if (circuit->lookup_width && (!d_lookup_tables || circuit->lookup_table_id_column >= circuit->num_constants ||
                                 circuit->lookup_variables_offset + circuit->lookup_width * circuit->lookup_num_repetitions >
@@ -241,7 +241,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   struct TrGuard {
     bj_transcript* t;
     ~TrGuard() { bj_transcript_free(t); }
-  } trg{c.transcript == 1 ? bj_transcript_new_blake2s() : bj_transcript_new()};
+  } trg{c.transcript == 1 ? bj_transcript_new_blake2s() : c.transcript == 2 ? bj_transcript_new_keccak256() : bj_transcript_new()};
   bj_transcript* tr = trg.t;
   auto challenge2 = [&]() {
     gl::e2 r;

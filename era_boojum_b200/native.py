@@ -61,6 +61,7 @@ SIGNATURES = {
     "bj_lde": (_i32, [_vp, _vp, _u64, _vp, _u32, _u32, _u32, _i32]),
     "bj_merkle_build_poseidon2": (_i32, [_vp, _vp, _u32, _u64, _u32, _u32, _vp, _vp]),
     "bj_merkle_build_blake2s": (_i32, [_vp, _vp, _u32, _u64, _u32, _u32, _vp, _vp]),
+    "bj_merkle_build_keccak256": (_i32, [_vp, _vp, _u32, _u64, _u32, _u32, _vp, _vp]),
     "bj_poseidon2_hash_rows": (_i32, [_vp, _vp, _u64, _u32, _vp]),
     "bj_poseidon2_permute": (_i32, [_vp, _vp, _u64]),
     "bj_fri_fold": (_i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),
@@ -79,6 +80,7 @@ SIGNATURES = {
     "bj_intt_natural_to_natural_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
     "bj_transcript_new": (_vp, []),
     "bj_transcript_new_blake2s": (_vp, []),
+    "bj_transcript_new_keccak256": (_vp, []),
     "bj_transcript_free": (None, [_vp]),
     "bj_transcript_witness_field_elements": (None, [_vp, _vp, _sz]),
     "bj_transcript_witness_merkle_tree_cap": (None, [_vp, _vp, _sz]),
@@ -115,6 +117,7 @@ SIGNATURES = {
     "bj_host_e2_mul": (None, [_vp, _vp, _vp]),
     "bj_host_e2_inv": (None, [_vp, _vp]),
     "bj_host_poseidon2_permutation": (None, [_vp]),
+    "bj_host_keccak256": (None, [_vp, _sz, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -117,6 +117,9 @@ BJ_API int32_t bj_merkle_build_poseidon2(bj_ctx* ctx, const uint64_t* const* h_s
  * elements, node = Blake2s-256(left || right); 32-byte digests stored as 4 LE u64 (same [n][4] layout). */
 BJ_API int32_t bj_merkle_build_blake2s(bj_ctx* ctx, const uint64_t* const* h_sources, uint32_t n_sources, uint64_t n_leaves,
                                 uint32_t elems_per_leaf, uint32_t cap_size, uint64_t* d_leaf_hashes, uint64_t* d_nodes);
+/* impl TreeHasher for sha3::Keccak256 (src/cs/oracle/mod.rs:247-313): same layout and arguments, Keccak-256 digests */
+BJ_API int32_t bj_merkle_build_keccak256(bj_ctx* ctx, const uint64_t* const* h_sources, uint32_t n_sources, uint64_t n_leaves,
+                                uint32_t elems_per_leaf, uint32_t cap_size, uint64_t* d_leaf_hashes, uint64_t* d_nodes);
 /* TreeHasher::hash_into_leaf on rows given contiguously: n_rows rows of row_len u64 (row-major) -> digests */
 BJ_API int32_t bj_poseidon2_hash_rows(bj_ctx* ctx, const uint64_t* d_rows, uint64_t n_rows, uint32_t row_len,
                                uint64_t* d_digests);
@@ -272,6 +275,7 @@ BJ_API bj_transcript* bj_transcript_new(void);          /* GoldilocksPoisedon2Tr
  * 8 LE bytes of their reduced value, caps as raw 32-byte digests; a challenge is 8 output bytes reduced mod p; query bits
  * take all 64 bits of 8 challenge bytes (BoolsBuffer, non-algebraic branch). */
 BJ_API bj_transcript* bj_transcript_new_blake2s(void);
+BJ_API bj_transcript* bj_transcript_new_keccak256(void); /* Keccak256Transcript (transcript.rs:262-367): same scheme, Keccak-256 */
 BJ_API void bj_transcript_free(bj_transcript* t);
 BJ_API void bj_transcript_witness_field_elements(bj_transcript* t, const uint64_t* els, size_t n);
 BJ_API void bj_transcript_witness_merkle_tree_cap(bj_transcript* t, const uint64_t* cap_digests, size_t n_digests);
@@ -296,7 +300,8 @@ BJ_API int32_t bj_do_fri(bj_ctx* ctx, bj_transcript* transcript, const uint64_t*
                   uint32_t cap_size, bj_fri_oracles** out);
 #define BJ_HASHER_POSEIDON2 0u
 #define BJ_HASHER_BLAKE2S 1u
-/* same with the tree hasher chosen (BJ_HASHER_*: GoldilocksPoseidon2Sponge or Blake2s256, src/cs/oracle/mod.rs:114-245) */
+#define BJ_HASHER_KECCAK256 2u
+/* same with the tree hasher chosen (BJ_HASHER_*: GoldilocksPoseidon2Sponge, Blake2s256 or Keccak256, src/cs/oracle/mod.rs:114-313) */
 BJ_API int32_t bj_do_fri_with_hasher(bj_ctx* ctx, bj_transcript* transcript, const uint64_t* d_c0, const uint64_t* d_c1,
                               uint32_t log_full_size, const uint32_t* schedule, uint32_t n_schedule, uint32_t log_lde,
                               uint32_t cap_size, uint32_t hasher, bj_fri_oracles** out);
@@ -364,8 +369,8 @@ typedef struct bj_circuit {
   const uint32_t* public_input_columns;
   const uint32_t* public_input_rows;
   uint32_t n_public_inputs;
-  uint32_t tree_hasher; /* BJ_HASHER_POSEIDON2 (recursive-mode bench) or BJ_HASHER_BLAKE2S (sha256_bench_non_recursive) */
-  uint32_t transcript;  /* 0: Poseidon2 sponge transcript, 1: Blake2sTranscript */
+  uint32_t tree_hasher; /* BJ_HASHER_POSEIDON2 (recursive-mode bench), BJ_HASHER_BLAKE2S (sha256_bench_non_recursive), BJ_HASHER_KECCAK256 */
+  uint32_t transcript;  /* 0: Poseidon2 sponge transcript, 1: Blake2sTranscript, 2: Keccak256Transcript */
 } bj_circuit;
 typedef struct bj_setup bj_setup;
 typedef struct bj_proof bj_proof;
@@ -394,6 +399,7 @@ BJ_API uint64_t bj_host_gl_mul_pow2(uint64_t a, uint32_t s);
 BJ_API void bj_host_e2_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
 BJ_API void bj_host_e2_inv(const uint64_t a[2], uint64_t out[2]);
 BJ_API void bj_host_poseidon2_permutation(uint64_t state[12]);
+BJ_API void bj_host_keccak256(const uint8_t* data, size_t n, uint8_t out[32]);
 
 #ifdef __cplusplus
 }

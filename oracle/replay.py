@@ -104,15 +104,33 @@ class Poseidon2Transcript:
         return (c0, c1)
 
 
+class _KeccakStream:
+    """hashlib-like wrapper of the pure-Python Keccak-256 oracle (oracle/keccak.py)."""
+
+    def __init__(self):
+        self.data = b""
+
+    def update(self, b):
+        self.data += bytes(b)
+
+    def digest(self):
+        from .keccak import keccak256
+        return keccak256(self.data)
+
+
 class Blake2sTranscript:
     """Blake2sTranscript (src/cs/implementations/transcript.rs:155-260): the byte buffer is hashed into a running
     Blake2s-256 whose state is re-seeded with every 32-byte output; challenges are 8 output bytes, little endian, reduced
-    mod p.  Caps are raw 32-byte digests (given here as 4 little-endian u64 each)."""
+    mod p.  Caps are raw 32-byte digests (given here as 4 little-endian u64 each).  Keccak256Transcript (:262-367) is the
+    same scheme over Keccak-256 (subclass below)."""
     IS_ALGEBRAIC = False
 
-    def __init__(self):
+    def _hasher(self):
         import hashlib
-        self._new = lambda: hashlib.blake2s(digest_size=32)
+        return hashlib.blake2s(digest_size=32)
+
+    def __init__(self):
+        self._new = self._hasher
         self.inner = self._new()
         self.buffer = b""
         self.available = b""
@@ -154,6 +172,22 @@ class Blake2sTranscript:
         return (c0, c1)
 
 
+class Keccak256Transcript(Blake2sTranscript):
+    def _hasher(self):
+        return _KeccakStream()
+
+
+def keccak_leaf_hash(elements):
+    """impl TreeHasher for sha3::Keccak256 (src/cs/oracle/mod.rs:247-313)."""
+    from .keccak import keccak256
+    return np.frombuffer(keccak256(b"".join((int(e) % P).to_bytes(8, "little") for e in elements)), dtype="<u8").copy()
+
+
+def keccak_node_hash(left, right):
+    from .keccak import keccak256
+    return np.frombuffer(keccak256(np.asarray(left, dtype="<u8").tobytes() + np.asarray(right, dtype="<u8").tobytes()), dtype="<u8").copy()
+
+
 def blake2s_leaf_hash(elements):
     """impl TreeHasher for Blake2s256 (src/cs/oracle/mod.rs:179-245): digest over the LE bytes of the reduced elements,
     returned as 4 little-endian u64 (byte-identical to [u8; 32])."""
@@ -180,6 +214,8 @@ def hasher_functions(name):
     """(leaf hash, path verifier) of a tree hasher."""
     if name == "blake2s":
         return blake2s_leaf_hash, (lambda leaf, path, cap, idx: merkle_verify_generic(leaf, path, cap, idx, blake2s_node_hash))
+    if name == "keccak256":
+        return keccak_leaf_hash, (lambda leaf, path, cap, idx: merkle_verify_generic(leaf, path, cap, idx, keccak_node_hash))
     return (lambda els: O.poseidon2_hash_leaf(np.array(els, dtype=np.uint64))), \
            (lambda leaf, path, cap, idx: O.merkle_verify(leaf, np.asarray(path, dtype=np.uint64).reshape(-1, 4), np.array(cap, dtype=np.uint64), idx))
 

@@ -821,3 +821,20 @@ def test_c_abi_rejects_misuse_with_status_codes(bj, ctx):
     # the context stays usable afterwards
     x = O.random_field(rng(1), (1, 16))
     assert np.array_equal(bj.to_numpy(ctx.fft_natural_to_bitreversed(bj.to_device(x), 1)), O.ntt_n2b(x, 1))
+
+
+@pytest.mark.parametrize("n_cols,log_leaves,cap,epl", [(1, 3, 1, 1), (8, 5, 4, 1), (17, 6, 8, 1), (18, 4, 2, 1), (93, 7, 16, 1), (2, 6, 4, 8), (34, 3, 8, 1)])
+def test_merkle_keccak256_matches_oracle(bj, ctx, n_cols, log_leaves, cap, epl):
+    """impl TreeHasher for sha3::Keccak256 (src/cs/oracle/mod.rs:247-313): leaves over 1, <17, =17, >17 and a multiple of
+    17 lanes (the rate is 17 u64), chunked leaves, caps from 1 to the number of leaves."""
+    n = 1 << log_leaves
+    cols = [O.random_field(rng(100 + c), n * epl) for c in range(n_cols)]
+    if n_cols > 2:
+        cols[1][:] = np.uint64(0xFFFFFFFFFFFFFFFF)          # non-canonical input: hashed as its reduced value
+    tree = ctx.merkle_tree_construct([bj.to_device(c) for c in cols], cap, elems_per_leaf=epl, hasher="keccak256")
+    leaves = [replay.keccak_leaf_hash([int(v) for c in cols for v in c[i * epl:(i + 1) * epl]]) for i in range(n)]
+    assert np.array_equal(bj.to_numpy(tree.leaf_hashes), np.array(leaves, dtype=np.uint64))
+    level = leaves
+    while len(level) > cap:
+        level = [replay.keccak_node_hash(level[2 * i], level[2 * i + 1]) for i in range(len(level) // 2)]
+    assert np.array_equal(tree.get_cap(), np.array(level, dtype=np.uint64))

@@ -325,3 +325,20 @@ def test_pow_blake2s_kernel_and_proof_with_pow_bits(env):
     bad["pow_challenge"] += 1
     with pytest.raises(AssertionError):
         OV.verify(setup.vk(), bad)
+
+
+def test_keccak256_hasher_and_transcript(env):
+    """H = Keccak256, TR = Keccak256Transcript (the third TreeHasher / transcript pair of the reference): both drivers agree
+    and the oracle verifier (pure-Python Keccak-256) accepts."""
+    bj, ctx, prover, synthetic = env
+    variables, sigmas, constants, gates, Q = synthetic.generate(ctx, 8, 20, seed=61)
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher="keccak256", transcript="keccak256")
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg)
+    proof = prover.prove(ctx, setup, variables)
+    assert OV.verify(setup.vk(), proof)
+    nat = ctx.native_setup(sigmas, constants, gates, Q, cfg)
+    assert json.dumps(nat.prove(variables), sort_keys=True) == json.dumps(proof, sort_keys=True)
+    bad = copy.deepcopy(proof)
+    bad["queries_per_fri_repetition"][1]["stage_2_query"]["proof"][0][0] ^= 1
+    with pytest.raises(AssertionError):
+        OV.verify(setup.vk(), bad)

@@ -142,3 +142,50 @@ def test_blake2s_transcript_known_answer():
     assert int(lib.bj_transcript_get_challenge(h)) == int.from_bytes(d[:8], "little") % replay.P
     assert int(lib.bj_transcript_get_challenge(h)) == int.from_bytes(d[8:16], "little") % replay.P
     lib.bj_transcript_free(h)
+
+
+def test_keccak256_host_against_known_answers_and_oracle():
+    """the library's Keccak-256 (same keccak.cuh source as the device Merkle kernels, compiled for the host) against the two
+    classic known answers and, for every length around the 136-byte rate, against the pure-Python oracle."""
+    from oracle.keccak import keccak256
+    lib = _lib()
+
+    def c_keccak(b):
+        out = (ctypes.c_uint8 * 32)()
+        buf = (ctypes.c_uint8 * max(1, len(b)))(*b)
+        lib.bj_host_keccak256(buf, len(b), out)
+        return bytes(out)
+
+    assert keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert keccak256(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+    assert c_keccak(b"") == keccak256(b"") and c_keccak(b"abc") == keccak256(b"abc")
+    r = np.random.default_rng(11)
+    for n in list(range(0, 20)) + [63, 64, 65, 134, 135, 136, 137, 271, 272, 273, 500]:
+        msg = bytes(r.integers(0, 256, size=n, dtype=np.uint8))
+        assert c_keccak(msg) == keccak256(msg), n
+
+
+def test_keccak256_transcript_matches_oracle_random_script():
+    lib = _lib()
+    r = np.random.default_rng(4)
+    for trial in range(6):
+        h = ctypes.c_void_p(lib.bj_transcript_new_keccak256())
+        o = replay.Keccak256Transcript()
+        bools = replay.BoolsBuffer(25)
+        for step in range(40):
+            op = r.integers(0, 4)
+            if op == 0:
+                els = r.integers(0, 2**64 - 1, size=int(r.integers(0, 20)), dtype=np.uint64)
+                lib.bj_transcript_witness_field_elements(h, els.ctypes.data_as(ctypes.c_void_p), len(els))
+                o.witness_field_elements([int(e) for e in els])
+            elif op == 1:
+                cap = r.integers(0, 2**64 - 1, size=(int(r.integers(1, 5)), 4), dtype=np.uint64)
+                lib.bj_transcript_witness_merkle_tree_cap(h, cap.ctypes.data_as(ctypes.c_void_p), cap.shape[0])
+                o.witness_merkle_tree_cap(cap.tolist())
+            elif op == 2:
+                for _ in range(int(r.integers(1, 7))):
+                    assert int(lib.bj_transcript_get_challenge(h)) == o.get_challenge()
+            else:
+                bits = bools.get_bits(o, 25)
+                assert int(lib.bj_transcript_get_index_bits(h, 25, 25)) == sum(b << i for i, b in enumerate(bits))
+        lib.bj_transcript_free(h)
