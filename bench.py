@@ -89,6 +89,8 @@ def run_reference(args, rank, world):
         return
     import numpy as np
     from oracle import oracle as O
+    # all host threads this process may use, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+    O.lib().orc_set_threads(len(os.sched_getaffinity(0)))
     threads = O.num_threads()
     rng = np.random.default_rng(0)
     cols = {m: max(1, min(threads, 1 << (BATCH_ELEMS_LOG - m))) for m in SIZES}
@@ -122,6 +124,7 @@ def run_reference(args, rank, world):
 def cpu_baseline_sample():
     import numpy as np
     from oracle import oracle as O
+    O.lib().orc_set_threads(len(os.sched_getaffinity(0)))
     threads = O.num_threads()
     m = 22
     cols = max(8, threads)
