@@ -608,8 +608,10 @@ static int32_t host_pipeline(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint
   if (n_cols == 0) return BJ_OK;
   const u64 n = 1ull << log_n;
   const size_t col_bytes = sizeof(u64) * n;
-  // ~64 MiB chunks, at least one column
-  u32 chunk_cols = (u32)std::max<u64>(1, std::min<u64>(n_cols, ((64ull << 20) / col_bytes)));
+  // chunks of ~ntt_chunk_mb MiB (BJ_NTT_CHUNK_MB), at least one column: small enough that the un-overlapped first upload
+  // and last download of a call stay short, large enough to keep the copy engines and the pass kernels efficient
+  const u64 chunk_bytes = (u64)(ctx->ntt_chunk_mb > 0 ? ctx->ntt_chunk_mb : 64) << 20;
+  u32 chunk_cols = (u32)std::max<u64>(1, std::min<u64>(n_cols, chunk_bytes / col_bytes));
   const u32 n_chunks = (n_cols + chunk_cols - 1) / chunk_cols;
   const int SLOTS = 3;
   if (!ctx->copy_streams_ready) {
