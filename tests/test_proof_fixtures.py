@@ -1,0 +1,134 @@
+"""Recorded product outputs (tests/golden/synthetic_proof_*.json, written by tools/make_proof_fixtures.py on a B200): small
+proofs of the synthetic circuits for the three tree-hasher / transcript configurations, with lookup argument, public inputs
+and proof of work in the Blake2s one.
+  * CPU: the oracle's restatement of the reference verifier accepts them and rejects tampering (guards the verifier
+    restatement itself, and pins the library's host transcripts / schedules through the C++ replay below);
+  * GPU: both prover drivers reproduce the recorded proofs bit for bit (proof stability across refactors)."""
+import copy
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import verifier as OV
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CONFIGS = ["poseidon2", "blake2s", "keccak256"]
+
+
+def _load(name):
+    with open(os.path.join(HERE, "golden", "synthetic_proof_%s.json" % name)) as f:
+        fx = json.load(f)
+    fx["vk"]["gates"] = [tuple(g) for g in fx["vk"]["gates"]]
+    return fx
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_oracle_verifier_accepts_recorded_proofs_and_rejects_tampering(name):
+    fx = _load(name)
+    vk, proof = fx["vk"], fx["proof"]
+    assert vk["hasher"] == name and OV.verify(vk, proof)
+    for mutate in (lambda p: p["values_at_z"][0]["coeffs"].__setitem__(0, p["values_at_z"][0]["coeffs"][0] ^ 1),
+                   lambda p: p["final_fri_monomials"][1].__setitem__(0, p["final_fri_monomials"][1][0] ^ 1),
+                   lambda p: p["queries_per_fri_repetition"][-1]["fri_queries"][0]["leaf_elements"].__setitem__(
+                       0, p["queries_per_fri_repetition"][-1]["fri_queries"][0]["leaf_elements"][0] ^ 1),
+                   lambda p: p["witness_oracle_cap"][3].__setitem__(1, p["witness_oracle_cap"][3][1] ^ 1)):
+        bad = copy.deepcopy(proof)
+        mutate(bad)
+        with pytest.raises(AssertionError):
+            OV.verify(vk, bad)
+    if fx["generator"]["pow_bits"]:
+        assert proof["pow_challenge"] != 0
+        bad = copy.deepcopy(proof)
+        bad["pow_challenge"] ^= 1
+        with pytest.raises(AssertionError):
+            OV.verify(vk, bad)
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_library_host_transcript_replays_recorded_proofs(name):
+    """the product's host C++ (transcript of the configured kind, FRI schedule, query-index bits) replays the Fiat-Shamir
+    script of the recorded proof and arrives at query indices whose Merkle paths verify - no device involved."""
+    from era_boojum_b200 import native
+    from oracle import replay as R
+    lib = native.lib
+    fx = _load(name)
+    vk, proof = fx["vk"], fx["proof"]
+    new = {"poseidon2": lib.bj_transcript_new, "blake2s": lib.bj_transcript_new_blake2s, "keccak256": lib.bj_transcript_new_keccak256}[name]
+    tr = ctypes.c_void_p(new())
+
+    def cap(c):
+        a = np.array(c, dtype=np.uint64).reshape(-1, 4)
+        lib.bj_transcript_witness_merkle_tree_cap(tr, a.ctypes.data_as(ctypes.c_void_p), a.shape[0])
+
+    def els(v):
+        a = np.array([int(x) for x in v], dtype=np.uint64)
+        lib.bj_transcript_witness_field_elements(tr, a.ctypes.data_as(ctypes.c_void_p), len(a))
+
+    def ch(k=2):
+        return [int(lib.bj_transcript_get_challenge(tr)) for _ in range(k)]
+
+    cap(vk["setup_merkle_tree_cap"])
+    for v in proof["public_inputs"]:
+        els([v])
+    cap(proof["witness_oracle_cap"])
+    ch(4 + (4 if vk["lookup"] else 0))                    # beta, gamma (+ lookup beta, gamma)
+    cap(proof["stage_2_oracle_cap"])
+    ch(2)                                                  # alpha
+    cap(proof["quotient_oracle_cap"])
+    ch(2)                                                  # z
+    for group in ("values_at_z", "values_at_z_omega", "values_at_0"):
+        for v in proof[group]:
+            els(v["coeffs"])
+    ch(2)                                                  # DEEP challenge
+    log_n, L, cap_size = vk["domain_size"].bit_length() - 1, vk["fri_lde_factor"], vk["cap_size"]
+    np_, nq, sl, fd = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    sched = (ctypes.c_uint32 * 32)()
+    assert lib.bj_compute_fri_schedule(proof["proof_config"]["security_level"], cap_size, proof["proof_config"]["pow_bits"],
+                                       L.bit_length() - 1, log_n, ctypes.byref(np_), ctypes.byref(nq), sched, ctypes.byref(sl),
+                                       ctypes.byref(fd)) == 0
+    assert nq.value == len(proof["queries_per_fri_repetition"]) and fd.value == len(proof["final_fri_monomials"][0])
+    for c in [proof["fri_base_oracle_cap"]] + proof["fri_intermediate_oracles_caps"]:
+        cap(c)
+        ch(2)
+    els(proof["final_fri_monomials"][0])
+    els(proof["final_fri_monomials"][1])
+    if np_.value:
+        seed = b"".join(int(x).to_bytes(8, "little") for x in ch(5))
+        import hashlib
+        first = int.from_bytes(hashlib.blake2s(seed + int(proof["pow_challenge"]).to_bytes(8, "little"), digest_size=32).digest()[:8], "little")
+        assert first & ((1 << np_.value) - 1) == 0
+        els([proof["pow_challenge"] & 0xFFFFFFFF, proof["pow_challenge"] >> 32])
+    leaf_fn, path_ok = R.hasher_functions(name)
+    bits = log_n + L.bit_length() - 1
+    for q in proof["queries_per_fri_repetition"]:
+        idx = int(lib.bj_transcript_get_index_bits(tr, bits, bits))
+        for oracle, c in (("witness_query", proof["witness_oracle_cap"]), ("setup_query", vk["setup_merkle_tree_cap"])):
+            assert path_ok(leaf_fn(q[oracle]["leaf_elements"]), q[oracle]["proof"], c, idx), (oracle, idx)
+    lib.bj_transcript_free(tr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CONFIGS)
+def test_provers_reproduce_recorded_proofs_bit_for_bit(name):
+    import era_boojum_b200 as bj
+    from era_boojum_b200 import prover, synthetic
+    fx = _load(name)
+    g = fx["generator"]
+    ctx = bj.Context.on_current_stream(0)
+    gen = synthetic.generate(ctx, g["log_n"], g["num_variables"], seed=g["seed"], lookup=g["lookup"])
+    lk = gen[5] if g["lookup"] else None
+    variables, sigmas, constants, gates, Q = gen[:5]
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, pow_bits=g["pow_bits"], hasher=name,
+                             transcript=name)
+    pis = [tuple(p) for p in g["public_inputs"]]
+    m = lk["multiplicities"] if lk else None
+    want = json.dumps(fx["proof"], sort_keys=True)
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg, lookup=lk, public_inputs=pis)
+    assert json.dumps(prover.prove(ctx, setup, variables, multiplicities=m), sort_keys=True) == want
+    nat = ctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk, public_inputs=pis)
+    assert json.dumps(nat.prove(variables, m), sort_keys=True) == want
+    nat.close()
+    ctx.close()
