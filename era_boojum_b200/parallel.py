@@ -12,7 +12,7 @@ The exchange between the two: ONE all-gather of the monomial coefficients (8*n*V
 digests move (32 bytes each).  The result is bit-identical to the single-GPU commitment.
 
 Compute goes through a small backend object so the same sharding / gathering / assembly code runs on the GPU (Context
-kernels) and, in the CPU tests, on the oracle (world_size 2, gloo).
+kernels, TorchBackend) and, in the CPU tests, on a test-side stand-in (tests/_oracle_backend.py; world_size 2, gloo).
 """
 import numpy as np
 
@@ -62,35 +62,6 @@ class TorchBackend:
 
     def empty(self, shape, like):
         return self.torch.empty(shape, dtype=self.torch.int64, device=like.device)
-
-
-class OracleBackend:
-    """CPU stand-in used by the gloo tests: same interface on torch CPU int64 tensors, computed by the oracle."""
-
-    def __init__(self):
-        import torch
-        from oracle import oracle as O
-        self.torch, self.O = torch, O
-
-    def _np(self, t):
-        return t.numpy().view(np.uint64)
-
-    def _t(self, a):
-        return self.torch.from_numpy(np.ascontiguousarray(a).view(np.int64))
-
-    def intt(self, cols):
-        return self._t(self.O.intt_n2n(self._np(cols)))
-
-    def coset_ntt(self, monomials, shift):
-        return self._t(self.O.ntt_n2b(self._np(monomials), shift))
-
-    def subtree(self, cols_2d, cap):
-        a = self._np(cols_2d)
-        lh, levels, capd = self.O.merkle_tree([a[c] for c in range(a.shape[0])], cap)
-        return (lh, levels), self._t(capd)
-
-    def empty(self, shape, like):
-        return self.torch.empty(shape, dtype=self.torch.int64)
 
 
 def commit_sharded(backend, dist, local_cols, n_cols_total, lde_factor, cap_size, group=None):

@@ -11,6 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import oracle as O
+from tests._oracle_backend import OracleBackend
 
 
 def _free_port():
@@ -29,7 +30,7 @@ def _worker(rank, world, port, V, log_n, L, cap, out):
     cols = O.random_field(np.random.default_rng(7), (V, 1 << log_n))
     blk = parallel.column_block(rank, world, V)
     local = torch.from_numpy(np.ascontiguousarray(cols[blk.start:blk.stop]).view(np.int64))
-    res = parallel.commit_sharded(parallel.OracleBackend(), dist, local, V, L, cap)
+    res = parallel.commit_sharded(OracleBackend(), dist, local, V, L, cap)
     want_lde = O.lde(cols, L.bit_length() - 1)
     for j, ev in res["cosets"].items():
         assert np.array_equal(ev.numpy().view(np.uint64), want_lde[:, j, :]), ("coset", j)
@@ -56,7 +57,7 @@ def test_sharding_maps():
     assert parallel.leaf_owner((5 << 10) + 3, 10, 4) == 1
     # single-process path (no process group) equals the oracle too
     cols = O.random_field(np.random.default_rng(1), (3, 32))
-    res = parallel.commit_sharded(parallel.OracleBackend(), None, torch.from_numpy(cols.view(np.int64)), 3, 4, 4)
+    res = parallel.commit_sharded(OracleBackend(), None, torch.from_numpy(cols.view(np.int64)), 3, 4, 4)
     want = O.lde(cols, 2)
     assert np.array_equal(res["cap"].numpy().view(np.uint64), O.merkle_tree([want[c].reshape(-1) for c in range(3)], 4)[2])
 
