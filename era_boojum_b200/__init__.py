@@ -60,6 +60,12 @@ class Transcript:
             self._h = None
 
 
+def _ok(status, what="libboojum_b200 call"):
+    """status check for context-free C-ABI calls (never inside an `assert`: `python -O` would drop the call itself)."""
+    if status != 0:
+        raise BoojumError(status, "%s: %s" % (what, lib.bj_status_string(status).decode()))
+
+
 class FriOracles:
     """FriOracles (cs/implementations/fri/mod.rs:36-47): base + intermediate oracle caps, monomial forms, queries."""
 
@@ -71,18 +77,18 @@ class FriOracles:
 
     def get_cap(self, i):
         out = np.zeros((self.cap_size, 4), np.uint64)
-        assert lib.bj_fri_oracles_get_cap(self._h, i, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        _ok(lib.bj_fri_oracles_get_cap(self._h, i, out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
     def monomial_forms(self):
         n = int(lib.bj_fri_oracles_num_monomials(self._h))
         c0, c1 = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
-        assert lib.bj_fri_oracles_get_monomials(self._h, c0.ctypes.data_as(ctypes.c_void_p), c1.ctypes.data_as(ctypes.c_void_p)) == 0
+        _ok(lib.bj_fri_oracles_get_monomials(self._h, c0.ctypes.data_as(ctypes.c_void_p), c1.ctypes.data_as(ctypes.c_void_p)))
         return c0, c1
 
     def challenges(self):
         out = np.zeros((self.num_oracles(), 2), np.uint64)
-        assert lib.bj_fri_oracles_get_challenges(self._h, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        _ok(lib.bj_fri_oracles_get_challenges(self._h, out.ctypes.data_as(ctypes.c_void_p)))
         return [tuple(int(x) for x in r) for r in out]
 
     def query(self, oracle_idx, leaf_index, log_fold):
@@ -301,7 +307,7 @@ class Context:
     @staticmethod
     def non_residues_for_copy_permutation(domain_size, num_columns):
         out = np.zeros(num_columns, np.uint64)
-        assert lib.bj_non_residues_for_copy_permutation(domain_size, num_columns, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        _ok(lib.bj_non_residues_for_copy_permutation(domain_size, num_columns, out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
     def compute_partial_products_in_extension(self, variables, sigmas, beta, gamma, max_degree):
@@ -467,7 +473,8 @@ class Context:
         ptrs = (ctypes.c_void_p * n_src)(*[s.data_ptr() for s in sources])
         idx = np.ascontiguousarray(np.array(indices, dtype=np.uint64))
         out = np.zeros((len(idx), n_src * elems_per_leaf), np.uint64)
-        self._check(lib.bj_query_leaf_elements(self._h, ptrs, n_src, elems_per_leaf, idx.ctypes.data_as(ctypes.c_void_p),
+        n_leaves = min(int(s.numel()) for s in sources) // elems_per_leaf
+        self._check(lib.bj_query_leaf_elements(self._h, ptrs, n_src, elems_per_leaf, n_leaves, idx.ctypes.data_as(ctypes.c_void_p),
                                                len(idx), out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
@@ -532,6 +539,7 @@ class NativeSetup:
         c.tree_hasher = {"poseidon2": 0, "blake2s": 1, "keccak256": 2}[getattr(config, "hasher", "poseidon2")]
         c.transcript = {"poseidon2": 0, "blake2s": 1, "keccak256": 2}[getattr(config, "transcript", "poseidon2")]
         self.cap_size = config.merkle_tree_cap_size
+        self._vk_args = (c.log_n, c.num_variables, c.num_constants, gates, quotient_degree, config, lookup, pis)
         h = ctypes.c_void_p()
         ctx._check(lib.bj_setup_create(ctx._h, ctypes.byref(c), ctx._ptr(sigmas), ctx._ptr(constants),
                                        ctx._ptr(lookup["tables"]) if lookup else None, ctypes.byref(h)))
@@ -540,8 +548,13 @@ class NativeSetup:
 
     def get_cap(self):
         out = np.zeros((self.cap_size, 4), np.uint64)
-        assert lib.bj_setup_get_cap(self._h, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        _ok(lib.bj_setup_get_cap(self._h, out.ctypes.data_as(ctypes.c_void_p)))
         return out
+
+    def vk(self):
+        """verification-key dict of this setup (same shape as prover.Setup.vk())"""
+        from .prover import verification_key
+        return verification_key(*self._vk_args, self.get_cap())
 
     def prove(self, variables, multiplicities=None, timings=None, as_json=False):
         """bj_prove -> the proof as a dict in the reference's serde shape (or the JSON text)."""
@@ -550,12 +563,12 @@ class NativeSetup:
                                      self.ctx._ptr(multiplicities) if multiplicities is not None else None, ctypes.byref(h)))
         try:
             need = ctypes.c_size_t()
-            assert lib.bj_proof_to_json(h, None, 0, ctypes.byref(need)) == 0
+            _ok(lib.bj_proof_to_json(h, None, 0, ctypes.byref(need)))
             buf = ctypes.create_string_buffer(need.value)
-            assert lib.bj_proof_to_json(h, buf, need.value, ctypes.byref(need)) == 0
+            _ok(lib.bj_proof_to_json(h, buf, need.value, ctypes.byref(need)))
             if timings is not None:
                 st = (ctypes.c_double * 6)()
-                assert lib.bj_proof_stage_seconds(h, st) == 0
+                _ok(lib.bj_proof_stage_seconds(h, st))
                 for k, v in zip(("1_witness_lde_commit", "2_stage2_products_lde_commit", "3_quotient", "4_openings", "5_deep_fri", "6_queries"), st):
                     timings[k] = float(v)
         finally:

@@ -117,6 +117,7 @@ using namespace bj;
 
 extern "C" int32_t bj_merkle_build_blake2s(bj_ctx* ctx, const uint64_t* const* h_sources, uint32_t n_sources, uint64_t n_leaves,
                                            uint32_t elems_per_leaf, uint32_t cap_size, uint64_t* d_leaf_hashes, uint64_t* d_nodes) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_sources || !d_leaf_hashes || n_sources == 0 || n_leaves == 0)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_merkle_build_blake2s: bad argument");
   if ((n_leaves & (n_leaves - 1)) || (cap_size & (cap_size - 1)) || cap_size == 0 || cap_size > n_leaves ||
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) blake2s_pow_kernel(const u32* __restrict_
 }  // namespace bj
 
 extern "C" int32_t bj_pow_blake2s(bj_ctx* ctx, const uint8_t* h_seed, uint32_t seed_len, uint32_t pow_bits, uint64_t* h_challenge) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || (!h_seed && seed_len) || !h_challenge || pow_bits > 32 || seed_len > 52)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_pow_blake2s: bad argument (pow_bits <= 32, seed <= 52 bytes)");
   u32 words[16] = {0};

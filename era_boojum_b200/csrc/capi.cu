@@ -59,16 +59,23 @@ using namespace bj;
 extern "C" {
 
 int32_t bj_selftest_field(bj_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* h_mismatches) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_mismatches) return BJ_ERR_INVALID_ARG;
-  unsigned long long* d = nullptr;
-  BJ_CUDA(ctx, cudaMalloc(&d, sizeof(unsigned long long)));
-  BJ_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
-  field_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, seed, d);
+  *h_mismatches = 0;
+  if (n == 0) return BJ_OK;
+  struct Counter {  // freed on every exit path
+    unsigned long long* d = nullptr;
+    ~Counter() {
+      if (d) cudaFree(d);
+    }
+  } c;
+  BJ_CUDA(ctx, cudaMalloc(&c.d, sizeof(unsigned long long)));
+  BJ_CUDA(ctx, cudaMemsetAsync(c.d, 0, sizeof(unsigned long long), ctx->stream));
+  field_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, seed, c.d);
   BJ_LAUNCH_CHECK(ctx);
   unsigned long long h = 0;
-  BJ_CUDA(ctx, cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  BJ_CUDA(ctx, cudaMemcpyAsync(&h, c.d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  cudaFree(d);
   *h_mismatches = h;
   return BJ_OK;
 }
@@ -101,9 +108,17 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
     return BJ_ERR_NO_DEVICE;
   }
   if (device < 0 || device >= count) return BJ_ERR_INVALID_ARG;
-  if (cudaSetDevice(device) != cudaSuccess) return BJ_ERR_CUDA;
   bj_ctx* ctx = new bj_ctx();
   ctx->device = device;
+  bj::DeviceGuard device_guard(ctx);  // the caller's current device is restored on return
+  {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) {
+      cudaGetLastError();
+      delete ctx;
+      return BJ_ERR_CUDA;
+    }
+  }
   ctx->stream = (cudaStream_t)stream;  // NULL == the CUDA legacy default stream (what torch uses by default)
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -132,6 +147,7 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
   }
   int32_t st = poseidon2_init_constants(ctx);
   if (st != BJ_OK) {
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
     return st;
   }
@@ -141,7 +157,7 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
 
 int32_t bj_ctx_destroy(bj_ctx* ctx) {
   if (!ctx) return BJ_OK;
-  cudaSetDevice(ctx->device);
+  bj::DeviceGuard device_guard(ctx);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->tw_fwd) cudaFree(ctx->tw_fwd);
   if (ctx->tw_inv) cudaFree(ctx->tw_inv);
@@ -169,6 +185,7 @@ int32_t bj_ctx_destroy(bj_ctx* ctx) {
 }
 
 int32_t bj_ctx_set_stream(bj_ctx* ctx, void* stream) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx) return BJ_ERR_INVALID_ARG;
   BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->stream = (cudaStream_t)stream;
@@ -176,6 +193,7 @@ int32_t bj_ctx_set_stream(bj_ctx* ctx, void* stream) {
 }
 
 int32_t bj_ctx_set_coset_shard(bj_ctx* ctx, uint32_t rank, uint32_t world, uint32_t log_lde) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx) return BJ_ERR_INVALID_ARG;
   if (world == 0 || (world & (world - 1)) || rank >= world || log_lde > 16 || world > (1u << log_lde))
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_ctx_set_coset_shard: world must be a power of two <= the LDE factor and rank < world");
@@ -188,6 +206,7 @@ int32_t bj_ctx_set_coset_shard(bj_ctx* ctx, uint32_t rank, uint32_t world, uint3
 }
 
 int32_t bj_ctx_synchronize(bj_ctx* ctx) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx) return BJ_ERR_INVALID_ARG;
   BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return BJ_OK;
@@ -197,6 +216,7 @@ const char* bj_last_error(const bj_ctx* ctx) { return ctx ? ctx->last_error.c_st
 uint64_t bj_launch_count(const bj_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int32_t bj_alloc(bj_ctx* ctx, size_t bytes, void** d_ptr) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_ptr) return BJ_ERR_INVALID_ARG;
   cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
   if (e != cudaSuccess) {
@@ -207,6 +227,7 @@ int32_t bj_alloc(bj_ctx* ctx, size_t bytes, void** d_ptr) {
   return BJ_OK;
 }
 int32_t bj_free(bj_ctx* ctx, void* d_ptr) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx) return BJ_ERR_INVALID_ARG;
   if (!d_ptr) return BJ_OK;
   BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -214,11 +235,13 @@ int32_t bj_free(bj_ctx* ctx, void* d_ptr) {
   return BJ_OK;
 }
 int32_t bj_upload(bj_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || (!d_dst && bytes) || (!h_src && bytes)) return BJ_ERR_INVALID_ARG;
   BJ_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return BJ_OK;
 }
 int32_t bj_download(bj_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || (!h_dst && bytes) || (!d_src && bytes)) return BJ_ERR_INVALID_ARG;
   BJ_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return BJ_OK;

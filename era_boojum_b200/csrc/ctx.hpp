@@ -113,6 +113,25 @@ struct bj_ctx {
   } while (0)
 
 namespace bj {
+// Every extern "C" entry that takes a context runs on THAT context's device whatever the caller's current device is (a
+// process may hold contexts on several GPUs, or switch devices between calls); the caller's current device is restored.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const bj_ctx* ctx) {
+    if (!ctx) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+    if (prev != ctx->device) switched = cudaSetDevice(ctx->device) == cudaSuccess && prev >= 0;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 int32_t ensure_scratch(bj_ctx* ctx, size_t bytes);
 int32_t ensure_twiddles(bj_ctx* ctx, int log_n);
 int32_t param_upload(bj_ctx* ctx, const void* host, size_t bytes, void** d_out);

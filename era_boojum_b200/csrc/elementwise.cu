@@ -218,8 +218,12 @@ __global__ void __launch_bounds__(256) deep_group_kernel(const DeepParams p) {
 
 // small parameter arena on the device (pointer tables, challenge vectors): bump allocation, sync on wrap
 int32_t param_upload(bj_ctx* ctx, const void* host, size_t bytes, void** d_out) {
-  const size_t ARENA = 1 << 20;
-  if (bytes > ARENA / 2) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "parameter block too large");
+  // Bump arena for the small parameter blocks of a call (pointer tables, challenge lists, gate programs).  A wrap restarts at
+  // offset 0 after the stream has drained; blocks are capped at ARENA / 32 and no entry point uploads more than 16 blocks, so
+  // the blocks a call places after a wrap (<= ARENA / 2 from the start) cannot reach the ones it placed before it (which lie
+  // in the upper half: the wrap happened because the arena was full).
+  const size_t ARENA = 8 << 20;
+  if (bytes > ARENA / 32) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "parameter block too large (256 KiB limit)");
   if (!ctx->param_arena) {
     BJ_CUDA(ctx, cudaMalloc(&ctx->param_arena, ARENA));
     ctx->param_off = 0;
@@ -243,6 +247,7 @@ using namespace bj;
 extern "C" {
 
 int32_t bj_batch_inverse(bj_ctx* ctx, uint64_t* d_data, uint64_t n) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || (!d_data && n)) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_batch_inverse: bad argument");
   if (n == 0) return BJ_OK;
   const u64 threads = (n + BI_K - 1) / BI_K;
@@ -252,6 +257,7 @@ int32_t bj_batch_inverse(bj_ctx* ctx, uint64_t* d_data, uint64_t n) {
 }
 
 int32_t bj_batch_inverse_ext(bj_ctx* ctx, uint64_t* d_c0, uint64_t* d_c1, uint64_t n) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || ((!d_c0 || !d_c1) && n)) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_batch_inverse_ext: bad argument");
   if (n == 0) return BJ_OK;
   const u64 threads = (n + BI_K - 1) / BI_K;
@@ -263,6 +269,7 @@ int32_t bj_batch_inverse_ext(bj_ctx* ctx, uint64_t* d_c0, uint64_t* d_c1, uint64
 int32_t bj_deep_quotient_group(bj_ctx* ctx, const uint64_t* const* h_src_c0, const uint64_t* const* h_src_c1,
                                uint32_t n_src, const uint64_t* h_values_at, const uint64_t* h_challenges,
                                const uint64_t h_at[2], uint32_t log_rows, uint64_t* d_acc_c0, uint64_t* d_acc_c1) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_src_c0 || !h_src_c1 || !h_values_at || !h_challenges || !h_at || !d_acc_c0 || !d_acc_c1 || n_src == 0 ||
       log_rows < 1 || log_rows > 32)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_deep_quotient_group: bad argument");

@@ -60,6 +60,7 @@ using namespace bj;
 extern "C" int32_t bj_fri_fold(bj_ctx* ctx, const uint64_t* d_c0, const uint64_t* d_c1, uint32_t log_m,
                                uint32_t log_fold, const uint64_t h_alpha[2], uint64_t* h_coset_inv_io,
                                uint64_t* d_out_c0, uint64_t* d_out_c1) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_c0 || !d_c1 || !h_alpha || !h_coset_inv_io || !d_out_c0 || !d_out_c1)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_fri_fold: NULL argument");
   if (log_fold < 1 || log_fold > 3 || log_fold > log_m || log_m > 32)

@@ -88,10 +88,15 @@ using namespace bj;
 extern "C" {
 
 int32_t bj_query_leaf_elements(bj_ctx* ctx, const uint64_t* const* h_sources, uint32_t n_sources, uint32_t elems_per_leaf,
-                               const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out) {
+                               uint64_t n_leaves, const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_sources || !h_indices || !h_out || n_sources == 0 || elems_per_leaf == 0)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_query_leaf_elements: bad argument");
   if (n_indices == 0) return BJ_OK;
+  for (uint32_t i = 0; i < n_indices; i++)
+    if (h_indices[i] >= n_leaves) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_query_leaf_elements: leaf index out of range");
+  for (uint32_t i = 0; i < n_sources; i++)
+    if (!h_sources[i]) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_query_leaf_elements: NULL source column");
   void *d_src, *d_idx;
   BJ_TRY(param_upload(ctx, h_sources, sizeof(u64*) * n_sources, &d_src));
   BJ_TRY(param_upload(ctx, h_indices, sizeof(u64) * n_indices, &d_idx));
@@ -108,10 +113,13 @@ int32_t bj_query_leaf_elements(bj_ctx* ctx, const uint64_t* const* h_sources, ui
 
 int32_t bj_merkle_paths(bj_ctx* ctx, const uint64_t* d_leaf_hashes, const uint64_t* d_nodes, uint64_t n_leaves,
                         uint32_t cap_size, const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_leaf_hashes || !h_indices || (!h_out && n_indices) || cap_size == 0 || n_leaves < cap_size)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_merkle_paths: bad argument");
   u32 depth = 0;
   while ((n_leaves >> depth) > cap_size) depth++;
+  for (uint32_t i = 0; i < n_indices; i++)
+    if (h_indices[i] >= n_leaves) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_merkle_paths: leaf index out of range");
   if (n_indices == 0 || depth == 0) return BJ_OK;
   if (!d_nodes) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_merkle_paths: d_nodes is NULL");
   void* d_idx;
@@ -129,6 +137,7 @@ int32_t bj_merkle_paths(bj_ctx* ctx, const uint64_t* d_leaf_hashes, const uint64
 
 void bj_fri_oracles_free(bj_fri_oracles* o) {
   if (!o) return;
+  bj::DeviceGuard device_guard(o->ctx);
   if (o->ctx) cudaStreamSynchronize(o->ctx->stream);
   delete o;
 }
@@ -136,12 +145,14 @@ void bj_fri_oracles_free(bj_fri_oracles* o) {
 int32_t bj_do_fri(bj_ctx* ctx, bj_transcript* transcript, const uint64_t* d_c0, const uint64_t* d_c1, uint32_t log_full_size,
                   const uint32_t* schedule, uint32_t n_schedule, uint32_t log_lde, uint32_t cap_size,
                   bj_fri_oracles** out) {
+  bj::DeviceGuard device_guard(ctx);
   return bj_do_fri_with_hasher(ctx, transcript, d_c0, d_c1, log_full_size, schedule, n_schedule, log_lde, cap_size, BJ_HASHER_POSEIDON2, out);
 }
 
 int32_t bj_do_fri_with_hasher(bj_ctx* ctx, bj_transcript* transcript, const uint64_t* d_c0, const uint64_t* d_c1, uint32_t log_full_size,
                               const uint32_t* schedule, uint32_t n_schedule, uint32_t log_lde, uint32_t cap_size, uint32_t hasher,
                               bj_fri_oracles** out) {
+  bj::DeviceGuard device_guard(ctx);
   if (hasher > BJ_HASHER_KECCAK256) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_do_fri: unknown tree hasher");
   if (!ctx || !transcript || !d_c0 || !d_c1 || !schedule || n_schedule == 0 || !out || cap_size == 0 ||
       (cap_size & (cap_size - 1)) || log_full_size > 32 || log_lde > log_full_size)
@@ -259,11 +270,12 @@ int32_t bj_fri_oracles_query(bj_fri_oracles* o, uint32_t oracle_idx, uint64_t le
                              uint64_t* h_path, uint32_t* path_len) {
   if (!o || oracle_idx >= o->levels.size() || !h_leaf_elements || !h_path || !path_len) return BJ_ERR_INVALID_ARG;
   bj_ctx* ctx = o->ctx;
+  bj::DeviceGuard device_guard(ctx);
   const FriLevel& lv = o->levels[oracle_idx];
   const u64 n_leaves = 1ull << (lv.log_size - lv.log_fold);
   if (leaf_index >= n_leaves) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_fri_oracles_query: leaf index out of range");
   const uint64_t* srcs[2] = {(const uint64_t*)lv.c0, (const uint64_t*)lv.c1};
-  BJ_TRY(bj_query_leaf_elements(ctx, srcs, 2, 1u << lv.log_fold, &leaf_index, 1, h_leaf_elements));
+  BJ_TRY(bj_query_leaf_elements(ctx, srcs, 2, 1u << lv.log_fold, n_leaves, &leaf_index, 1, h_leaf_elements));
   u32 depth = 0;
   while ((n_leaves >> depth) > o->cap_size) depth++;
   *path_len = depth;

@@ -130,6 +130,7 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
                                                      const uint64_t* const* h_constant_cols, uint32_t n_constants,
                                                      const uint64_t* h_alpha_powers, uint32_t n_alpha_powers,
                                                      uint64_t n_points, uint64_t* d_q_c0, uint64_t* d_q_c1) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_gates || n_gates == 0 || !d_q_c0 || !d_q_c1 || n_points == 0 || (!h_alpha_powers && n_alpha_powers))
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_quotient_gates_general_purpose: bad argument");
   std::vector<DevGate> gates;

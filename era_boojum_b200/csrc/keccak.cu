@@ -69,6 +69,7 @@ extern "C" {
 
 int32_t bj_merkle_build_keccak256(bj_ctx* ctx, const uint64_t* const* h_sources, uint32_t n_sources, uint64_t n_leaves,
                                   uint32_t elems_per_leaf, uint32_t cap_size, uint64_t* d_leaf_hashes, uint64_t* d_nodes) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_sources || !d_leaf_hashes || n_sources == 0 || n_leaves == 0)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_merkle_build_keccak256: bad argument");
   if ((n_leaves & (n_leaves - 1)) || (cap_size & (cap_size - 1)) || cap_size == 0 || cap_size > n_leaves ||

@@ -129,6 +129,7 @@ int32_t bj_lookup_polys_specialized(bj_ctx* ctx, const uint64_t* const* h_lookup
                                     const uint64_t* d_table_id_col, const uint64_t* const* h_table_cols, uint32_t n_table_cols,
                                     const uint64_t* d_multiplicity, const uint64_t h_beta[2], const uint64_t h_gamma[2],
                                     uint32_t log_n, uint64_t* d_out) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_lookup_cols || !h_table_cols || !d_multiplicity || !h_beta || !h_gamma || !d_out || log_n > 32)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_lookup_polys_specialized: bad argument");
   LookupParams p{};
@@ -146,6 +147,7 @@ int32_t bj_quotient_lookup_specialized(bj_ctx* ctx, const uint64_t* const* h_loo
                                        const uint64_t* d_multiplicity_lde, const uint64_t* const* h_a_ldes, const uint64_t* d_b_c0,
                                        const uint64_t* d_b_c1, const uint64_t h_beta[2], const uint64_t h_gamma[2],
                                        const uint64_t* h_alphas, uint64_t n_points, uint64_t* d_q_c0, uint64_t* d_q_c1) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_lookup_ldes || !h_table_ldes || !d_multiplicity_lde || !h_a_ldes || !d_b_c0 || !d_b_c1 || !h_beta || !h_gamma ||
       !h_alphas || !d_q_c0 || !d_q_c1 || n_points == 0)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_quotient_lookup_specialized: bad argument");

@@ -513,6 +513,7 @@ using namespace bj;
 extern "C" {
 
 int32_t bj_twiddles(bj_ctx* ctx, uint32_t log_n, int32_t inverse, uint64_t* d_out) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_out || log_n < 1 || log_n > 32) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_twiddles: bad argument");
   BJ_TRY(ensure_twiddles(ctx, (int)log_n));
   BJ_CUDA(ctx, cudaMemcpyAsync(d_out, inverse ? ctx->tw_inv : ctx->tw_fwd, sizeof(u64) << (log_n - 1),
@@ -522,6 +523,7 @@ int32_t bj_twiddles(bj_ctx* ctx, uint32_t log_n, int32_t inverse, uint64_t* d_ou
 
 int32_t bj_ntt_natural_to_bitreversed(bj_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint32_t n_cols,
                                       uint64_t col_stride, uint64_t coset) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_data || log_n > 32 || col_stride < (1ull << log_n))
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_ntt_natural_to_bitreversed: bad argument");
   if (n_cols == 0) return BJ_OK;
@@ -531,6 +533,7 @@ int32_t bj_ntt_natural_to_bitreversed(bj_ctx* ctx, uint64_t* d_data, uint32_t lo
 
 int32_t bj_intt_natural_to_natural(bj_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint32_t n_cols,
                                    uint64_t col_stride, uint64_t coset) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_data || log_n > 32 || col_stride < (1ull << log_n))
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_intt_natural_to_natural: bad argument");
   if (n_cols == 0) return BJ_OK;
@@ -551,6 +554,7 @@ int32_t bj_intt_natural_to_natural(bj_ctx* ctx, uint64_t* d_data, uint32_t log_n
 }
 
 int32_t bj_bitreverse(bj_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint32_t n_cols, uint64_t col_stride) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_data || log_n > 40) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_bitreverse: bad argument");
   if (n_cols == 0 || log_n == 0) return BJ_OK;
   const u64 n = 1ull << log_n;
@@ -562,6 +566,7 @@ int32_t bj_bitreverse(bj_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint32_t n_
 
 int32_t bj_lde(bj_ctx* ctx, const uint64_t* d_in, uint64_t in_col_stride, uint64_t* d_out, uint32_t log_n,
                uint32_t log_lde, uint32_t n_cols, int32_t from_monomials) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_in || !d_out || log_n + log_lde > 32 || in_col_stride < (1ull << log_n))
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_lde: bad argument");
   if (n_cols == 0) return BJ_OK;
@@ -670,11 +675,13 @@ static int32_t host_pipeline(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint
 
 int32_t bj_ntt_natural_to_bitreversed_host(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint32_t n_cols,
                                            uint64_t coset) {
+  bj::DeviceGuard device_guard(ctx);
   return host_pipeline(ctx, h_data, log_n, n_cols, coset, false);
 }
 
 int32_t bj_intt_natural_to_natural_host(bj_ctx* ctx, uint64_t* h_data, uint32_t log_n, uint32_t n_cols,
                                         uint64_t coset) {
+  bj::DeviceGuard device_guard(ctx);
   if (ctx && gl::canon(coset) == 0) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "coset must be invertible");
   return host_pipeline(ctx, h_data, log_n, n_cols, coset, true);
 }

@@ -82,6 +82,7 @@ using namespace bj;
 
 extern "C" int32_t bj_barycentric_evaluate(bj_ctx* ctx, const uint64_t* const* h_cols, uint32_t n_cols, uint32_t log_n,
                                            const uint64_t h_at[2], uint64_t* h_out) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_cols || !h_at || !h_out || n_cols == 0 || log_n > 32)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_barycentric_evaluate: bad argument");
   if (ctx->shard.first != 0) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_barycentric_evaluate: coset 0 belongs to shard rank 0");

@@ -119,6 +119,7 @@ extern "C" {
 int32_t bj_merkle_build_poseidon2(bj_ctx* ctx, const uint64_t* const* h_sources, uint32_t n_sources,
                                   uint64_t n_leaves, uint32_t elems_per_leaf, uint32_t cap_size,
                                   uint64_t* d_leaf_hashes, uint64_t* d_nodes) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_sources || !d_leaf_hashes || n_sources == 0 || n_leaves == 0)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_merkle_build_poseidon2: bad argument");
   if ((n_leaves & (n_leaves - 1)) || (cap_size & (cap_size - 1)) || cap_size == 0 || cap_size > n_leaves ||
@@ -138,6 +139,7 @@ int32_t bj_merkle_build_poseidon2(bj_ctx* ctx, const uint64_t* const* h_sources,
 
 int32_t bj_poseidon2_hash_rows(bj_ctx* ctx, const uint64_t* d_rows, uint64_t n_rows, uint32_t row_len,
                                uint64_t* d_digests) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_rows || !d_digests) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_poseidon2_hash_rows: bad argument");
   if (n_rows == 0) return BJ_OK;
   poseidon2_rows_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, ctx->stream>>>((const u64*)d_rows, n_rows, row_len,
@@ -147,6 +149,7 @@ int32_t bj_poseidon2_hash_rows(bj_ctx* ctx, const uint64_t* d_rows, uint64_t n_r
 }
 
 int32_t bj_poseidon2_permute(bj_ctx* ctx, uint64_t* d_states, uint64_t n_states) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_states) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_poseidon2_permute: bad argument");
   if (n_states == 0) return BJ_OK;
   poseidon2_permute_kernel<<<(unsigned)((n_states + 127) / 128), 128, 0, ctx->stream>>>((u64*)d_states, n_states);

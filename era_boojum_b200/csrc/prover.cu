@@ -83,11 +83,22 @@ static void json_u64_list(std::string& s, const u64* v, size_t n) {
   }
   s += ']';
 }
-static void json_digests(std::string& s, const u64* v, size_t n_digests) {
+// TreeHasher::Output in serde form: Poseidon2 digests are [GoldilocksField; 4] = 4 numbers; Blake2s256 / Keccak256 digests are
+// [u8; 32] = 32 numbers (src/cs/oracle/mod.rs:180, 245).  Internally every digest is kept as 4 little-endian u64.
+static void json_digests(std::string& s, const u64* v, size_t n_digests, bool as_bytes) {
   s += '[';
   for (size_t i = 0; i < n_digests; i++) {
     if (i) s += ',';
-    json_u64_list(s, v + 4 * i, 4);
+    if (!as_bytes) {
+      json_u64_list(s, v + 4 * i, 4);
+      continue;
+    }
+    s += '[';
+    for (int b = 0; b < 32; b++) {
+      if (b) s += ',';
+      s += std::to_string((unsigned)((v[4 * i + b / 8] >> (8 * (b % 8))) & 0xff));
+    }
+    s += ']';
   }
   s += ']';
 }
@@ -147,6 +158,7 @@ extern "C" {
 
 int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* d_sigmas, const uint64_t* d_constants,
                         const uint64_t* d_lookup_tables, bj_setup** out) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !circuit || !d_sigmas || !out || circuit->num_variables == 0 || circuit->log_n == 0 || circuit->log_n > 28 ||
       !is_pow2(circuit->fri_lde_factor) || !is_pow2(circuit->merkle_tree_cap_size) || !is_pow2(circuit->quotient_degree) ||
       circuit->quotient_degree > circuit->fri_lde_factor || (circuit->num_constants && !d_constants) ||
@@ -158,6 +170,18 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_setup_create: inconsistent lookup description");
   if (ctx->shard.log_stride) BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "bj_setup_create: coset-sharded contexts are driven from the host language");
   *out = nullptr;
+  {
+    // a proof needs at least one FRI folding step (the JSON has a fri_base_oracle_cap): reject circuits so small that
+    // compute_fri_schedule (prover.rs:2281-2372) returns an empty schedule for this cap size, instead of failing inside bj_prove
+    uint32_t log_l = 0, new_pow = 0, nq = 0, sched[32], sched_len = 0, fd = 0;
+    while ((1u << log_l) < circuit->fri_lde_factor) log_l++;
+    if (log_l == 0) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_setup_create: fri_lde_factor must be at least 2");
+    BJ_TRY(bj_compute_fri_schedule(circuit->security_level, circuit->merkle_tree_cap_size, circuit->pow_bits, log_l, circuit->log_n, &new_pow, &nq,
+                                   sched, &sched_len, &fd));
+    if (sched_len == 0)
+      BJ_FAIL(ctx, BJ_ERR_INVALID_ARG,
+              "bj_setup_create: degenerate instance - 2^log_n * fri_lde_factor is too small for merkle_tree_cap_size (empty FRI schedule)");
+  }
   std::unique_ptr<bj_setup> s(new bj_setup());
   s->ctx = ctx;
   s->c = *circuit;
@@ -205,6 +229,7 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
 
 void bj_setup_free(bj_setup* s) {
   if (!s) return;
+  bj::DeviceGuard device_guard(s->ctx);
   if (s->ctx) cudaStreamSynchronize(s->ctx->stream);
   delete s;
 }
@@ -216,6 +241,7 @@ int32_t bj_setup_get_cap(const bj_setup* s, uint64_t* h_cap) {
 }
 
 int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables, const uint64_t* d_multiplicities, bj_proof** out) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !setup || !d_variables || !out || setup->ctx != ctx) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_prove: bad argument");
   const bj_circuit& c = setup->c;
   const bool lk = c.lookup_width != 0;
@@ -560,7 +586,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     uint32_t depth = 0;
     while ((o->n_leaves >> depth) > o->cap_size) depth++;
     std::vector<uint64_t> rows((size_t)num_queries * row_len), paths((size_t)num_queries * (depth ? depth : 1) * 4);
-    BJ_TRY(bj_query_leaf_elements(ctx, o->cols.data(), (uint32_t)row_len, 1, idxs.data(), num_queries, rows.data()));
+    BJ_TRY(bj_query_leaf_elements(ctx, o->cols.data(), (uint32_t)row_len, 1, o->n_leaves, idxs.data(), num_queries, rows.data()));
     BJ_TRY(bj_merkle_paths(ctx, (const uint64_t*)o->leaf_hashes.p, (const uint64_t*)o->nodes.p, o->n_leaves, o->cap_size, idxs.data(), num_queries,
                            paths.data()));
     for (uint32_t q = 0; q < num_queries; q++) {
@@ -589,16 +615,17 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   // ---- serde_json shape of Proof (proof.rs:57-143) ----
   std::string& s = pf->json;
   s.reserve(1 << 20);
+  const bool digest_bytes = c.tree_hasher != BJ_HASHER_POSEIDON2;
   s += "{\"proof_config\":{\"fri_lde_factor\":" + std::to_string(L) + ",\"merkle_tree_cap_size\":" + std::to_string(cap) +
        ",\"fri_folding_schedule\":null,\"security_level\":" + std::to_string(c.security_level) + ",\"pow_bits\":" + std::to_string(c.pow_bits) +
        "},\"public_inputs\":";
   json_u64_list(s, pf->public_inputs.data(), pf->public_inputs.size());
   s += ",\"witness_oracle_cap\":";
-  json_digests(s, pf->witness_cap.data(), cap);
+  json_digests(s, pf->witness_cap.data(), cap, digest_bytes);
   s += ",\"stage_2_oracle_cap\":";
-  json_digests(s, pf->stage2_cap.data(), cap);
+  json_digests(s, pf->stage2_cap.data(), cap, digest_bytes);
   s += ",\"quotient_oracle_cap\":";
-  json_digests(s, pf->quotient_cap.data(), cap);
+  json_digests(s, pf->quotient_cap.data(), cap, digest_bytes);
   s += ",\"final_fri_monomials\":[";
   json_u64_list(s, pf->mono_c0.data(), pf->mono_c0.size());
   s += ',';
@@ -610,11 +637,11 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   s += ",\"values_at_0\":";
   json_ext_list(s, pf->values_at_0);
   s += ",\"fri_base_oracle_cap\":";
-  json_digests(s, pf->fri_caps[0].data(), cap);
+  json_digests(s, pf->fri_caps[0].data(), cap, digest_bytes);
   s += ",\"fri_intermediate_oracles_caps\":[";
   for (uint32_t i = 1; i < n_fri; i++) {
     if (i > 1) s += ',';
-    json_digests(s, pf->fri_caps[i].data(), cap);
+    json_digests(s, pf->fri_caps[i].data(), cap, digest_bytes);
   }
   s += "],\"queries_per_fri_repetition\":[";
   static const char* names[4] = {"witness_query", "stage_2_query", "quotient_query", "setup_query"};
@@ -622,7 +649,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     s += "{\"leaf_elements\":";
     json_u64_list(s, a.leaf_elements.data(), a.leaf_elements.size());
     s += ",\"proof\":";
-    json_digests(s, a.path.data(), a.path.size() / 4);
+    json_digests(s, a.path.data(), a.path.size() / 4, digest_bytes);
     s += '}';
   };
   for (uint32_t q = 0; q < num_queries; q++) {

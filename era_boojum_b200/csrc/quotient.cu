@@ -119,6 +119,7 @@ int32_t bj_quotient_copy_permutation(bj_ctx* ctx, const uint64_t* const* h_varia
                                      const uint64_t* d_z_c1, const uint64_t* const* h_partial_ldes, const uint64_t h_beta[2],
                                      const uint64_t h_gamma[2], const uint64_t* h_alphas, uint32_t log_n, uint32_t log_lde,
                                      uint32_t log_quotient_degree, uint32_t chunk_size, uint64_t* d_q_c0, uint64_t* d_q_c1) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_variable_ldes || !h_sigma_ldes || !h_non_residues || !d_z_c0 || !d_z_c1 || !h_beta || !h_gamma || !h_alphas ||
       !d_q_c0 || !d_q_c1 || n_cols == 0 || chunk_size == 0 || log_quotient_degree > log_lde || log_n + log_lde > 32)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_quotient_copy_permutation: bad argument");
@@ -168,6 +169,7 @@ int32_t bj_quotient_copy_permutation(bj_ctx* ctx, const uint64_t* const* h_varia
 
 int32_t bj_quotient_divide_by_vanishing(bj_ctx* ctx, uint64_t* d_q_c0, uint64_t* d_q_c1, uint32_t log_n,
                                         uint32_t log_quotient_degree) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_q_c0 || !d_q_c1 || log_n + log_quotient_degree > 32)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_quotient_divide_by_vanishing: bad argument");
   std::vector<u64> van;

@@ -93,6 +93,7 @@ extern "C" {
 
 int32_t bj_materialize_columns(bj_ctx* ctx, const uint64_t* d_all_values, uint64_t n_values, const uint64_t* d_hint, uint32_t n_cols,
                                uint64_t hint_rows, uint32_t log_n, uint64_t* d_out) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_all_values || !d_hint || !d_out || n_cols == 0 || log_n > 32 || hint_rows > (1ull << log_n))
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_materialize_columns: bad argument");
   const u64 n = 1ull << log_n, total = n * n_cols;
@@ -111,6 +112,7 @@ int32_t bj_materialize_columns(bj_ctx* ctx, const uint64_t* d_all_values, uint64
 }
 
 int32_t bj_create_permutation_polys(bj_ctx* ctx, const uint64_t* d_placement, uint32_t n_cols, uint32_t log_n, uint64_t* d_sigmas) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !d_placement || !d_sigmas || n_cols == 0 || log_n > 32 || ((u64)n_cols << log_n) >= (1ull << 31))
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_create_permutation_polys: bad argument (at most 2^31 - 1 cells)");
   const u64 n = 1ull << log_n, n_cells = n * n_cols;

@@ -226,6 +226,7 @@ int32_t bj_copy_permutation_stage2(bj_ctx* ctx, const uint64_t* const* h_variabl
                                    uint32_t n_cols, const uint64_t* h_non_residues, const uint64_t h_beta[2],
                                    const uint64_t h_gamma[2], uint32_t log_n, uint32_t chunk_size, uint64_t* d_z_c0,
                                    uint64_t* d_z_c1, uint64_t* d_partials) {
+  bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_variable_cols || !h_sigma_cols || !h_non_residues || !h_beta || !h_gamma || !d_z_c0 || !d_z_c1 || n_cols == 0 ||
       chunk_size == 0 || log_n > 32)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_copy_permutation_stage2: bad argument");

@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-from . import Transcript, to_numpy
+from . import BoojumError, Transcript, to_numpy
 from .parallel import LocalComm, assemble_cap, local_leaf_index
 
 P = 0xFFFFFFFF00000001
@@ -30,6 +30,15 @@ def _omega(log_n):
     for _ in range(log_n, 32):
         w = w * w % P
     return w
+
+
+def _digests(arr, hasher):
+    """serde form of TreeHasher::Output values held as rows of 4 little-endian u64: Poseidon2 -> [u64; 4]; Blake2s256 /
+    Keccak256 -> [u8; 32] (src/cs/oracle/mod.rs:180, 245)."""
+    a = np.ascontiguousarray(np.asarray(arr, dtype=np.uint64).reshape(-1, 4))
+    if hasher == "poseidon2":
+        return a.tolist()
+    return a.astype("<u8").view(np.uint8).reshape(-1, 32).tolist()
 
 
 def _ext_dict(v):
@@ -102,17 +111,24 @@ class Setup:
         return self.lde[self.num_variables + self.num_constants + j].reshape(-1)
 
     def vk(self):
-        lk = None
-        if self.lookup:
-            lk = {k: self.lookup[k] for k in ("width", "num_repetitions", "variables_offset", "table_id_column")}
-        return {"lookup": lk, "domain_size": 1 << self.log_n, "num_variables": self.num_variables, "num_constants": self.num_constants,
-                "quotient_degree": self.quotient_degree, "fri_lde_factor": self.config.fri_lde_factor,
-                "cap_size": self.config.merkle_tree_cap_size,
-                "gates": [(g["name"], g["num_repetitions"], list(g["selector_path"]), g.get("variables_initial_offset", 0),
-                           g["constants_placement_offset"]) for g in self.gates],
-                "public_inputs_locations": [list(p) for p in self.public_inputs],
-                "hasher": self.config.hasher, "transcript": self.config.transcript,
-                "setup_merkle_tree_cap": self.cap.tolist()}
+        return verification_key(self.log_n, self.num_variables, self.num_constants, self.gates, self.quotient_degree, self.config,
+                                self.lookup, self.public_inputs, self.cap)
+
+
+def verification_key(log_n, num_variables, num_constants, gates, quotient_degree, config, lookup, public_inputs, cap):
+    """The fixed parameters a verifier needs (VerificationKey, verifier.rs:31-79) for circuits of this driver, plus the setup cap
+    in serde form; shared by the Python Setup and the native bj_setup wrapper."""
+    lk = None
+    if lookup:
+        lk = {k: lookup[k] for k in ("width", "num_repetitions", "variables_offset", "table_id_column")}
+    return {"lookup": lk, "domain_size": 1 << log_n, "num_variables": num_variables, "num_constants": num_constants,
+            "quotient_degree": quotient_degree, "fri_lde_factor": config.fri_lde_factor,
+            "cap_size": config.merkle_tree_cap_size,
+            "gates": [(g["name"], g["num_repetitions"], list(g["selector_path"]), g.get("variables_initial_offset", 0),
+                       g["constants_placement_offset"]) for g in gates],
+            "public_inputs_locations": [list(p) for p in public_inputs],
+            "hasher": config.hasher, "transcript": config.transcript,
+            "setup_merkle_tree_cap": _digests(cap, config.hasher)}
 
 
 def _commit(ctx, comm, cols, L, cap, hasher="poseidon2"):
@@ -340,9 +356,13 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     from .native import lib
     np_, nq, sl, fd = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
     sched = (ctypes.c_uint32 * 32)()
-    assert lib.bj_compute_fri_schedule(cfg.security_level, cap, cfg.pow_bits, log_L, log_n, ctypes.byref(np_), ctypes.byref(nq),
-                                       sched, ctypes.byref(sl), ctypes.byref(fd)) == 0
+    st = lib.bj_compute_fri_schedule(cfg.security_level, cap, cfg.pow_bits, log_L, log_n, ctypes.byref(np_), ctypes.byref(nq),
+                                     sched, ctypes.byref(sl), ctypes.byref(fd))
+    if st != 0:
+        raise BoojumError(st, "bj_compute_fri_schedule: " + lib.bj_status_string(st).decode())
     schedule = list(sched[: sl.value])
+    if not schedule:
+        raise BoojumError(-1, "degenerate FRI instance: log_n + log_lde too small for cap size %d (no folding step)" % cap)
     if comm:
         fri = _ShardedFri(ctx, comm, tr, deep0, deep1, schedule, L, cap, cfg.hasher)
         mono0, mono1 = fri.mono
@@ -370,7 +390,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     rows = {name: (ctx.query_leaf_elements(cols, loc), ctx.merkle_paths(tree, loc)) for name, cols, tree in oracles} if mine else {}
     answered = {}
     for pos, (qi, idx) in enumerate(mine):
-        q = {name: {"leaf_elements": rows[name][0][pos].tolist(), "proof": rows[name][1][pos].tolist()} for name, _, _ in oracles}
+        q = {name: {"leaf_elements": rows[name][0][pos].tolist(), "proof": _digests(rows[name][1][pos], cfg.hasher)} for name, _, _ in oracles}
         fqs, sub, log_len = [], idx, log_n
         for lvl, k in enumerate(schedule):
             if comm:
@@ -380,7 +400,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
                 path = ctx.merkle_paths(tree_l, [leaf])[0]
             else:
                 le, path = fri.query(lvl, sub >> k, k)
-            fqs.append({"leaf_elements": le.tolist(), "proof": path.tolist()})
+            fqs.append({"leaf_elements": le.tolist(), "proof": _digests(path, cfg.hasher)})
             sub >>= k
             log_len -= k
         q["fri_queries"] = fqs
@@ -394,11 +414,12 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     mark("6_queries", t0)
     return {
         "proof_config": cfg.to_dict(), "public_inputs": public_values,
-        "witness_oracle_cap": w_cap.tolist(), "stage_2_oracle_cap": s2_cap.tolist(), "quotient_oracle_cap": qt_cap.tolist(),
+        "witness_oracle_cap": _digests(w_cap, cfg.hasher), "stage_2_oracle_cap": _digests(s2_cap, cfg.hasher),
+        "quotient_oracle_cap": _digests(qt_cap, cfg.hasher),
         "final_fri_monomials": [mono0.tolist(), mono1.tolist()],
         "values_at_z": [_ext_dict(v) for v in values_at_z], "values_at_z_omega": [_ext_dict(v) for v in values_at_z_omega],
         "values_at_0": [_ext_dict(v) for v in values_at_0],
-        "fri_base_oracle_cap": fri_caps[0].tolist(),
-        "fri_intermediate_oracles_caps": [c_.tolist() for c_ in fri_caps[1:]],
+        "fri_base_oracle_cap": _digests(fri_caps[0], cfg.hasher),
+        "fri_intermediate_oracles_caps": [_digests(c_, cfg.hasher) for c_ in fri_caps[1:]],
         "queries_per_fri_repetition": queries, "pow_challenge": pow_challenge, "_marker": None,
     }

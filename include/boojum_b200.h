@@ -316,9 +316,10 @@ BJ_API int32_t bj_fri_oracles_get_challenges(const bj_fri_oracles* o, uint64_t* 
 BJ_API int32_t bj_fri_oracles_query(bj_fri_oracles* o, uint32_t oracle_idx, uint64_t leaf_index, uint64_t* h_leaf_elements,
                              uint64_t* h_path, uint32_t* path_len);
 /* Query helpers for the base oracles (witness / stage 2 / quotient / setup): gather the leaf preimages of n_indices
- * leaves (h_out[q][s * elems_per_leaf + e]) and their Merkle paths (h_out[q][depth][4]); both synchronise. */
+ * leaves (h_out[q][s * elems_per_leaf + e]) and their Merkle paths (h_out[q][depth][4]); both synchronise.  Every source
+ * column holds n_leaves * elems_per_leaf elements; an index >= n_leaves is rejected with BJ_ERR_INVALID_ARG (no launch). */
 BJ_API int32_t bj_query_leaf_elements(bj_ctx* ctx, const uint64_t* const* h_sources, uint32_t n_sources, uint32_t elems_per_leaf,
-                               const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out);
+                               uint64_t n_leaves, const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out);
 BJ_API int32_t bj_merkle_paths(bj_ctx* ctx, const uint64_t* d_leaf_hashes, const uint64_t* d_nodes, uint64_t n_leaves,
                         uint32_t cap_size, const uint64_t* h_indices, uint32_t n_indices, uint64_t* h_out);
 

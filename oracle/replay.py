@@ -210,6 +210,37 @@ def merkle_verify_generic(leaf_hash, path, cap, idx, node_hash):
     return bool(np.array_equal(cur, np.asarray(cap, dtype=np.uint64).reshape(-1, 4)[idx]))
 
 
+def _digest_words(d):
+    """a digest in serde form -> 4 little-endian u64 words: [u64; 4] (Poseidon2) passes through, [u8; 32] (Blake2s256 /
+    Keccak256, src/cs/oracle/mod.rs:180, 245) is packed."""
+    d = [int(x) for x in d]
+    if len(d) == 4:
+        return d
+    assert len(d) == 32 and all(0 <= x < 256 for x in d), "digest must be [u64; 4] or [u8; 32]"
+    return [int.from_bytes(bytes(d[8 * i: 8 * i + 8]), "little") for i in range(4)]
+
+
+def normalize_digests(obj):
+    """Proof / VerificationKey dict in the reference's serde shape -> the same dict with every TreeHasher::Output as 4 u64
+    words (the form the replay code computes with).  Returns a shallow-rebuilt copy; the input is not modified."""
+    out = dict(obj)
+    for k in ("witness_oracle_cap", "stage_2_oracle_cap", "quotient_oracle_cap", "fri_base_oracle_cap", "setup_merkle_tree_cap"):
+        if k in out:
+            out[k] = [_digest_words(d) for d in out[k]]
+    if "fri_intermediate_oracles_caps" in out:
+        out["fri_intermediate_oracles_caps"] = [[_digest_words(d) for d in cap] for cap in out["fri_intermediate_oracles_caps"]]
+    if "queries_per_fri_repetition" in out:
+        def ans(a):
+            return {"leaf_elements": a["leaf_elements"], "proof": [_digest_words(d) for d in a["proof"]]}
+        qs = []
+        for q in out["queries_per_fri_repetition"]:
+            nq = {k: ans(v) for k, v in q.items() if k != "fri_queries"}
+            nq["fri_queries"] = [ans(a) for a in q["fri_queries"]]
+            qs.append(nq)
+        out["queries_per_fri_repetition"] = qs
+    return out
+
+
 def hasher_functions(name):
     """(leaf hash, path verifier) of a tree hasher."""
     if name == "blake2s":

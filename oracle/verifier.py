@@ -54,6 +54,7 @@ GATES = {"fma": (_fma, 4, (4, 0)), "reduction4": (_reduction4, 5, (5, 0)), "cons
 def verify(vk, proof):
     """vk: dict(domain_size, num_variables, num_constants, quotient_degree, gates=[(name, reps, path)], fri_lde_factor,
     cap_size, setup_merkle_tree_cap).  proof: dict in the reference's serde shape.  Returns True or raises AssertionError."""
+    vk, proof = R.normalize_digests(vk), R.normalize_digests(proof)   # Blake2s / Keccak digests arrive as [u8; 32]
     n = vk["domain_size"]
     log_n = n.bit_length() - 1
     L = proof["proof_config"]["fri_lde_factor"]

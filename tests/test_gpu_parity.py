@@ -40,7 +40,7 @@ def test_twiddles_match_reference_table(bj, ctx):
             assert np.array_equal(got[: max(1, (1 << log_n) // 2)], O.twiddles(log_n, inv))
 
 
-@pytest.mark.parametrize("log_n", list(range(0, 17)) + [18, 20])
+@pytest.mark.parametrize("log_n", list(range(0, 22)))
 @pytest.mark.parametrize("coset", [1, 7])
 def test_ntt_forward_matches_oracle(bj, ctx, log_n, coset):
     n_cols = 3 if log_n <= 16 else 2
@@ -50,7 +50,7 @@ def test_ntt_forward_matches_oracle(bj, ctx, log_n, coset):
     assert np.array_equal(bj.to_numpy(d), O.ntt_n2b(a, coset))
 
 
-@pytest.mark.parametrize("log_n", list(range(0, 17)) + [18, 20])
+@pytest.mark.parametrize("log_n", list(range(0, 22)))
 @pytest.mark.parametrize("coset", [1, 7])
 def test_ntt_inverse_matches_oracle(bj, ctx, log_n, coset):
     n_cols = 3 if log_n <= 16 else 2
@@ -114,7 +114,7 @@ def test_ntt_strided_batch(bj, ctx):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("log_n", [22, 24])
+@pytest.mark.parametrize("log_n", [21, 22, 23, 24])
 def test_ntt_full_size_vs_oracle_and_properties(bj, ctx, log_n):
     """BASELINE config 2 sizes: one column compared with the oracle directly, plus linearity and round trip."""
     n = 1 << log_n
@@ -165,6 +165,21 @@ def test_lde_large_first_coset_subset(bj, ctx):
     assert np.array_equal(out8[:, :2, :], out2)
     want = O.lde(a[:1], 3)
     assert np.array_equal(out8[0], want[0])
+
+
+def test_lde_prover_shape_2pow22_factor8_vs_oracle(bj, ctx):
+    """The prover's LDE shape (BASELINE configs[3]/[4]): n = 2^22, L = 8; 8 columns go through bj_lde together (so the
+    batched/fused code path is the one that runs) and one column is compared with the oracle on all 8 cosets."""
+    log_n = 22
+    a = O.random_field(rng(2208), (8, 1 << log_n))
+    d = bj.to_device(a)
+    out = bj.to_numpy(ctx.transform_raw_storages_to_lde(d, 8))
+    want = O.lde(a[5:6], 3)
+    assert np.array_equal(out[5], want[0])
+    # the other columns: cosets are NTTs of the same monomials -> check coset 0 of each column against a forward NTT
+    mono = O.intt_n2n(a[:2])
+    assert np.array_equal(out[0, 0], O.ntt_n2b(mono[0], 7))
+    assert np.array_equal(out[1, 0], O.ntt_n2b(mono[1], 7))
 
 
 # ------------------------------------------------------------------------------------ Poseidon2 / Merkle -----
@@ -714,6 +729,59 @@ def test_quotient_copy_permutation_and_vanishing_match_oracle(bj, ctx):
     # re-multiplying and comparing with the undivided values above.
 
 
+# ------------------------------------------------------------------------------------------- lookup argument -----
+@pytest.mark.parametrize("n_sub,width,with_id", [(1, 1, False), (3, 4, True), (8, 4, True), (2, 3, False)])
+def test_lookup_polys_and_quotient_terms_match_oracle(bj, ctx, n_sub, width, with_id):
+    """bj_lookup_polys_specialized / bj_quotient_lookup_specialized against the Python-int restatement of
+    lookup_argument_in_ext.rs:320-947 and :949-1319 (oracle/lookup.py) on random columns: the formulas are pointwise, so
+    no satisfying assignment is needed for parity (non-canonical inputs included)."""
+    import torch
+    from oracle import lookup as LK
+    log_n, log_lde, log_q = 5, 3, 2
+    n = 1 << log_n
+    r = rng(100 * n_sub + width)
+    n_tab = width + (1 if with_id else 0)
+    cols = r.integers(0, 2**64, size=(n_sub * width, n), dtype=np.uint64)
+    tid = r.integers(0, 2**64, size=n, dtype=np.uint64) if with_id else None
+    tabs = O.random_field(r, (n_tab, n))
+    mult = O.random_field(r, n)
+    beta = tuple(int(x) for x in O.random_field(r, 2))
+    gamma = tuple(int(x) for x in O.random_field(r, 2))
+    d_cols, d_tabs, d_mult = bj.to_device(cols), bj.to_device(tabs), bj.to_device(mult)
+    d_tid = bj.to_device(tid) if with_id else None
+    A, B = ctx.compute_lookup_poly_pairs_specialized([d_cols[i] for i in range(n_sub * width)], width, d_tid,
+                                                     [d_tabs[i] for i in range(n_tab)], d_mult, beta, gamma)
+    wA, wB = LK.lookup_polys(list(cols), width, tid, list(tabs), mult, beta, gamma)
+    for i in range(n_sub):
+        g0, g1 = bj.to_numpy(A[i][0]), bj.to_numpy(A[i][1])
+        assert [(int(a), int(b)) for a, b in zip(g0, g1)] == wA[i], i
+    g0, g1 = bj.to_numpy(B[0]), bj.to_numpy(B[1])
+    assert [(int(a), int(b)) for a, b in zip(g0, g1)] == wB
+
+    # quotient terms on the first Q*n points of LDE columns (the kernel is pointwise: random "LDE" columns suffice)
+    npts = n << log_q
+    full = n << log_lde
+    L_cols = r.integers(0, 2**64, size=(n_sub * width, full), dtype=np.uint64)
+    L_tid = O.random_field(r, full) if with_id else None
+    L_tabs = O.random_field(r, (n_tab, full))
+    L_mult = O.random_field(r, full)
+    L_a = O.random_field(r, (n_sub, 2, full))
+    L_b = O.random_field(r, (2, full))
+    alphas = [tuple(int(x) for x in O.random_field(r, 2)) for _ in range(n_sub + 1)]
+    dc, dt, dm, da, db = (bj.to_device(x) for x in (L_cols, L_tabs, L_mult, L_a, L_b))
+    dtid = bj.to_device(L_tid) if with_id else None
+    init = O.random_field(r, (2, npts))                      # the kernel ACCUMULATES into q
+    dq = bj.to_device(init)
+    ctx.quotient_lookup_specialized([dc[i] for i in range(n_sub * width)], width, dtid, [dt[i] for i in range(n_tab)], dm,
+                                    [(da[i, 0], da[i, 1]) for i in range(n_sub)], (db[0], db[1]), beta, gamma, alphas, dq[0], dq[1])
+    got = bj.to_numpy(dq)
+    for t in list(range(0, npts, 5)) + [npts - 1]:
+        term = LK.quotient_lookup_point(t, list(L_cols), width, L_tid, list(L_tabs), L_mult,
+                                        [(L_a[i, 0], L_a[i, 1]) for i in range(n_sub)], (L_b[0], L_b[1]), beta, gamma, alphas)
+        want = ((int(init[0][t]) + term[0]) % P, (int(init[1][t]) + term[1]) % P)
+        assert (int(got[0][t]), int(got[1][t])) == want, t
+
+
 # ------------------------------------------------------------------------------------------- Blake2s tree -----
 def _blake2s_leaf(vals):
     import hashlib
@@ -818,9 +886,47 @@ def test_c_abi_rejects_misuse_with_status_codes(bj, ctx):
     assert lib.bj_do_fri(h, tr, p, p, 6, sched, 2, 1, 4, ctypes.byref(out)) == INV      # final degree would be zero
     assert lib.bj_do_fri_with_hasher(h, tr, p, p, 6, sched, 1, 1, 4, 7, ctypes.byref(out)) == INV   # unknown hasher
     lib.bj_transcript_free(tr)
+    # query helpers validate leaf indices on the host before any launch (a bad index from a C / Rust caller is a status, not an
+    # out-of-bounds device read)
+    idx = (ctypes.c_uint64 * 2)(3, 64)
+    hout = (ctypes.c_uint64 * 64)()
+    assert lib.bj_query_leaf_elements(h, srcs, 1, 1, 64, idx, 2, hout) == INV          # index 64 of 64 leaves
+    assert lib.bj_query_leaf_elements(h, srcs, 1, 1, 65, idx, 2, hout) == 0
+    assert lib.bj_merkle_paths(h, p, p, 16, 4, idx, 2, hout) == INV                    # index 64 of 16 leaves
+    one = ctypes.c_uint64(0)
+    assert lib.bj_selftest_field(h, 0, 1, ctypes.byref(one)) == 0 and one.value == 0   # n == 0: nothing to do, no launch
     # the context stays usable afterwards
     x = O.random_field(rng(1), (1, 16))
     assert np.array_equal(bj.to_numpy(ctx.fft_natural_to_bitreversed(bj.to_device(x), 1)), O.ntt_n2b(x, 1))
+
+
+def test_entry_points_run_on_the_device_of_their_context(bj):
+    """A context stays bound to its device whatever the caller's current device is (two contexts on two GPUs in one thread
+    when the box has them; otherwise the current device is moved away with a second context on the same GPU), and no entry
+    point leaves the caller's current device changed."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    other = 1 if n_dev > 1 else 0
+    x = O.random_field(rng(9), (2, 1 << 10))
+    want = O.ntt_n2b(x, 7)
+    torch.cuda.set_device(0)
+    c0 = bj.Context(0)
+    torch.cuda.set_device(other)
+    c1 = bj.Context(other)
+    assert torch.cuda.current_device() == other
+    d0, d1 = bj.to_device(x, "cuda:0"), bj.to_device(x, "cuda:%d" % other)
+    c0.fft_natural_to_bitreversed(d0, 7)                  # current device is `other`, the context lives on 0
+    assert torch.cuda.current_device() == other
+    torch.cuda.set_device(0)
+    c1.fft_natural_to_bitreversed(d1, 7)                  # and the other way round
+    tree = c1.merkle_tree_construct([d1[0], d1[1]], 4)
+    assert torch.cuda.current_device() == 0
+    c0.synchronize(), c1.synchronize()
+    assert np.array_equal(bj.to_numpy(d0), want) and np.array_equal(bj.to_numpy(d1), want)
+    lh, _, cap = O.merkle_tree([want[0], want[1]], 4)
+    assert np.array_equal(tree.get_cap(), cap)
+    c0.close(), c1.close()
+    torch.cuda.set_device(0)
 
 
 @pytest.mark.parametrize("n_cols,log_leaves,cap,epl", [(1, 3, 1, 1), (8, 5, 4, 1), (17, 6, 8, 1), (18, 4, 2, 1), (93, 7, 16, 1), (2, 6, 4, 8), (34, 3, 8, 1)])
