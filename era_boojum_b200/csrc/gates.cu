@@ -24,7 +24,9 @@
 
 namespace bj {
 
-constexpr int GATE_MAX_TMP = 96;
+constexpr int GATE_MAX_TMP = 128;            // live temporaries per thread after host-side slot allocation
+constexpr u32 GATE_MAX_PROGRAM_TMP = 1u << 20;  // temporaries a recorded program may name (SSA: one per relation)
+constexpr u32 GATE_OP_PUSH = 7;               // internal: fold operand a into the accumulator with alpha power `dst` of the repetition
 
 struct DevOperand {
   u32 kind;  // bj_gate_index kinds
@@ -38,20 +40,20 @@ struct DevOp {
 };
 struct DevGate {
   u32 ops_begin, n_ops;
-  u32 writes_begin, n_writes;
+  u32 n_writes;                               // quotient terms per repetition
   u32 num_repetitions;
   u32 var_offset, wit_offset, const_offset;  // PerChunkOffset
   u32 var_base, wit_base;                     // first column of repetition 0 (specialised placement; 0 for general purpose)
   u32 const_placement;                        // first constant column of the gate (= selector path length)
   u32 path_len;
   u32 path_bits;  // bit i = path[i]
+  u32 term_base;  // index of the gate's first alpha power
 };
 
 struct GateEvalParams {
   const DevGate* gates;
   u32 n_gates;
   const DevOp* ops;
-  const DevOperand* writes;
   const u64* const* vars;
   const u64* const* wits;
   const u64* const* consts;
@@ -78,13 +80,13 @@ __global__ void __launch_bounds__(128) gate_eval_kernel(const GateEvalParams p) 
   if (t >= p.n_rows) return;
   u64 tmp[GATE_MAX_TMP];
   gl::e2 q = {0, 0};
-  u32 term = 0;
   for (u32 g = 0; g < p.n_gates; g++) {
     const DevGate gate = p.gates[g];
     gl::e2 acc = {0, 0};
     for (u32 rep = 0; rep < gate.num_repetitions; rep++) {
       const u32 vbase = gate.var_base + rep * gate.var_offset, wbase = gate.wit_base + rep * gate.wit_offset;
       const u32 cshared = gate.const_placement, cbase = cshared + rep * gate.const_offset;
+      const u64* alpha_rep = p.alphas + 2 * (size_t)(gate.term_base + rep * gate.n_writes);
       for (u32 i = 0; i < gate.n_ops; i++) {
         const DevOp op = p.ops[gate.ops_begin + i];
         const u64 a = gate_fetch(op.a, tmp, p, t, vbase, wbase, cbase, cshared);
@@ -96,16 +98,15 @@ __global__ void __launch_bounds__(128) gate_eval_kernel(const GateEvalParams p) 
           case BJ_REL_NEGATE: r = gl::neg(a); break;
           case BJ_REL_MUL: r = gl::mul(a, gate_fetch(op.b, tmp, p, t, vbase, wbase, cbase, cshared)); break;
           case BJ_REL_SQUARE: r = gl::sqr(a); break;
-          default: r = gl_inv_chain(gl::canon(a)); break;  // BJ_REL_INVERSE
+          case BJ_REL_INVERSE: r = gl_inv_chain(gl::canon(a)); break;
+          default: {  // GATE_OP_PUSH: push_evaluation_result - the term times its alpha power goes into the gate's accumulator
+            const u64 a0 = __ldg(alpha_rep + 2 * op.dst), a1 = __ldg(alpha_rep + 2 * op.dst + 1);
+            acc.c0 = gl::add(acc.c0, gl::mul(a, a0));
+            acc.c1 = gl::add(acc.c1, gl::mul(a, a1));
+            continue;
+          }
         }
         tmp[op.dst] = r;
-      }
-      for (u32 i = 0; i < gate.n_writes; i++) {
-        const u64 v = gate_fetch(p.writes[gate.writes_begin + i], tmp, p, t, vbase, wbase, cbase, cshared);
-        const u64 a0 = __ldg(p.alphas + 2 * term), a1 = __ldg(p.alphas + 2 * term + 1);
-        acc.c0 = gl::add(acc.c0, gl::mul(v, a0));
-        acc.c1 = gl::add(acc.c1, gl::mul(v, a1));
-        term++;
       }
     }
     u64 sel = 1;
@@ -135,9 +136,9 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_quotient_gates_general_purpose: bad argument");
   std::vector<DevGate> gates;
   std::vector<DevOp> ops;
-  std::vector<DevOperand> writes;
   uint64_t total_terms = 0;
-  auto check_index = [&](const bj_gate_index& ix, const bj_gate_desc& g, uint32_t n_tmp_defined, DevOperand* out) -> bool {
+  // operand range checks against the columns the caller passed (all repetitions)
+  auto check_index = [&](const bj_gate_index& ix, const bj_gate_desc& g, DevOperand* out) -> bool {
     const uint32_t reps = g.num_repetitions ? g.num_repetitions - 1 : 0;
     switch (ix.kind) {
       case BJ_IDX_VARIABLE:
@@ -153,7 +154,7 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
         if (g.constants_placement_offset + ix.value >= n_constants) return false;
         break;
       case BJ_IDX_TEMPORARY:
-        if (ix.value >= GATE_MAX_TMP || ix.value >= n_tmp_defined) return false;
+        if (ix.value >= GATE_MAX_PROGRAM_TMP) return false;
         break;
       case BJ_IDX_CONSTANT_VALUE: break;
       default: return false;
@@ -170,8 +171,6 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
       BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate descriptor: bad selector path or NULL program");
     DevGate d{};
     d.ops_begin = (u32)ops.size();
-    d.n_ops = g.n_relations;
-    d.writes_begin = (u32)writes.size();
     d.n_writes = g.n_writes;
     d.num_repetitions = g.num_repetitions;
     d.var_offset = g.variables_offset;
@@ -182,34 +181,99 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     d.const_placement = g.constants_placement_offset;
     d.path_len = g.selector_path_len;
     d.path_bits = 0;
+    d.term_base = (u32)total_terms;
     for (uint32_t i = 0; i < g.selector_path_len; i++)
       if (g.selector_path[i]) d.path_bits |= 1u << i;
-    // temporaries must be defined before use (SSA order, as GPUVariablesContext records them)
-    bool defined[GATE_MAX_TMP] = {false};
-    auto tmp_ok = [&](const bj_gate_index& ix) { return ix.kind != BJ_IDX_TEMPORARY || (ix.value < GATE_MAX_TMP && defined[ix.value]); };
-    uint32_t max_tmp = 0;
+    // 1. the recorded program (SSA as GPUVariablesContext records it: every relation defines a fresh TemporaryValue, used
+    //    only afterwards), with the pushes of the quotient terms placed right behind the relation that defines them
+    //    (push_evaluation_result is called inline by evaluate_once; the alpha power of a term is fixed by its write index)
+    std::vector<DevOp> prog;
+    prog.reserve(g.n_relations + g.n_writes);
+    std::vector<int32_t> def_at;  // program temporary -> index in `prog` of its defining op (-1: undefined)
+    auto defined = [&](const bj_gate_index& ix) { return ix.kind != BJ_IDX_TEMPORARY || (ix.value < def_at.size() && def_at[ix.value] >= 0); };
+    std::vector<std::vector<uint32_t>> pushes_of(g.n_relations);  // relation index -> write indices it feeds
+    std::vector<uint32_t> late_pushes;                              // writes of bare columns / constants
     for (uint32_t i = 0; i < g.n_relations; i++) {
       const bj_gate_relation& r = g.relations[i];
-      if (r.op > BJ_REL_INVERSE || r.dst_temporary >= GATE_MAX_TMP)
-        BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "gate program: unknown relation or more than 96 temporaries");
+      if (r.op > BJ_REL_INVERSE || r.dst_temporary >= GATE_MAX_PROGRAM_TMP)
+        BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "gate program: unknown relation or temporary index beyond 2^20");
+      if (r.dst_temporary >= def_at.size()) def_at.resize(r.dst_temporary + 1, -1);
+    }
+    {
+      std::vector<int32_t> def_rel(def_at.size(), -1);
+      for (uint32_t i = 0; i < g.n_relations; i++) {
+        if (def_rel[g.relations[i].dst_temporary] >= 0)
+          BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: temporary defined twice (programs are SSA)");
+        def_rel[g.relations[i].dst_temporary] = (int32_t)i;
+      }
+      for (uint32_t k = 0; k < g.n_writes; k++) {
+        const bj_gate_index& w = g.writes[k];
+        if (w.kind == BJ_IDX_TEMPORARY) {
+          if (w.value >= def_rel.size() || def_rel[w.value] < 0) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: write of an undefined temporary");
+          pushes_of[def_rel[w.value]].push_back(k);
+        } else {
+          late_pushes.push_back(k);
+        }
+      }
+    }
+    auto emit_push = [&](uint32_t k) -> bool {
+      DevOp o{};
+      o.op = GATE_OP_PUSH;
+      o.dst = k;
+      return check_index(g.writes[k], g, &o.a) && (prog.push_back(o), true);
+    };
+    for (uint32_t i = 0; i < g.n_relations; i++) {
+      const bj_gate_relation& r = g.relations[i];
       DevOp o{};
       o.op = r.op;
       o.dst = r.dst_temporary;
       const bool binary = r.op == BJ_REL_ADD || r.op == BJ_REL_SUB || r.op == BJ_REL_MUL;
-      bj_gate_index bdummy{BJ_IDX_CONSTANT_VALUE, 0, 0};
-      if (!tmp_ok(r.a) || (binary && !tmp_ok(r.b)) || !check_index(r.a, g, GATE_MAX_TMP, &o.a) ||
-          !check_index(binary ? r.b : bdummy, g, GATE_MAX_TMP, &o.b))
+      const bj_gate_index bdummy{BJ_IDX_CONSTANT_VALUE, 0, 0};
+      if (!defined(r.a) || (binary && !defined(r.b)) || !check_index(r.a, g, &o.a) || !check_index(binary ? r.b : bdummy, g, &o.b))
         BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: operand out of range or temporary used before definition");
-      defined[r.dst_temporary] = true;
-      if (r.dst_temporary + 1 > max_tmp) max_tmp = r.dst_temporary + 1;
-      ops.push_back(o);
+      def_at[r.dst_temporary] = (int32_t)prog.size();
+      prog.push_back(o);
+      for (uint32_t k : pushes_of[i])
+        if (!emit_push(k)) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: write operand out of range");
     }
-    for (uint32_t i = 0; i < g.n_writes; i++) {
-      DevOperand w;
-      if (!tmp_ok(g.writes[i]) || !check_index(g.writes[i], g, max_tmp ? max_tmp : 1, &w))
-        BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: write operand out of range");
-      writes.push_back(w);
+    for (uint32_t k : late_pushes)
+      if (!emit_push(k)) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: write operand out of range");
+    // 2. slot allocation: a temporary lives from its definition to its last use; its slot is then reused (the kernel reads both
+    //    operands before it writes the destination, so a destination may take over the slot of an operand that dies there)
+    {
+      std::vector<int32_t> last_use(def_at.size(), -1), slot(def_at.size(), -1);
+      for (size_t i = 0; i < prog.size(); i++) {
+        if (prog[i].a.kind == BJ_IDX_TEMPORARY) last_use[prog[i].a.value] = (int32_t)i;
+        if (prog[i].op != GATE_OP_PUSH && prog[i].b.kind == BJ_IDX_TEMPORARY) last_use[prog[i].b.value] = (int32_t)i;
+      }
+      std::vector<uint32_t> free_slots;
+      uint32_t next_slot = 0;
+      for (size_t i = 0; i < prog.size(); i++) {
+        DevOp& o = prog[i];
+        const bool is_push = o.op == GATE_OP_PUSH;
+        uint64_t ta = o.a.kind == BJ_IDX_TEMPORARY ? o.a.value : ~0ull, tb = (!is_push && o.b.kind == BJ_IDX_TEMPORARY) ? o.b.value : ~0ull;
+        if (ta != ~0ull) o.a.value = (uint64_t)slot[ta];
+        if (tb != ~0ull) o.b.value = (uint64_t)slot[tb];
+        if (ta != ~0ull && last_use[ta] == (int32_t)i) free_slots.push_back((uint32_t)slot[ta]);
+        if (tb != ~0ull && tb != ta && last_use[tb] == (int32_t)i) free_slots.push_back((uint32_t)slot[tb]);
+        if (is_push) continue;
+        const uint32_t t_dst = o.dst;
+        uint32_t sl;
+        if (!free_slots.empty()) {
+          sl = free_slots.back();
+          free_slots.pop_back();
+        } else {
+          sl = next_slot++;
+        }
+        if (sl >= (uint32_t)GATE_MAX_TMP)
+          BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "gate program: more than 128 temporaries live at once");
+        slot[t_dst] = (int32_t)sl;
+        o.dst = sl;
+        if (last_use[t_dst] < 0) free_slots.push_back(sl);  // defined but never read
+      }
     }
+    d.n_ops = (u32)prog.size();
+    ops.insert(ops.end(), prog.begin(), prog.end());
     total_terms += (uint64_t)g.n_writes * g.num_repetitions;
     gates.push_back(d);
   }
@@ -222,11 +286,29 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
   p.gates = (const DevGate*)d;
   p.n_gates = n_gates;
   static const DevOp dummy_op{};
-  BJ_TRY(param_upload(ctx, ops.empty() ? &dummy_op : ops.data(), sizeof(DevOp) * std::max<size_t>(ops.size(), 1), &d));
+  // small programs ride in the parameter arena; a long one (the Poseidon2 flattened gate is ~9k relations) gets its own
+  // stream-ordered buffer, released behind the kernel
+  void* big_program = nullptr;
+  const size_t ops_bytes = sizeof(DevOp) * std::max<size_t>(ops.size(), 1);
+  if (ops_bytes > (128u << 10)) {
+    BJ_CUDA(ctx, cudaMallocAsync(&big_program, ops_bytes, ctx->stream));
+    const cudaError_t e = cudaMemcpyAsync(big_program, ops.data(), ops_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+      cudaFreeAsync(big_program, ctx->stream);
+      BJ_FAIL(ctx, BJ_ERR_CUDA, std::string("gate program upload: ") + cudaGetErrorString(e));
+    }
+    d = big_program;
+  } else {
+    BJ_TRY(param_upload(ctx, ops.empty() ? &dummy_op : ops.data(), ops_bytes, &d));
+  }
+  struct ProgramGuard {  // freed (stream-ordered, i.e. after the kernel) on every exit path
+    void* p;
+    cudaStream_t s;
+    ~ProgramGuard() {
+      if (p) cudaFreeAsync(p, s);
+    }
+  } program_guard{big_program, ctx->stream};
   p.ops = (const DevOp*)d;
-  static const DevOperand dummy_w{};
-  BJ_TRY(param_upload(ctx, writes.empty() ? &dummy_w : writes.data(), sizeof(DevOperand) * std::max<size_t>(writes.size(), 1), &d));
-  p.writes = (const DevOperand*)d;
   static const u64* const null_ptr = nullptr;
   BJ_TRY(param_upload(ctx, n_variables ? (const void*)h_variable_cols : (const void*)&null_ptr, sizeof(u64*) * std::max(n_variables, 1u), &d));
   p.vars = (const u64* const*)d;

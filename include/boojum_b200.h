@@ -204,7 +204,8 @@ typedef struct bj_gate_index {
 } bj_gate_index;
 typedef struct bj_gate_relation {
   uint32_t op;            /* BJ_REL_* */
-  uint32_t dst_temporary; /* TemporaryValue index this relation defines (< 96) */
+  uint32_t dst_temporary; /* TemporaryValue index this relation defines: programs are SSA (one fresh index per relation, < 2^20);
+                           * the library assigns slots by liveness - at most 128 temporaries may be live at once */
   bj_gate_index a, b;     /* b ignored by the unary relations */
 } bj_gate_relation;
 typedef struct bj_gate_desc {

@@ -516,6 +516,90 @@ def test_gate_evaluator_all_relations(bj, ctx):
         assert int(g0[t]) == (t7 * 3 + t1 * 7) % P and int(g1[t]) == (t7 * 5 + t1 * 11) % P
 
 
+def test_gate_programs_of_the_reference_fixture_circuit(bj, ctx, golden_fixture):
+    """The gate set the reference verifies proof.json with (recursive_verifier.rs:2290-2368; the 13 gate types of
+    gpu_synthesizer/mod.rs:826-838 minus the two this circuit does not use), as recorded SSA programs through
+    bj_quotient_gates_general_purpose: 11 evaluators over 130 general-purpose columns with the vk's own selector tree (the
+    Poseidon2 flattened gate alone is ~9k relations, 118 terms) plus the boolean gate over a specialised column, against the
+    same evaluators run over the base field (oracle/verifier_reference.py, pinned by the quotient identity on proof.json)."""
+    from era_boojum_b200 import gate_library as GL
+    from era_boojum_b200 import placement as PL
+    from oracle import verifier_reference as VR
+    fp = golden_fixture["vk"]["fixed_parameters"]
+    cfg = VR.REFERENCE_FIXTURE_GATES
+    lay = VR.circuit_layout(fp, cfg)
+    rows = 96
+    r = rng(1300)
+    V, C = lay["num_variables"], lay["num_constants"]
+    var_cols = [r.integers(0, 2**64, size=rows, dtype=np.uint64) for _ in range(V)]      # non-canonical values included
+    const_cols = [O.random_field(r, rows) for _ in range(C)]
+    tree = fp["selectors_placement"]
+    gates, plan = [], []
+    for s_ in lay["specialized"]:                               # specialised-column gates come first (prover.rs:608-625)
+        gates.append(GL.placed(s_["gate"], s_["reps"], [], constants_placement_offset=lay["consts_gp"] + s_["const_base"],
+                               variables_initial_offset=s_["var_base"]))
+        plan.append((s_["gate"], s_["reps"], [], s_["var_base"], lay["consts_gp"] + s_["const_base"]))
+    for gate_idx, gate in enumerate(cfg["general_purpose"]):
+        if gate.terms == 0:
+            continue
+        reps = gate.num_repetitions_in_geometry(lay["gp_vars"], 0, fp["parameters"]["num_constant_columns"])
+        path = PL.output_placement(tree, gate_idx)
+        gates.append(GL.placed(gate, reps, path))
+        plan.append((gate, reps, path, 0, len(path)))
+    n_terms = sum(g.terms * reps for g, reps, *_ in plan)
+    assert n_terms == 415
+    alphas = [tuple(int(x) for x in O.random_field(r, 2)) for _ in range(n_terms)]
+    q0, q1 = O.random_field(r, rows), O.random_field(r, rows)
+    d0, d1 = bj.to_device(q0), bj.to_device(q1)
+    ctx.evaluate_gates_over_general_purpose_columns(gates, [bj.to_device(c) for c in var_cols], [],
+                                                    [bj.to_device(c) for c in const_cols], alphas, d0, d1)
+    g0, g1 = bj.to_numpy(d0), bj.to_numpy(d1)
+    B = VR.BaseBackend
+    for t in list(range(0, rows, 7)) + [rows - 1]:
+        vr = [int(c[t]) % P for c in var_cols]
+        cr = [int(c[t]) for c in const_cols]
+        w0 = w1 = k = 0
+        for gate, reps, path, var_base, const_base in plan:
+            terms = GL.evaluate_gate_terms(gate, B, lambda i: vr[i], lambda i: 0, lambda i: cr[i], reps, var_base=var_base,
+                                           const_base=const_base)
+            sel = 1
+            for depth, bit in enumerate(path):
+                sel = sel * (cr[depth] if bit else (1 - cr[depth])) % P
+            a0 = a1 = 0
+            for term in terms:
+                a0, a1, k = (a0 + term * alphas[k][0]) % P, (a1 + term * alphas[k][1]) % P, k + 1
+            w0, w1 = (w0 + sel * a0) % P, (w1 + sel * a1) % P
+        assert int(g0[t]) == (int(q0[t]) + w0) % P and int(g1[t]) == (int(q1[t]) + w1) % P, t
+
+
+def test_gate_program_limits(bj, ctx):
+    """a program may name 2^20 temporaries, but at most 128 may be live at once; programs must be SSA."""
+    import torch
+    from era_boojum_b200 import native as N
+    V, T, K = N.IDX_VARIABLE, N.IDX_TEMPORARY, N.IDX_CONSTANT_VALUE
+    rows = 32
+    v = [bj.to_device(O.random_field(rng(2), rows))]
+    d0 = torch.zeros(rows, dtype=torch.int64, device="cuda:0")
+    d1 = torch.zeros(rows, dtype=torch.int64, device="cuda:0")
+    # 200 temporaries all kept alive until the end -> unsupported
+    rel = [(N.REL_ADD, i, (V, 0), (K, i)) for i in range(200)]
+    rel += [(N.REL_ADD, 200 + i, (T, i), (T, 199 - i)) for i in range(200)]
+    gate = dict(relations=rel, writes=[(T, 399)], num_repetitions=1, constants_placement_offset=0, selector_path=[])
+    with pytest.raises(bj.BoojumError) as e:
+        ctx.evaluate_gates_over_general_purpose_columns([gate], v, [], [], [(1, 0)], d0, d1)
+    assert e.value.status == N.BJ_ERR_UNSUPPORTED
+    # a chain of 5000 relations with two live temporaries is fine: x + 5000
+    rel = [(N.REL_ADD, 0, (V, 0), (K, 1))] + [(N.REL_ADD, i, (T, i - 1), (K, 1)) for i in range(1, 5000)]
+    gate = dict(relations=rel, writes=[(T, 4999)], num_repetitions=1, constants_placement_offset=0, selector_path=[])
+    ctx.evaluate_gates_over_general_purpose_columns([gate], v, [], [], [(1, 0)], d0, d1)
+    assert np.array_equal(bj.to_numpy(d0), (bj.to_numpy(v[0]).astype(object) + 5000) % P)
+    # not SSA (temporary 0 defined twice)
+    gate = dict(relations=[(N.REL_ADD, 0, (V, 0), (K, 1)), (N.REL_ADD, 0, (V, 0), (K, 2))], writes=[(T, 0)], num_repetitions=1,
+                constants_placement_offset=0, selector_path=[])
+    with pytest.raises(bj.BoojumError):
+        ctx.evaluate_gates_over_general_purpose_columns([gate], v, [], [], [(1, 0)], d0, d1)
+
+
 # --------------------------------------------------------------------------------------- do_fri / queries -----
 @pytest.mark.parametrize("log_n,log_lde,cap,schedule", [(8, 3, 16, [3, 3, 1]), (10, 1, 4, [3, 3, 2]), (12, 3, 16, [3, 3, 3, 2])])
 def test_do_fri_matches_oracle_and_verifies(bj, ctx, log_n, log_lde, cap, schedule):
