@@ -2,7 +2,7 @@
 """bench.py - headline measurement for the Boojum polynomial-commitment hot path on B200.
 
 metric  : Goldilocks NTT G-elements/s (BASELINE.json metric, first half).  The second half, proof-generation seconds
-          at 2^22 rows at N GPUs, is reported in the extra objects "prove" (Poseidon2 tree + transcript: configs[4]) and
+          at 2^22 rows at N GPUs, is reported in the extra objects "prove" (Poseidon2 tree + Poseidon transcript: configs[4]) and
           "prove_non_recursive" (Blake2s tree + transcript: configs[3]) on a synthetic SHA-256-bench-shaped circuit (the
           real circuit needs the Rust synthesiser); one GPU runs the library's C++ driver bj_prove, several GPUs the
           coset-sharded prover over NCCL.  "merkle" reports configs[2]; "ntt_family" the inverse / LDE figures of configs[1].
@@ -451,9 +451,9 @@ def main():
         del wit, host_w
         from oracle import verifier as OV   # checker only: runs on the finished proof, outside every timed region
 
-        def prove_once(hasher):
-            """one timed proof of the synthetic SHA-shaped circuit with the given tree hasher + matching transcript"""
-            cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher=hasher, transcript=hasher)
+        def prove_once(hasher, transcript):
+            """one timed proof of the synthetic SHA-shaped circuit with the given tree hasher (H) and transcript (TR)"""
+            cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher=hasher, transcript=transcript)
             if world == 1:
                 # one GPU: the host driver is the library's own C++ (bj_setup_create / bj_prove), proof returned as serde JSON
                 setup = pctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk)
@@ -487,10 +487,10 @@ def main():
                     verified = bool(OV.verify(setup.vk(), proof))
                 except AssertionError as e:
                     verified = False
-                    sys.stderr.write("bench: the oracle verifier REJECTED the timed %s proof: %r\n" % (hasher, e))
+                    sys.stderr.write("bench: the oracle verifier REJECTED the timed %s/%s proof: %r\n" % (hasher, transcript, e))
                 verify_s = time.perf_counter() - t0
             res = {"rows_log2": args.prove_log_n, "seconds": round(secs, 4), "queries": len(proof["queries_per_fri_repetition"]),
-                   "n_gpus": world, "tree_hasher_and_transcript": hasher, "verified": verified,
+                   "n_gpus": world, "tree_hasher": hasher, "transcript": transcript, "verified": verified,
                    "h2d_witness_s": round(h2d_witness_s, 4), "h2d_witness_bytes": h2d_witness_bytes,
                    "seconds_with_witness_h2d": round(secs + h2d_witness_s, 4),
                    "stages_s": {k: round(v, 4) for k, v in stages.items()}}
@@ -506,9 +506,11 @@ def main():
                   "scaling": "strong (one proof, LDE cosets sharded over the GPUs)" if world > 1 else "single GPU",
                   "driver": "python + torch.distributed over the C-ABI (era_boojum_b200/prover.py)" if world > 1 else "bj_prove (host C++ in libboojum_b200.so), JSON proof parsed inside the timed region",
                   "note": "best of 2 timed proofs after one warm-up; the witness H2D (pinned host -> device, CUDA events) is reported as h2d_witness_s and added in seconds_with_witness_h2d; `verified` = the last timed proof accepted by oracle/verifier.py after the timed region; wall clock, max over ranks"}
-        # BASELINE configs[4] (recursive mode: Poseidon2 tree + transcript) and configs[3] (non-recursive: Blake2s tree + transcript)
-        out["prove"] = dict(common, **prove_once("poseidon2"))
-        out["prove_non_recursive"] = dict(common, **prove_once("blake2s"))
+        # BASELINE configs[4] = run_sha256_prover_recursive_mode_poseidon2 (src/gadgets/sha256/mod.rs:286-293): Poseidon2 tree hasher +
+        # GoldilocksPoisedonTranscript (the Poseidon v1 sponge transcript); configs[3] = run_sha256_prover_non_recursive (:264-271):
+        # Blake2s256 tree hasher + Blake2sTranscript
+        out["prove"] = dict(common, **prove_once("poseidon2", "poseidon"))
+        out["prove_non_recursive"] = dict(common, **prove_once("blake2s", "blake2s"))
         del variables, sigmas, constants, lk
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_sample()

@@ -30,10 +30,12 @@ class Transcript:
     """GoldilocksPoisedon2Transcript (cs/implementations/transcript.rs:62-129, 140-151) - host side."""
 
     def __init__(self, kind="poseidon2"):
-        """kind: "poseidon2" (GoldilocksPoisedon2Transcript), "blake2s" (Blake2sTranscript, transcript.rs:155-260) or "keccak256"
-        (Keccak256Transcript, :262-367)."""
+        """kind: "poseidon2" (GoldilocksPoisedon2Transcript), "blake2s" (Blake2sTranscript, transcript.rs:155-260), "keccak256"
+        (Keccak256Transcript, :262-367) or "poseidon" (GoldilocksPoisedonTranscript, :131-138, the sponge transcript over the
+        Poseidon v1 permutation: the TR of the reference's recursive-mode SHA-256 benches)."""
         self.kind = kind
-        new = {"poseidon2": lib.bj_transcript_new, "blake2s": lib.bj_transcript_new_blake2s, "keccak256": lib.bj_transcript_new_keccak256}
+        new = {"poseidon2": lib.bj_transcript_new, "blake2s": lib.bj_transcript_new_blake2s, "keccak256": lib.bj_transcript_new_keccak256,
+               "poseidon": lib.bj_transcript_new_poseidon}
         self._h = ctypes.c_void_p(new[kind]())
 
     def witness_field_elements(self, els):
@@ -537,7 +539,7 @@ class NativeSetup:
         pr = (ctypes.c_uint32 * max(1, len(pis)))(*[b for _, b in pis])
         c.public_input_columns, c.public_input_rows, c.n_public_inputs = pc, pr, len(pis)
         c.tree_hasher = {"poseidon2": 0, "blake2s": 1, "keccak256": 2}[getattr(config, "hasher", "poseidon2")]
-        c.transcript = {"poseidon2": 0, "blake2s": 1, "keccak256": 2}[getattr(config, "transcript", "poseidon2")]
+        c.transcript = {"poseidon2": 0, "blake2s": 1, "keccak256": 2, "poseidon": 3}[getattr(config, "transcript", "poseidon2")]
         self.cap_size = config.merkle_tree_cap_size
         self._vk_args = (c.log_n, c.num_variables, c.num_constants, gates, quotient_degree, config, lookup, pis)
         h = ctypes.c_void_p()

@@ -4,7 +4,10 @@
 //   Blake2sTranscript                                  src/cs/implementations/transcript.rs:155-260
 //   BoolsBuffer::get_bits (query index bits)           src/cs/implementations/transcript.rs:369-417
 //   compute_fri_schedule                               src/cs/implementations/prover.rs:2281-2372
-// The permutation is the same poseidon2.cuh source the kernels use, compiled for the host.
+//   GoldilocksPoisedonTranscript = the same sponge transcript over the Poseidon (v1) permutation, the transcript of
+//     run_sha256_prover_recursive_mode[_poseidon2] (src/gadgets/sha256/mod.rs:275-293; transcript.rs:131-138;
+//     permutation src/implementations/poseidon_goldilocks_naive.rs:11-165)
+// The Poseidon2 permutation is the same poseidon2.cuh source the kernels use, compiled for the host.
 #include <cstring>
 #include <vector>
 #include "ctx.hpp"
@@ -93,8 +96,44 @@ struct HostBlake2s {
 };
 }  // namespace bj
 
+namespace bj {
+// Poseidon (v1) over Goldilocks, t = 12, x^7, 4 + 22 + 4 rounds (src/implementations/poseidon_goldilocks_naive.rs:123-165): every
+// round adds its 12 round constants, applies the S-box to the whole state (full rounds) or to element 0 (partial rounds) and
+// multiplies by the circulant MDS matrix with entries 2^MDS_MATRIX_EXPS[(column - row) mod 12] (:11-31, 67-90).
+static void host_poseidon_v1_permutation(u64 state[12]) {
+  static const int EXPS[12] = {0, 0, 1, 0, 3, 5, 1, 8, 12, 3, 16, 10};
+  u64 s[12];
+  for (int i = 0; i < 12; i++) s[i] = gl::canon(state[i]);
+  for (int round = 0; round < 30; round++) {
+    for (int i = 0; i < 12; i++) s[i] = gl::canon(gl::add_lazy(s[i], gl::canon(BJ_POSEIDON_RC_HOST[round * 12 + i])));
+    const int n_sbox = (round < 4 || round >= 26) ? 12 : 1;
+    for (int i = 0; i < n_sbox; i++) {
+      const u64 x = s[i], x2 = gl::mul(x, x), x3 = gl::mul(x2, x), x4 = gl::mul(x2, x2);
+      s[i] = gl::mul(x4, x3);
+    }
+    u64 r[12];
+    for (int row = 0; row < 12; row++) {
+      unsigned __int128 acc = 0;  // 12 terms below 2^(64+16): no overflow (MAX_ROW_VALUE_BITS == 81, :34-58)
+      for (int col = 0; col < 12; col++) acc += (unsigned __int128)s[col] << EXPS[(col + 12 - row) % 12];
+      // reduce hi * 2^64 + lo with 2^64 = 2^32 - 1 (hi < 2^17)
+      const u64 lo = (u64)acc, hi = (u64)(acc >> 64);
+      r[row] = gl::canon(gl::add_lazy(gl::canon(lo), gl::mul(hi, 0xFFFFFFFFull)));
+    }
+    for (int i = 0; i < 12; i++) s[i] = r[i];
+  }
+  for (int i = 0; i < 12; i++) state[i] = s[i];
+}
+}  // namespace bj
+
 struct bj_transcript {
-  int kind = 0;  // 0: Poseidon2 sponge, 1: Blake2sTranscript (transcript.rs:155-260), 2: Keccak256Transcript (:262-367)
+  // 0: Poseidon2 sponge, 1: Blake2sTranscript (transcript.rs:155-260), 2: Keccak256Transcript (:262-367),
+  // 3: Poseidon (v1) sponge = GoldilocksPoisedonTranscript (:131-138)
+  int kind = 0;
+  bool algebraic() const { return kind == 0 || kind == 3; }
+  void permute() {
+    if (kind == 3) bj::host_poseidon_v1_permutation(state);
+    else bj::poseidon2_permutation(state);
+  }
   bj::HostBlake2s b2s;
   bj::HostKeccak256 keccak;
   std::vector<uint8_t> byte_buffer, byte_available;
@@ -167,11 +206,17 @@ bj_transcript* bj_transcript_new_keccak256(void) {
   t->kind = 2;
   return t;
 }
+bj_transcript* bj_transcript_new_poseidon(void) {
+  bj_transcript* t = new bj_transcript();
+  t->kind = 3;
+  return t;
+}
+void bj_host_poseidon_permutation(uint64_t state[12]) { bj::host_poseidon_v1_permutation((bj::u64*)state); }
 void bj_transcript_free(bj_transcript* t) { delete t; }
 
 void bj_transcript_witness_field_elements(bj_transcript* t, const uint64_t* els, size_t n) {
   if (!t || (!els && n)) return;
-  if (t->kind != 0) {  // el.as_u64_reduced().to_le_bytes()
+  if (!t->algebraic()) {  // el.as_u64_reduced().to_le_bytes()
     for (size_t i = 0; i < n; i++) {
       const u64 v = gl::canon(els[i]);
       for (int k = 0; k < 8; k++) t->byte_buffer.push_back((uint8_t)(v >> (8 * k)));
@@ -182,7 +227,7 @@ void bj_transcript_witness_field_elements(bj_transcript* t, const uint64_t* els,
 }
 
 void bj_transcript_witness_merkle_tree_cap(bj_transcript* t, const uint64_t* cap, size_t n_digests) {
-  if (t && t->kind != 0) {  // caps are raw 32-byte digests (4 little-endian u64 each), not field elements
+  if (t && !t->algebraic()) {  // caps are raw 32-byte digests (4 little-endian u64 each), not field elements
     if (!cap && n_digests) return;
     for (size_t i = 0; i < 4 * n_digests; i++)
       for (int k = 0; k < 8; k++) t->byte_buffer.push_back((uint8_t)(cap[i] >> (8 * k)));
@@ -193,14 +238,14 @@ void bj_transcript_witness_merkle_tree_cap(bj_transcript* t, const uint64_t* cap
 
 uint64_t bj_transcript_get_challenge(bj_transcript* t) {
   if (!t) return 0;
-  if (t->kind != 0) {  // 8 challenge bytes, little endian, reduced (from_u64_with_reduction)
+  if (!t->algebraic()) {  // 8 challenge bytes, little endian, reduced (from_u64_with_reduction)
     uint8_t b[8];
     b2s_challenge_bytes(t, 8, b);
     return gl::canon(le64(b));
   }
   if (t->buffer.empty()) {
     if (t->avail_pos < t->available.size()) return t->available[t->avail_pos++];
-    poseidon2_permutation(t->state);  // run_round_function, then take the 8 rate elements
+    t->permute();  // run_round_function, then take the 8 rate elements
     transcript_refill(t);
     return t->available[t->avail_pos++];
   }
@@ -211,7 +256,7 @@ uint64_t bj_transcript_get_challenge(bj_transcript* t) {
   while (to_absorb.size() % 8) to_absorb.push_back(0);
   for (size_t i = 0; i < to_absorb.size(); i += 8) {
     for (int k = 0; k < 8; k++) t->state[k] = to_absorb[i + k];
-    poseidon2_permutation(t->state);
+    t->permute();
   }
   transcript_refill(t);
   return t->available[t->avail_pos++];
@@ -221,7 +266,7 @@ uint64_t bj_transcript_get_challenge(bj_transcript* t) {
 uint64_t bj_transcript_get_index_bits(bj_transcript* t, uint32_t num_bits, uint32_t max_needed) {
   if (!t || num_bits > 64 || max_needed >= 64) return 0;
   while (t->bits.size() - t->bits_pos < num_bits) {
-    if (t->kind != 0) {  // non-algebraic transcript: 8 uniform bytes, all 64 bits (transcript.rs:401-413)
+    if (!t->algebraic()) {  // non-algebraic transcript: 8 uniform bytes, all 64 bits (transcript.rs:401-413)
       uint8_t bb[8];
       b2s_challenge_bytes(t, 8, bb);
       const u64 el = le64(bb);

@@ -162,7 +162,7 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
   if (!ctx || !circuit || !d_sigmas || !out || circuit->num_variables == 0 || circuit->log_n == 0 || circuit->log_n > 28 ||
       !is_pow2(circuit->fri_lde_factor) || !is_pow2(circuit->merkle_tree_cap_size) || !is_pow2(circuit->quotient_degree) ||
       circuit->quotient_degree > circuit->fri_lde_factor || (circuit->num_constants && !d_constants) ||
-      (circuit->n_gates && !circuit->gates) || circuit->tree_hasher > BJ_HASHER_KECCAK256 || circuit->transcript > 2)
+      (circuit->n_gates && !circuit->gates) || circuit->tree_hasher > BJ_HASHER_KECCAK256 || circuit->transcript > 3)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_setup_create: bad argument");
   if (circuit->lookup_width && (!d_lookup_tables || circuit->lookup_table_id_column >= circuit->num_constants ||
                                 circuit->lookup_variables_offset + circuit->lookup_width * circuit->lookup_num_repetitions >
@@ -267,7 +267,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   struct TrGuard {
     bj_transcript* t;
     ~TrGuard() { bj_transcript_free(t); }
-  } trg{c.transcript == 1 ? bj_transcript_new_blake2s() : c.transcript == 2 ? bj_transcript_new_keccak256() : bj_transcript_new()};
+  } trg{c.transcript == 1 ? bj_transcript_new_blake2s() : c.transcript == 2 ? bj_transcript_new_keccak256() : c.transcript == 3 ? bj_transcript_new_poseidon() : bj_transcript_new()};
   bj_transcript* tr = trg.t;
   auto challenge2 = [&]() {
     gl::e2 r;

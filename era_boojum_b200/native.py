@@ -81,6 +81,7 @@ SIGNATURES = {
     "bj_transcript_new": (_vp, []),
     "bj_transcript_new_blake2s": (_vp, []),
     "bj_transcript_new_keccak256": (_vp, []),
+    "bj_transcript_new_poseidon": (_vp, []),
     "bj_transcript_free": (None, [_vp]),
     "bj_transcript_witness_field_elements": (None, [_vp, _vp, _sz]),
     "bj_transcript_witness_merkle_tree_cap": (None, [_vp, _vp, _sz]),
@@ -117,6 +118,7 @@ SIGNATURES = {
     "bj_host_e2_mul": (None, [_vp, _vp, _vp]),
     "bj_host_e2_inv": (None, [_vp, _vp]),
     "bj_host_poseidon2_permutation": (None, [_vp]),
+    "bj_host_poseidon_permutation": (None, [_vp]),
     "bj_host_keccak256": (None, [_vp, _sz, _vp]),
 }
 

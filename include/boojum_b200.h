@@ -277,6 +277,10 @@ BJ_API bj_transcript* bj_transcript_new(void);          /* GoldilocksPoisedon2Tr
  * take all 64 bits of 8 challenge bytes (BoolsBuffer, non-algebraic branch). */
 BJ_API bj_transcript* bj_transcript_new_blake2s(void);
 BJ_API bj_transcript* bj_transcript_new_keccak256(void); /* Keccak256Transcript (transcript.rs:262-367): same scheme, Keccak-256 */
+/* GoldilocksPoisedonTranscript (transcript.rs:131-138): the algebraic sponge transcript over the Poseidon (v1) permutation
+ * (src/implementations/poseidon_goldilocks_naive.rs) - the TR of run_sha256_prover_recursive_mode and
+ * run_sha256_prover_recursive_mode_poseidon2 (src/gadgets/sha256/mod.rs:275-293) */
+BJ_API bj_transcript* bj_transcript_new_poseidon(void);
 BJ_API void bj_transcript_free(bj_transcript* t);
 BJ_API void bj_transcript_witness_field_elements(bj_transcript* t, const uint64_t* els, size_t n);
 BJ_API void bj_transcript_witness_merkle_tree_cap(bj_transcript* t, const uint64_t* cap_digests, size_t n_digests);
@@ -372,7 +376,7 @@ typedef struct bj_circuit {
   const uint32_t* public_input_rows;
   uint32_t n_public_inputs;
   uint32_t tree_hasher; /* BJ_HASHER_POSEIDON2 (recursive-mode bench), BJ_HASHER_BLAKE2S (sha256_bench_non_recursive), BJ_HASHER_KECCAK256 */
-  uint32_t transcript;  /* 0: Poseidon2 sponge transcript, 1: Blake2sTranscript, 2: Keccak256Transcript */
+  uint32_t transcript;  /* 0: Poseidon2 sponge transcript, 1: Blake2sTranscript, 2: Keccak256Transcript, 3: Poseidon (v1) sponge transcript */
 } bj_circuit;
 typedef struct bj_setup bj_setup;
 typedef struct bj_proof bj_proof;
@@ -401,6 +405,7 @@ BJ_API uint64_t bj_host_gl_mul_pow2(uint64_t a, uint32_t s);
 BJ_API void bj_host_e2_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
 BJ_API void bj_host_e2_inv(const uint64_t a[2], uint64_t out[2]);
 BJ_API void bj_host_poseidon2_permutation(uint64_t state[12]);
+BJ_API void bj_host_poseidon_permutation(uint64_t state[12]); /* Poseidon (v1), poseidon_goldilocks_naive.rs:154-165 */
 BJ_API void bj_host_keccak256(const uint8_t* data, size_t n, uint8_t out[32]);
 
 #ifdef __cplusplus

@@ -104,6 +104,64 @@ class Poseidon2Transcript:
         return (c0, c1)
 
 
+POSEIDON_MDS_EXPS = [0, 0, 1, 0, 3, 5, 1, 8, 12, 3, 16, 10]     # src/implementations/poseidon_goldilocks_naive.rs:11
+
+
+def _poseidon_round_constants():
+    """ALL_ROUND_CONSTANTS (poseidon_goldilocks_params.rs:14-114) from the oracle's own header"""
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "poseidon_rc.h")
+    vals = [int(v, 16) for v in re.findall(r"0x([0-9a-f]{16})ull", open(path).read())]
+    assert len(vals) == 360
+    return vals
+
+
+_POSEIDON_RC = None
+
+
+def poseidon_permutation(state):
+    """poseidon_permutation_naive (src/implementations/poseidon_goldilocks_naive.rs:154-165): 4 full + 22 partial + 4 full rounds
+    of (add round constants :113-120, x^7 on all / on element 0 :103-110, circulant MDS with entries
+    2^EXPS[(column - row) mod 12] :13-31, 67-90).  Python ints.  NOTE: no known-answer vector for this permutation exists in
+    the reference tree (its tests only compare its own naive and optimised forms), and the public Plonky2 vectors use a
+    different MDS matrix: the Poseidon (v1) transcript is pinned by restatement only."""
+    global _POSEIDON_RC
+    if _POSEIDON_RC is None:
+        _POSEIDON_RC = _poseidon_round_constants()
+    s = [int(x) % P for x in state]
+    for rnd in range(30):
+        s = [(x + _POSEIDON_RC[rnd * 12 + i]) % P for i, x in enumerate(s)]
+        for i in range(12 if (rnd < 4 or rnd >= 26) else 1):
+            s[i] = pow(s[i], 7, P)
+        s = [sum(s[col] << POSEIDON_MDS_EXPS[(col + 12 - row) % 12] for col in range(12)) % P for row in range(12)]
+    return s
+
+
+class PoseidonTranscript(Poseidon2Transcript):
+    """GoldilocksPoisedonTranscript = AlgebraicSpongeBasedTranscript<_, 8, 12, 4, PoseidonGoldilocks, Overwrite>
+    (transcript.rs:131-138): the sponge logic of the Poseidon2 transcript over the Poseidon (v1) permutation - the TR of
+    run_sha256_prover_recursive_mode_poseidon2 (src/gadgets/sha256/mod.rs:286-293)."""
+
+    def get_challenge(self):
+        if not self.buffer:
+            if self.available:
+                return self.available.pop(0)
+            self.state = poseidon_permutation(self.state)
+            self.available = [int(x) for x in self.state[:8]]
+            return self.get_challenge()
+        to_absorb = self.buffer + [1]
+        self.buffer = []
+        while len(to_absorb) % 8:
+            to_absorb.append(0)
+        self.state = [int(x) for x in self.state]
+        for i in range(0, len(to_absorb), 8):
+            self.state[:8] = to_absorb[i:i + 8]
+            self.state = poseidon_permutation(self.state)
+        self.available = [int(x) for x in self.state[:8]]
+        return self.get_challenge()
+
+
 class _KeccakStream:
     """hashlib-like wrapper of the pure-Python Keccak-256 oracle (oracle/keccak.py)."""
 

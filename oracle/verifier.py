@@ -71,7 +71,8 @@ def verify(vk, proof):
     n_tables = wdt + 1 if lk else 0
 
     hasher = vk.get("hasher", "poseidon2")                # tree hasher and transcript of the proof system instance
-    tr = {"poseidon2": R.Poseidon2Transcript, "blake2s": R.Blake2sTranscript, "keccak256": R.Keccak256Transcript}[vk.get("transcript", "poseidon2")]()
+    tr = {"poseidon2": R.Poseidon2Transcript, "blake2s": R.Blake2sTranscript, "keccak256": R.Keccak256Transcript,
+          "poseidon": R.PoseidonTranscript}[vk.get("transcript", "poseidon2")]()
     leaf_fn, path_ok = R.hasher_functions(hasher)
     tr.witness_merkle_tree_cap(vk["setup_merkle_tree_cap"])
     pi_locations = vk.get("public_inputs_locations", [])

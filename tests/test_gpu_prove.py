@@ -174,6 +174,29 @@ def test_native_cxx_prover_equals_python_driver(env, log_n, lookup):
     nat.close()
 
 
+def test_recursive_mode_poseidon2_type_parameters(env):
+    """H = GoldilocksPoseidon2Sponge, TR = GoldilocksPoisedonTranscript (Poseidon v1 sponge): the type parameters of
+    run_sha256_prover_recursive_mode_poseidon2 (src/gadgets/sha256/mod.rs:286-293, BASELINE configs[4]).  Both drivers give the
+    same proof, the oracle verifier (Python-int Poseidon v1) accepts it, and it differs from the Poseidon2-transcript proof."""
+    bj, ctx, prover, synthetic = env
+    variables, sigmas, constants, gates, Q, lk = synthetic.generate(ctx, 9, 60, seed=5, lookup=True)
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher="poseidon2", transcript="poseidon")
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg, lookup=lk)
+    ref = prover.prove(ctx, setup, variables, multiplicities=lk["multiplicities"])
+    nat = ctx.native_setup(sigmas.contiguous(), constants.contiguous(), gates, Q, cfg, lookup=lk)
+    got = nat.prove(variables.contiguous(), lk["multiplicities"])
+    assert json.dumps(got, sort_keys=True) == json.dumps(ref, sort_keys=True)
+    assert nat.vk() == setup.vk() and setup.vk()["transcript"] == "poseidon"
+    assert OV.verify(setup.vk(), got)
+    cfg2 = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100)
+    other = prover.prove(ctx, prover.Setup(ctx, sigmas, constants, gates, Q, cfg2, lookup=lk), variables, multiplicities=lk["multiplicities"])
+    assert other["witness_oracle_cap"] == got["witness_oracle_cap"] and other["values_at_z"] != got["values_at_z"]
+    bad = dict(setup.vk(), transcript="poseidon2")
+    with pytest.raises(AssertionError):
+        OV.verify(bad, got)
+    nat.close()
+
+
 def test_native_cxx_prover_rejects_unsatisfied_witness(env):
     bj, ctx, prover, synthetic = env
     variables, sigmas, constants, gates, Q = synthetic.generate(ctx, 8, 20, seed=2)

@@ -8,7 +8,8 @@ log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 hasher = sys.argv[2] if len(sys.argv) > 2 else "poseidon2"
 ctx = bj.Context.on_current_stream(0)
 variables, sigmas, constants, gates, Q, lk = synthetic.generate(ctx, log_n, 60, seed=42, lookup=True)
-cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher=hasher, transcript=hasher)
+transcript = "poseidon" if hasher == "poseidon2" else hasher   # the reference benches' (H, TR) pairs (sha256/mod.rs:264-293)
+cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher=hasher, transcript=transcript)
 nat = ctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk)
 if os.environ.get("WARM", "1") == "1":
     nat.prove(variables, lk["multiplicities"])
