@@ -23,7 +23,7 @@ import numpy as np
 from . import native
 from .native import BoojumError, P, lib
 
-__all__ = ["Context", "MerkleTreeWithCap", "Transcript", "FriOracles", "BoojumError", "P", "to_device", "to_numpy"]
+__all__ = ["Context", "Comm", "MerkleTreeWithCap", "Transcript", "FriOracles", "BoojumError", "P", "to_device", "to_numpy"]
 
 
 class Transcript:
@@ -514,6 +514,83 @@ class Context:
         self._check(lib.bj_fri_fold(self._h, self._ptr(c0), self._ptr(c1), log_m, log_fold, al, ctypes.byref(ci),
                                     self._ptr(o0), self._ptr(o1)))
         return o0, o1, int(ci.value)
+
+
+class Comm:
+    """bj_comm: the communicator of the native coset-sharded prover (csrc/comm.cu).  Creating one on a Context declares the
+    context's coset shard; native_setup() / NativeSetup.prove() on that context then run sharded and every rank returns the
+    same proof.  Transports: NCCL (one process per GPU) or "local" (ranks = threads of one process on one GPU)."""
+
+    def __init__(self, ctx, handle, rank, world, lde_degree):
+        self.ctx, self._h, self.rank, self.world = ctx, handle, rank, world
+        ctx.shard_rank, ctx.shard_world = rank, world
+        ctx._children.add(self)
+
+    @staticmethod
+    def unique_id():
+        """ncclGetUniqueId (rank 0); hand the 128 bytes to the other ranks by any side channel"""
+        buf = (ctypes.c_uint8 * 128)()
+        _ok(lib.bj_comm_unique_id(buf), "bj_comm_unique_id")
+        return bytes(buf)
+
+    @classmethod
+    def nccl(cls, ctx, unique_id, rank, world, lde_degree):
+        h = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * 128)(*unique_id)
+        ctx._check(lib.bj_comm_create_nccl(ctx._h, buf, rank, world, lde_degree.bit_length() - 1, ctypes.byref(h)))
+        return cls(ctx, h, rank, world, lde_degree)
+
+    @classmethod
+    def from_torch_distributed(cls, ctx, dist, lde_degree, group=None):
+        """one process per GPU launched by torchrun: torch.distributed only carries the 128-byte NCCL unique id"""
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls.nccl(ctx, box[0], rank, world, lde_degree)
+
+    @staticmethod
+    def local_group(world):
+        g = ctypes.c_void_p()
+        _ok(lib.bj_comm_group_create(world, ctypes.byref(g)), "bj_comm_group_create")
+        return g
+
+    @staticmethod
+    def destroy_local_group(group):
+        lib.bj_comm_group_destroy(group)
+
+    @classmethod
+    def local(cls, ctx, group, rank, world, lde_degree):
+        h = ctypes.c_void_p()
+        ctx._check(lib.bj_comm_create_local(ctx._h, group, rank, lde_degree.bit_length() - 1, ctypes.byref(h)))
+        return cls(ctx, h, rank, world, lde_degree)
+
+    def all_gather(self, send, recv):
+        """device tensors: recv[r] = rank r's send"""
+        self.ctx._check(lib.bj_comm_all_gather(self._h, self.ctx._ptr(send), self.ctx._ptr(recv), send.numel()))
+        return recv
+
+    def all_gather_host(self, arr):
+        a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1)
+        out = np.zeros((self.world, a.shape[0]), np.uint64)
+        self.ctx._check(lib.bj_comm_all_gather_host(self._h, a.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), a.shape[0]))
+        return out
+
+    def broadcast_host(self, arr, root=0):
+        a = np.ascontiguousarray(arr, dtype=np.uint64)
+        self.ctx._check(lib.bj_comm_broadcast_host(self._h, a.ctypes.data_as(ctypes.c_void_p), a.size, root))
+        return a
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.bj_comm_destroy(self._h)
+            self._h = None
+            self.ctx.shard_rank, self.ctx.shard_world = 0, 1
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class NativeSetup:

@@ -44,8 +44,11 @@ struct CosetShard {
 
 }  // namespace bj
 
+struct bj_comm;
+
 struct bj_ctx {
   int device = 0;
+  bj_comm* comm = nullptr;  // communicator of a coset-sharded multi-GPU prover (comm.cu); nullptr = single GPU
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string last_error;
@@ -133,6 +136,15 @@ struct DeviceGuard {
   DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 int32_t ensure_scratch(bj_ctx* ctx, size_t bytes);
+// collectives of the sharded prover (comm.cu); all no-ops / plain copies for a world of one
+int32_t comm_all_gather(bj_comm* c, const u64* d_send, u64* d_recv, u64 n);
+int32_t comm_all_gather_host(bj_comm* c, const u64* h_send, u64* h_recv, u64 n);
+int32_t comm_broadcast_host(bj_comm* c, u64* h_buf, u64 n, uint32_t root);
+uint32_t comm_world(const bj_ctx* ctx);
+uint32_t comm_rank(const bj_ctx* ctx);
+// global cap (cap_size digests) of an oracle whose local tree (this rank's cosets [k][row]) ends in cap_size / world digests:
+// cap node c of the global tree belongs to coset c / (cap_size / L) (leaf index = coset * n + row, proof.rs:89-91)
+int32_t comm_assemble_cap(bj_ctx* ctx, const u64* h_local_cap, uint32_t cap_size, uint32_t lde_factor, u64* h_global_cap);
 int32_t ensure_twiddles(bj_ctx* ctx, int log_n);
 int32_t param_upload(bj_ctx* ctx, const void* host, size_t bytes, void** d_out);
 }  // namespace bj

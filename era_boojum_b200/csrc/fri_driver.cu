@@ -171,28 +171,41 @@ int32_t bj_do_fri_with_hasher(bj_ctx* ctx, bj_transcript* transcript, const uint
   const u64* cur0 = (const u64*)d_c0;
   const u64* cur1 = (const u64*)d_c1;
   u32 log_m = log_full_size;
+  // coset-sharded context: the codewords hold this rank's cosets only ([local coset][row], 1 / world of every vector); folds and
+  // oracle subtrees are local (a fold of 2^k neighbours never leaves a coset), caps are assembled across the ranks so that all
+  // of them draw the same challenges, and the last codeword (a few hundred elements) is gathered and interpolated everywhere
+  const u32 world = comm_world(ctx);
+  u32 log_world = 0;
+  while ((1u << log_world) < world) log_world++;
+  if (world > 1 && (log_lde != ctx->shard_log_lde || cap_size < (1u << log_lde)))
+    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_do_fri: sharded FRI needs cap_size >= LDE factor and the LDE factor of the shard");
+  const u32 cap_local = cap_size / world;
   for (u32 i = 0; i < n_schedule; i++) {
     const u32 k = schedule[i];
     fo->levels.emplace_back();
     FriLevel& lv = fo->levels.back();
-    lv.log_size = log_m;
+    lv.log_size = log_m - log_world;  // LOCAL size: queries address the local [coset][row] layout
     lv.log_fold = k;
     lv.c0 = cur0;
     lv.c1 = cur1;
     // oracle over the step's input: 2^k consecutive c0 values then the same 2^k c1 values per leaf (fri/mod.rs:173-187, 252-268)
-    const u64 n_leaves = 1ull << (log_m - k);
-    if (n_leaves < cap_size) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_do_fri: oracle smaller than the cap (schedule / cap mismatch)");
+    const u64 n_leaves = (1ull << (log_m - k)) / world;
+    if (n_leaves < cap_local || cap_local == 0) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_do_fri: oracle smaller than the cap (schedule / cap mismatch)");
     lv.leaf_hashes.reset(new DevBuf());
     lv.nodes.reset(new DevBuf());
     BJ_TRY(lv.leaf_hashes->alloc(ctx, sizeof(u64) * 4 * n_leaves));
-    BJ_TRY(lv.nodes->alloc(ctx, sizeof(u64) * 4 * (n_leaves - cap_size)));
+    BJ_TRY(lv.nodes->alloc(ctx, sizeof(u64) * 4 * (n_leaves - cap_local)));
     const uint64_t* srcs[2] = {(const uint64_t*)cur0, (const uint64_t*)cur1};
     BJ_TRY((hasher == BJ_HASHER_BLAKE2S ? bj_merkle_build_blake2s : hasher == BJ_HASHER_KECCAK256 ? bj_merkle_build_keccak256 : bj_merkle_build_poseidon2)(
-        ctx, srcs, 2, n_leaves, 1u << k, cap_size, (uint64_t*)lv.leaf_hashes->p, (uint64_t*)lv.nodes->p));
+        ctx, srcs, 2, n_leaves, 1u << k, cap_local, (uint64_t*)lv.leaf_hashes->p, (uint64_t*)lv.nodes->p));
     lv.cap.resize(4 * (size_t)cap_size);
-    const u64* cap_src = n_leaves == cap_size ? lv.leaf_hashes->u() : lv.nodes->u() + 4 * (n_leaves - 2 * (u64)cap_size);
-    BJ_CUDA(ctx, cudaMemcpyAsync(lv.cap.data(), cap_src, sizeof(u64) * 4 * cap_size, cudaMemcpyDeviceToHost, ctx->stream));
-    BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+      std::vector<u64> local_cap(4 * (size_t)cap_local);
+      const u64* cap_src = n_leaves == cap_local ? lv.leaf_hashes->u() : lv.nodes->u() + 4 * (n_leaves - 2 * (u64)cap_local);
+      BJ_CUDA(ctx, cudaMemcpyAsync(local_cap.data(), cap_src, sizeof(u64) * 4 * cap_local, cudaMemcpyDeviceToHost, ctx->stream));
+      BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      BJ_TRY(comm_assemble_cap(ctx, local_cap.data(), cap_size, 1u << log_lde, lv.cap.data()));
+    }
     bj_transcript_witness_merkle_tree_cap(transcript, (const uint64_t*)lv.cap.data(), cap_size);
     uint64_t alpha[2];
     alpha[0] = bj_transcript_get_challenge(transcript);
@@ -201,8 +214,8 @@ int32_t bj_do_fri_with_hasher(bj_ctx* ctx, bj_transcript* transcript, const uint
     fo->challenges.push_back(alpha[1]);
     // fold k times (interpolate_independent_cosets / interpolate_flattened_cosets)
     std::unique_ptr<DevBuf> n0(new DevBuf()), n1(new DevBuf());
-    BJ_TRY(n0->alloc(ctx, sizeof(u64) << (log_m - k)));
-    BJ_TRY(n1->alloc(ctx, sizeof(u64) << (log_m - k)));
+    BJ_TRY(n0->alloc(ctx, (sizeof(u64) << (log_m - k)) / world));
+    BJ_TRY(n1->alloc(ctx, (sizeof(u64) << (log_m - k)) / world));
     uint64_t kap = kappa;
     BJ_TRY(bj_fri_fold(ctx, (const uint64_t*)cur0, (const uint64_t*)cur1, log_m, k, alpha, &kap, (uint64_t*)n0->p, (uint64_t*)n1->p));
     kappa = kap;
@@ -221,8 +234,26 @@ int32_t bj_do_fri_with_hasher(bj_ctx* ctx, bj_transcript* transcript, const uint
   DevBuf f0, f1;
   BJ_TRY(f0.alloc(ctx, sizeof(u64) * fft_size));
   BJ_TRY(f1.alloc(ctx, sizeof(u64) * fft_size));
-  BJ_CUDA(ctx, cudaMemcpyAsync(f0.p, cur0, sizeof(u64) * fft_size, cudaMemcpyDeviceToDevice, ctx->stream));
-  BJ_CUDA(ctx, cudaMemcpyAsync(f1.p, cur1, sizeof(u64) * fft_size, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (world == 1) {
+    BJ_CUDA(ctx, cudaMemcpyAsync(f0.p, cur0, sizeof(u64) * fft_size, cudaMemcpyDeviceToDevice, ctx->stream));
+    BJ_CUDA(ctx, cudaMemcpyAsync(f1.p, cur1, sizeof(u64) * fft_size, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    // local [L / world][mc] (c0 | c1) from every rank -> global [L][mc]: coset slot k of rank r is coset k * world + r
+    const u64 loc = fft_size / world, mc = fft_size >> log_lde, l_loc = (1ull << log_lde) / world;
+    DevBuf snd, rcv;
+    BJ_TRY(snd.alloc(ctx, sizeof(u64) * 2 * loc));
+    BJ_TRY(rcv.alloc(ctx, sizeof(u64) * 2 * fft_size));
+    BJ_CUDA(ctx, cudaMemcpyAsync(snd.u(), cur0, sizeof(u64) * loc, cudaMemcpyDeviceToDevice, ctx->stream));
+    BJ_CUDA(ctx, cudaMemcpyAsync(snd.u() + loc, cur1, sizeof(u64) * loc, cudaMemcpyDeviceToDevice, ctx->stream));
+    BJ_TRY(comm_all_gather(ctx->comm, snd.u(), rcv.u(), 2 * loc));
+    for (u32 r = 0; r < world; r++)
+      for (u64 kk = 0; kk < l_loc; kk++) {
+        const u64 j = kk * world + r;
+        BJ_CUDA(ctx, cudaMemcpyAsync((u64*)f0.p + j * mc, rcv.u() + (u64)r * 2 * loc + kk * mc, sizeof(u64) * mc, cudaMemcpyDeviceToDevice, ctx->stream));
+        BJ_CUDA(ctx, cudaMemcpyAsync((u64*)f1.p + j * mc, rcv.u() + (u64)r * 2 * loc + loc + kk * mc, sizeof(u64) * mc, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+    BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // snd / rcv are released below
+  }
   const u64 coset = gl::inv(kappa);
   BJ_TRY(bj_bitreverse(ctx, (uint64_t*)f0.p, log_m, 1, fft_size));
   BJ_TRY(bj_bitreverse(ctx, (uint64_t*)f1.p, log_m, 1, fft_size));
@@ -276,10 +307,11 @@ int32_t bj_fri_oracles_query(bj_fri_oracles* o, uint32_t oracle_idx, uint64_t le
   if (leaf_index >= n_leaves) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_fri_oracles_query: leaf index out of range");
   const uint64_t* srcs[2] = {(const uint64_t*)lv.c0, (const uint64_t*)lv.c1};
   BJ_TRY(bj_query_leaf_elements(ctx, srcs, 2, 1u << lv.log_fold, n_leaves, &leaf_index, 1, h_leaf_elements));
+  const u32 cap_local = o->cap_size / comm_world(ctx);  // the level's tree covers this rank's cosets
   u32 depth = 0;
-  while ((n_leaves >> depth) > o->cap_size) depth++;
+  while ((n_leaves >> depth) > cap_local) depth++;
   *path_len = depth;
-  return bj_merkle_paths(ctx, (const uint64_t*)lv.leaf_hashes->p, (const uint64_t*)lv.nodes->p, n_leaves, o->cap_size, &leaf_index, 1, h_path);
+  return bj_merkle_paths(ctx, (const uint64_t*)lv.leaf_hashes->p, (const uint64_t*)lv.nodes->p, n_leaves, cap_local, &leaf_index, 1, h_path);
 }
 
 }  // extern "C"

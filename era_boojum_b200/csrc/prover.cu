@@ -54,19 +54,26 @@ struct Oracle {
   std::vector<u64> cap;  // host, 4 * cap_size
 };
 
-static int32_t oracle_build(bj_ctx* ctx, Oracle& o, u64 n_leaves, u32 cap_size, u32 hasher) {
+// n_leaves / cap_size are GLOBAL; on a coset-sharded context the tree covers this rank's cosets (n_leaves / world leaves,
+// cap_size / world local cap nodes - same depth), and o.cap is the assembled global cap (lde_factor locates the cosets).
+static int32_t oracle_build(bj_ctx* ctx, Oracle& o, u64 n_leaves, u32 cap_size, u32 hasher, u32 lde_factor) {
+  const u32 world = comm_world(ctx);
+  const u32 cap_global = cap_size;
+  n_leaves /= world;
+  cap_size /= world;
   o.n_leaves = n_leaves;
   o.cap_size = cap_size;
-  if (n_leaves < cap_size) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "prover: oracle smaller than the cap");
+  if (cap_size == 0 || n_leaves < cap_size) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "prover: oracle smaller than the cap");
   BJ_TRY(o.leaf_hashes.alloc(ctx, 4 * n_leaves));
   BJ_TRY(o.nodes.alloc(ctx, 4 * (n_leaves - cap_size)));
   BJ_TRY((hasher == BJ_HASHER_BLAKE2S ? bj_merkle_build_blake2s : hasher == BJ_HASHER_KECCAK256 ? bj_merkle_build_keccak256 : bj_merkle_build_poseidon2)(
       ctx, o.cols.data(), (u32)o.cols.size(), n_leaves, 1, cap_size, (uint64_t*)o.leaf_hashes.p, (uint64_t*)o.nodes.p));
-  o.cap.resize(4 * (size_t)cap_size);
+  std::vector<u64> local(4 * (size_t)cap_size);
   const u64* src = n_leaves == cap_size ? o.leaf_hashes.p : o.nodes.p + 4 * (n_leaves - 2 * (u64)cap_size);
-  BJ_CUDA(ctx, cudaMemcpyAsync(o.cap.data(), src, sizeof(u64) * 4 * cap_size, cudaMemcpyDeviceToHost, ctx->stream));
+  BJ_CUDA(ctx, cudaMemcpyAsync(local.data(), src, sizeof(u64) * 4 * cap_size, cudaMemcpyDeviceToHost, ctx->stream));
   BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return BJ_OK;
+  o.cap.resize(4 * (size_t)cap_global);
+  return comm_assemble_cap(ctx, local.data(), cap_global, lde_factor, o.cap.data());
 }
 
 struct GateCopy {
@@ -128,7 +135,8 @@ struct bj_setup {
   uint32_t n_tables = 0;
   bj::DevMem lde;  // [V + C + T][L][n]
   bj::Oracle tree;
-  const uint64_t* col(uint32_t j) const { return (const uint64_t*)lde.p + ((size_t)j << (c.log_n + log_l())); }
+  uint64_t col_len = 0;  // elements of one LDE column held by this context: n * (L / world)
+  const uint64_t* col(uint32_t j) const { return (const uint64_t*)lde.p + (size_t)j * col_len; }
   uint32_t log_l() const {
     uint32_t l = 0;
     while ((1u << l) < c.fri_lde_factor) l++;
@@ -168,7 +176,11 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
                                 circuit->lookup_variables_offset + circuit->lookup_width * circuit->lookup_num_repetitions >
                                     circuit->num_variables))
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_setup_create: inconsistent lookup description");
-  if (ctx->shard.log_stride) BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "bj_setup_create: coset-sharded contexts are driven from the host language");
+  if (ctx->shard.log_stride && !ctx->comm)
+    BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "bj_setup_create: a coset-sharded context needs a communicator (bj_comm_create_*) for the native driver");
+  if (ctx->comm && (circuit->merkle_tree_cap_size < circuit->fri_lde_factor || comm_world(ctx) > circuit->fri_lde_factor ||
+                    (1u << ctx->shard_log_lde) != circuit->fri_lde_factor))
+    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_setup_create: sharded proving needs cap_size >= LDE factor >= world and the LDE factor the communicator was created for");
   *out = nullptr;
   {
     // a proof needs at least one FRI folding step (the JSON has a fri_base_oracle_cap): reject circuits so small that
@@ -217,12 +229,13 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
   const uint32_t V = circuit->num_variables, C = circuit->num_constants, T = s->n_tables;
   const uint32_t log_n = circuit->log_n, log_l = s->log_l();
   const u64 n = 1ull << log_n;
-  BJ_TRY(s->lde.alloc(ctx, (size_t)(V + C + T) << (log_n + log_l)));
+  s->col_len = (n << log_l) / comm_world(ctx);
+  BJ_TRY(s->lde.alloc(ctx, (size_t)(V + C + T) * s->col_len));
   BJ_TRY(bj_lde(ctx, d_sigmas, n, (uint64_t*)s->lde.p, log_n, log_l, V, 0));
-  if (C) BJ_TRY(bj_lde(ctx, d_constants, n, (uint64_t*)s->lde.p + ((size_t)V << (log_n + log_l)), log_n, log_l, C, 0));
-  if (T) BJ_TRY(bj_lde(ctx, d_lookup_tables, n, (uint64_t*)s->lde.p + ((size_t)(V + C) << (log_n + log_l)), log_n, log_l, T, 0));
+  if (C) BJ_TRY(bj_lde(ctx, d_constants, n, (uint64_t*)s->lde.p + (size_t)V * s->col_len, log_n, log_l, C, 0));
+  if (T) BJ_TRY(bj_lde(ctx, d_lookup_tables, n, (uint64_t*)s->lde.p + (size_t)(V + C) * s->col_len, log_n, log_l, T, 0));
   for (uint32_t j = 0; j < V + C + T; j++) s->tree.cols.push_back(s->col(j));
-  BJ_TRY(oracle_build(ctx, s->tree, n << log_l, circuit->merkle_tree_cap_size, circuit->tree_hasher));
+  BJ_TRY(oracle_build(ctx, s->tree, n << log_l, circuit->merkle_tree_cap_size, circuit->tree_hasher, circuit->fri_lde_factor));
   *out = s.release();
   return BJ_OK;
 }
@@ -254,7 +267,12 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   const uint32_t log_n = c.log_n, log_l = setup->log_l();
   uint32_t log_q = 0;
   while ((1u << log_q) < Q) log_q++;
-  const u64 n = 1ull << log_n, nL = n << log_l, nQ = n << log_q;
+  const u64 n = 1ull << log_n, nQ = n << log_q;
+  // coset shard (multi-GPU): this context holds L / world cosets of every LDE column and Q_loc of the first Q cosets
+  const uint32_t world = comm_world(ctx), rank = comm_rank(ctx);
+  const u64 nL = (n << log_l) / world;                                   // LOCAL length of an LDE column
+  const u64 nQl = ctx->shard.local_cosets(Q) << log_n;                    // LOCAL quotient points
+  if (setup->col_len != nL) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_prove: the setup was built with a different shard");
   const uint32_t T = setup->n_tables, wdt = c.lookup_width, nsub = c.lookup_num_repetitions, voff = c.lookup_variables_offset;
   auto t_prev = std::chrono::steady_clock::now();
   auto mark = [&](int stage) -> int32_t {
@@ -291,7 +309,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
 
   // ---- round 1: witness commitment ----
   DevMem w_lde, m_lde;
-  BJ_TRY(w_lde.alloc(ctx, (size_t)V << (log_n + log_l)));
+  BJ_TRY(w_lde.alloc(ctx, (size_t)V * nL));
   BJ_TRY(bj_lde(ctx, d_variables, n, (uint64_t*)w_lde.p, log_n, log_l, V, 0));
   std::vector<const uint64_t*> w_cols(V);
   for (uint32_t j = 0; j < V; j++) w_cols[j] = (const uint64_t*)w_lde.p + (size_t)j * nL;
@@ -302,7 +320,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     BJ_TRY(bj_lde(ctx, d_multiplicities, n, (uint64_t*)m_lde.p, log_n, log_l, 1, 0));
     w_or.cols.push_back((const uint64_t*)m_lde.p);  // variables | witness (none) | multiplicities
   }
-  BJ_TRY(oracle_build(ctx, w_or, nL, cap, c.tree_hasher));
+  BJ_TRY(oracle_build(ctx, w_or, n << log_l, cap, c.tree_hasher, L));
   pf->witness_cap = w_or.cap;
   bj_transcript_witness_merkle_tree_cap(tr, (const uint64_t*)w_or.cap.data(), cap);
   BJ_TRY(mark(0));
@@ -345,7 +363,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   for (uint32_t j = 0; j < n_s2; j++) s2_cols[j] = (const uint64_t*)s2_lde.p + (size_t)j * nL;
   Oracle s2_or;
   s2_or.cols = s2_cols;
-  BJ_TRY(oracle_build(ctx, s2_or, nL, cap, c.tree_hasher));
+  BJ_TRY(oracle_build(ctx, s2_or, n << log_l, cap, c.tree_hasher, L));
   pf->stage2_cap = s2_or.cap;
   bj_transcript_witness_merkle_tree_cap(tr, (const uint64_t*)s2_or.cap.data(), cap);
   const uint32_t a_off = 2 + 2 * n_partial;
@@ -370,11 +388,21 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   for (uint32_t j = 0; j < V; j++) sigma_cols[j] = setup->col(j);
   for (uint32_t j = 0; j < C; j++) const_cols[j] = setup->col(V + j);
   for (uint32_t j = 0; j < T; j++) table_cols[j] = setup->col(V + C + j);
-  DevMem qq;  // [2][nQ]: c0 then c1
+  DevMem qq, qloc;  // qq: [2][nQ] global (c0 then c1); qloc: this rank's cosets among the first Q
   BJ_TRY(qq.alloc(ctx, 2 * nQ));
-  BJ_CUDA(ctx, cudaMemsetAsync(qq.p, 0, sizeof(u64) * 2 * nQ, ctx->stream));
   uint64_t* q0 = (uint64_t*)qq.p;
   uint64_t* q1 = q0 + nQ;
+  uint64_t* const gq0 = q0;
+  uint64_t* const gq1 = q1;
+  if (world > 1) {
+    BJ_TRY(qloc.alloc(ctx, 2 * std::max<u64>(nQl, 1)));
+    q0 = (uint64_t*)qloc.p;
+    q1 = q0 + nQl;
+    BJ_CUDA(ctx, cudaMemsetAsync(qloc.p, 0, sizeof(u64) * 2 * std::max<u64>(nQl, 1), ctx->stream));
+  } else {
+    BJ_CUDA(ctx, cudaMemsetAsync(qq.p, 0, sizeof(u64) * 2 * nQ, ctx->stream));
+  }
+  if (nQl) {
   if (lk) {
     std::vector<const uint64_t*> ll(wdt * nsub), al(2 * nsub);
     for (uint32_t i = 0; i < wdt * nsub; i++) ll[i] = w_cols[voff + i];
@@ -382,11 +410,11 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     const uint64_t lb[2] = {lookup_beta.c0, lookup_beta.c1}, lg[2] = {lookup_gamma.c0, lookup_gamma.c1};
     BJ_TRY(bj_quotient_lookup_specialized(ctx, ll.data(), nsub, wdt, const_cols[c.lookup_table_id_column], table_cols.data(), T,
                                           (const uint64_t*)m_lde.p, al.data(), s2_cols[a_off + 2 * nsub], s2_cols[a_off + 2 * nsub + 1], lb, lg,
-                                          powers.data(), nQ, q0, q1));
+                                          powers.data(), nQl, q0, q1));
   }
   if (n_gate_terms)
     BJ_TRY(bj_quotient_gates_general_purpose(ctx, setup->gates.data(), (uint32_t)setup->gates.size(), w_cols.data(), V, nullptr, 0,
-                                             const_cols.data(), C, powers.data() + 2 * (size_t)n_lk_terms, n_gate_terms, nQ, q0, q1));
+                                             const_cols.data(), C, powers.data() + 2 * (size_t)n_lk_terms, n_gate_terms, nQl, q0, q1));
   {
     std::vector<uint64_t> nr(V);
     BJ_TRY(bj_non_residues_for_copy_permutation(n, V, nr.data()));
@@ -396,6 +424,34 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
                                         log_n, log_l, log_q, Q, q0, q1));
   }
   BJ_TRY(bj_quotient_divide_by_vanishing(ctx, q0, q1, log_n, log_q));
+  }  // nQl
+  if (world > 1) {
+    // the one bulk exchange: the quotient cosets recombine (they are interpolated together at size n * Q).  Every rank sends
+    // `per` = ceil(Q / world) coset slots (c0 | c1 per slot; ranks beyond Q send padding), one all-gather, then the owned
+    // slots are scattered to their global coset positions j = k * world + r.
+    const u64 per = std::max<u64>(1, Q / world);
+    DevMem snd, rcv;
+    BJ_TRY(snd.alloc(ctx, per * 2 * n));
+    BJ_TRY(rcv.alloc(ctx, (u64)world * per * 2 * n));
+    BJ_CUDA(ctx, cudaMemsetAsync(snd.p, 0, sizeof(u64) * per * 2 * n, ctx->stream));
+    const u64 q_loc = nQl >> log_n;
+    for (u64 k = 0; k < q_loc; k++) {
+      BJ_CUDA(ctx, cudaMemcpyAsync(snd.p + (2 * k) * n, q0 + k * n, sizeof(u64) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      BJ_CUDA(ctx, cudaMemcpyAsync(snd.p + (2 * k + 1) * n, q1 + k * n, sizeof(u64) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    BJ_TRY(comm_all_gather(ctx->comm, snd.p, rcv.p, per * 2 * n));
+    for (uint32_t r = 0; r < world; r++)
+      for (u64 k = 0; k < per; k++) {
+        const u64 j = k * world + r;
+        if (j >= Q) continue;
+        const u64* part = rcv.p + ((u64)r * per + k) * 2 * n;
+        BJ_CUDA(ctx, cudaMemcpyAsync(gq0 + j * n, part, sizeof(u64) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        BJ_CUDA(ctx, cudaMemcpyAsync(gq1 + j * n, part + n, sizeof(u64) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+    q0 = gq0;
+    q1 = gq1;
+    qloc.release();
+  }
   // cosets -> natural order, one interpolation of size n*Q on the coset 7, Q chunks of n coefficients (prover.rs:1399-1467)
   BJ_TRY(bj_bitreverse(ctx, q0, log_n + log_q, 2, nQ));
   BJ_TRY(bj_intt_natural_to_natural(ctx, q0, log_n + log_q, 2, nQ, gl::MULT_GEN));
@@ -421,7 +477,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   for (uint32_t j = 0; j < 2 * Q; j++) qt_cols[j] = (const uint64_t*)qt_lde.p + (size_t)j * nL;
   Oracle qt_or;
   qt_or.cols = qt_cols;
-  BJ_TRY(oracle_build(ctx, qt_or, nL, cap, c.tree_hasher));
+  BJ_TRY(oracle_build(ctx, qt_or, n << log_l, cap, c.tree_hasher, L));
   pf->quotient_cap = qt_or.cap;
   bj_transcript_witness_merkle_tree_cap(tr, (const uint64_t*)qt_or.cap.data(), cap);
   BJ_TRY(mark(2));
@@ -474,9 +530,37 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     return BJ_OK;
   };
   std::vector<Src> z_omega_sources{{s2_cols[0], s2_cols[1]}};
-  BJ_TRY(open_at(sources, z, pf->values_at_z));
-  BJ_TRY(open_at(z_omega_sources, z_omega, pf->values_at_z_omega));
-  BJ_TRY(open_at(zero_sources, gl::e2{0, 0}, pf->values_at_0));
+  if (rank == 0) {  // the barycentric evaluation reads coset 0, which rank 0 owns
+    BJ_TRY(open_at(sources, z, pf->values_at_z));
+    BJ_TRY(open_at(z_omega_sources, z_omega, pf->values_at_z_omega));
+    BJ_TRY(open_at(zero_sources, gl::e2{0, 0}, pf->values_at_0));
+  }
+  if (world > 1) {
+    const size_t n_open = sources.size() + z_omega_sources.size() + zero_sources.size();
+    std::vector<u64> flat(2 * n_open);
+    if (rank == 0) {
+      size_t k = 0;
+      for (const auto* vs : {&pf->values_at_z, &pf->values_at_z_omega, &pf->values_at_0})
+        for (const auto& v : *vs) {
+          flat[k++] = v.c0;
+          flat[k++] = v.c1;
+        }
+    }
+    BJ_TRY(comm_broadcast_host(ctx->comm, flat.data(), flat.size(), 0));
+    if (rank != 0) {
+      size_t k = 0;
+      auto take = [&](std::vector<gl::e2>& dst, size_t cnt) {
+        dst.resize(cnt);
+        for (auto& v : dst) {
+          v.c0 = flat[k++];
+          v.c1 = flat[k++];
+        }
+      };
+      take(pf->values_at_z, sources.size());
+      take(pf->values_at_z_omega, z_omega_sources.size());
+      take(pf->values_at_0, zero_sources.size());
+    }
+  }
   for (const auto* vs : {&pf->values_at_z, &pf->values_at_z_omega, &pf->values_at_0})
     for (const auto& v : *vs) {
       const uint64_t e[2] = {v.c0, v.c1};
@@ -529,8 +613,8 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
       v[2 * i + 1] = vals[i].c1;
     }
     const uint64_t a[2] = {at.c0, at.c1};
-    return bj_deep_quotient_group(ctx, p0.data(), p1.data(), (uint32_t)srcs.size(), v.data(), chs, a, log_n + log_l, (uint64_t*)deep.p,
-                                  (uint64_t*)deep.p + nL);
+    return bj_deep_quotient_group(ctx, p0.data(), p1.data(), (uint32_t)srcs.size(), v.data(), chs, a, log_n + log_l /* global */,
+                                  (uint64_t*)deep.p, (uint64_t*)deep.p + nL);
   };
   BJ_TRY(deep_group(sources, pf->values_at_z, z, ch.data()));
   BJ_TRY(deep_group(z_omega_sources, pf->values_at_z_omega, z_omega, ch.data() + 2 * sources.size()));
@@ -580,15 +664,39 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   std::vector<uint64_t> idxs(num_queries);
   for (auto& i : idxs) i = bj_transcript_get_index_bits(tr, max_bits, max_bits);
   pf->queries.assign(num_queries, {});
+  // a query is answered by the rank that owns the coset of its index (leaf t = coset * n + row lies in that rank's subtree);
+  // the other ranks look up a dummy leaf, the answers are exchanged and every rank keeps the owner's
+  std::vector<uint64_t> loc_idx(num_queries);
+  std::vector<uint32_t> owner(num_queries);
+  for (uint32_t q = 0; q < num_queries; q++) {
+    const uint64_t j = idxs[q] >> log_n, i = idxs[q] & (n - 1);
+    owner[q] = (uint32_t)(j % world);
+    loc_idx[q] = owner[q] == rank ? (((j / world) << log_n) | i) : 0;
+  }
+  auto exchange = [&](std::vector<uint64_t>& buf, size_t rec_len) -> int32_t {  // buf: [num_queries][rec_len]
+    if (world == 1) return BJ_OK;
+    std::vector<uint64_t> all((size_t)world * buf.size());
+    BJ_TRY(comm_all_gather_host(ctx->comm, (const u64*)buf.data(), (u64*)all.data(), buf.size()));
+    for (uint32_t q = 0; q < num_queries; q++)
+      memcpy(buf.data() + (size_t)q * rec_len, all.data() + (size_t)owner[q] * buf.size() + (size_t)q * rec_len, sizeof(uint64_t) * rec_len);
+    return BJ_OK;
+  };
   const Oracle* base[4] = {&w_or, &s2_or, &qt_or, &setup->tree};
   for (const Oracle* o : base) {
     const size_t row_len = o->cols.size();
     uint32_t depth = 0;
     while ((o->n_leaves >> depth) > o->cap_size) depth++;
-    std::vector<uint64_t> rows((size_t)num_queries * row_len), paths((size_t)num_queries * (depth ? depth : 1) * 4);
-    BJ_TRY(bj_query_leaf_elements(ctx, o->cols.data(), (uint32_t)row_len, 1, o->n_leaves, idxs.data(), num_queries, rows.data()));
-    BJ_TRY(bj_merkle_paths(ctx, (const uint64_t*)o->leaf_hashes.p, (const uint64_t*)o->nodes.p, o->n_leaves, o->cap_size, idxs.data(), num_queries,
-                           paths.data()));
+    const size_t plen = (size_t)(depth ? depth : 1) * 4;
+    std::vector<uint64_t> rows((size_t)num_queries * row_len), paths((size_t)num_queries * plen);
+    BJ_TRY(bj_query_leaf_elements(ctx, o->cols.data(), (uint32_t)row_len, 1, o->n_leaves, loc_idx.data(), num_queries, rows.data()));
+    if (depth) {
+      std::vector<uint64_t> tight((size_t)num_queries * depth * 4);
+      BJ_TRY(bj_merkle_paths(ctx, (const uint64_t*)o->leaf_hashes.p, (const uint64_t*)o->nodes.p, o->n_leaves, o->cap_size, loc_idx.data(),
+                             num_queries, tight.data()));
+      paths = tight;
+    }
+    BJ_TRY(exchange(rows, row_len));
+    if (depth) BJ_TRY(exchange(paths, (size_t)depth * 4));
     for (uint32_t q = 0; q < num_queries; q++) {
       QueryAnswer a;
       a.leaf_elements.assign(rows.begin() + (size_t)q * row_len, rows.begin() + (size_t)(q + 1) * row_len);
@@ -596,18 +704,35 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
       pf->queries[q].push_back(std::move(a));
     }
   }
-  for (uint32_t q = 0; q < num_queries; q++) {
-    uint64_t sub = idxs[q];
+  {
+    uint32_t log_len = log_n;  // coset length of the level's codeword
+    std::vector<uint64_t> sub(idxs);
     for (uint32_t lvl = 0; lvl < sched_len; lvl++) {
       const uint32_t k = sched[lvl];
-      QueryAnswer a;
-      a.leaf_elements.resize((size_t)2 << k);
-      std::vector<uint64_t> path(4 * 40);
+      const size_t le_len = (size_t)2 << k;
+      std::vector<uint64_t> les((size_t)num_queries * le_len, 0), paths((size_t)num_queries * 4 * 40, 0);
       uint32_t plen = 0;
-      BJ_TRY(bj_fri_oracles_query(fri, lvl, sub >> k, (uint64_t*)a.leaf_elements.data(), path.data(), &plen));
-      a.path.assign(path.begin(), path.begin() + 4 * (size_t)plen);
-      pf->queries[q].push_back(std::move(a));
-      sub >>= k;
+      for (uint32_t q = 0; q < num_queries; q++) {
+        const uint64_t j = sub[q] >> log_len, i = sub[q] & ((1ull << log_len) - 1);
+        const uint64_t local = owner[q] == rank ? ((((j / world) << log_len) | i) >> k) : 0;
+        uint32_t pl = 0;
+        BJ_TRY(bj_fri_oracles_query(fri, lvl, local, les.data() + (size_t)q * le_len, paths.data() + (size_t)q * 4 * 40, &pl));
+        plen = pl;
+        sub[q] >>= k;
+      }
+      // compact the paths to [num_queries][plen * 4] before the exchange
+      std::vector<uint64_t> tight((size_t)num_queries * std::max<uint32_t>(plen, 1) * 4, 0);
+      for (uint32_t q = 0; q < num_queries; q++)
+        memcpy(tight.data() + (size_t)q * plen * 4, paths.data() + (size_t)q * 4 * 40, sizeof(uint64_t) * plen * 4);
+      BJ_TRY(exchange(les, le_len));
+      if (plen) BJ_TRY(exchange(tight, (size_t)plen * 4));
+      for (uint32_t q = 0; q < num_queries; q++) {
+        QueryAnswer a;
+        a.leaf_elements.assign(les.begin() + (size_t)q * le_len, les.begin() + (size_t)(q + 1) * le_len);
+        a.path.assign(tight.begin() + (size_t)q * plen * 4, tight.begin() + (size_t)(q + 1) * plen * 4);
+        pf->queries[q].push_back(std::move(a));
+      }
+      log_len -= k;
     }
   }
   BJ_TRY(mark(5));

@@ -102,6 +102,17 @@ SIGNATURES = {
     "bj_pow_blake2s": (_i32, [_vp, _vp, _u32, _u32, _vp]),
     "bj_materialize_columns": (_i32, [_vp, _vp, _u64, _vp, _u32, _u64, _u32, _vp]),
     "bj_create_permutation_polys": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "bj_comm_unique_id": (_i32, [_vp]),
+    "bj_comm_create_nccl": (_i32, [_vp, _vp, _u32, _u32, _u32, _pp]),
+    "bj_comm_group_create": (_i32, [_u32, _pp]),
+    "bj_comm_group_destroy": (None, [_vp]),
+    "bj_comm_create_local": (_i32, [_vp, _vp, _u32, _u32, _pp]),
+    "bj_comm_destroy": (_i32, [_vp]),
+    "bj_comm_rank": (_u32, [_vp]),
+    "bj_comm_world": (_u32, [_vp]),
+    "bj_comm_all_gather": (_i32, [_vp, _vp, _vp, _u64]),
+    "bj_comm_all_gather_host": (_i32, [_vp, _vp, _vp, _u64]),
+    "bj_comm_broadcast_host": (_i32, [_vp, _vp, _u64, _u32]),
     "bj_setup_create": (_i32, [_vp, _vp, _vp, _vp, _vp, _pp]),
     "bj_setup_free": (None, [_vp]),
     "bj_setup_get_cap": (_i32, [_vp, _vp]),

@@ -67,6 +67,39 @@ BJ_API const char* bj_last_error(const bj_ctx* ctx);
 /* number of kernels this library launched through ctx so far (for launch accounting) */
 BJ_API uint64_t bj_launch_count(const bj_ctx* ctx);
 
+/* ---- multi-GPU: communicator of the coset-sharded prover (one process - or one thread - per GPU) ----
+ * Creating a communicator on a context declares its coset shard (bj_ctx_set_coset_shard(ctx, rank, world, log_lde)) and makes
+ * bj_setup_create / bj_prove / bj_do_fri on that context run SHARDED: every rank passes the same full witness, keeps the LDE
+ * cosets j = rank (mod world) of every committed polynomial, builds the Merkle subtrees of its cosets, and all ranks return
+ * the same proof (identical to the single-GPU proof).  What crosses GPUs: cap digests of every oracle, the quotient cosets
+ * (one all-gather of 2 * Q * n u64 - they are interpolated together, prover.rs:1399-1467), the openings (computed by the owner
+ * of coset 0), the last FRI codeword and the query answers.  Requirements: world a power of two <= the LDE factor,
+ * merkle_tree_cap_size >= the LDE factor.
+ *   NCCL transport: rank 0 calls bj_comm_unique_id and hands the 128 bytes to the other ranks by any side channel (MPI, TCP,
+ *   torch.distributed ...); every rank then calls bj_comm_create_nccl.  libnccl.so.2 is loaded at run time (the copy already
+ *   in the process is reused); BJ_ERR_UNSUPPORTED if it is absent.
+ *   Local transport: bj_comm_group_create(world) once, bj_comm_create_local per rank (ranks = host threads whose contexts sit
+ *   on one device): lets one GPU run the sharded driver end to end.
+ * Destroy the communicator before its context.  The raw collectives are exported for host code that shards other stages. */
+typedef struct bj_comm bj_comm;
+typedef struct bj_comm_group bj_comm_group;
+#define BJ_COMM_UNIQUE_ID_BYTES 128
+BJ_API int32_t bj_comm_unique_id(uint8_t out[BJ_COMM_UNIQUE_ID_BYTES]);
+BJ_API int32_t bj_comm_create_nccl(bj_ctx* ctx, const uint8_t unique_id[BJ_COMM_UNIQUE_ID_BYTES], uint32_t rank, uint32_t world,
+                            uint32_t log_lde, bj_comm** out);
+BJ_API int32_t bj_comm_group_create(uint32_t world, bj_comm_group** out);
+BJ_API void bj_comm_group_destroy(bj_comm_group* group);
+BJ_API int32_t bj_comm_create_local(bj_ctx* ctx, bj_comm_group* group, uint32_t rank, uint32_t log_lde, bj_comm** out);
+BJ_API int32_t bj_comm_destroy(bj_comm* comm);
+BJ_API uint32_t bj_comm_rank(const bj_comm* comm);
+BJ_API uint32_t bj_comm_world(const bj_comm* comm);
+/* d_recv[r * n .. (r + 1) * n) = rank r's d_send[0 .. n): ncclAllGather on the context's stream (asynchronous); the local
+ * transport completes before returning.  d_send may be its own slot of d_recv. */
+BJ_API int32_t bj_comm_all_gather(bj_comm* comm, const uint64_t* d_send, uint64_t* d_recv, uint64_t n_u64_per_rank);
+/* the same for small host buffers (staged through the device); synchronises */
+BJ_API int32_t bj_comm_all_gather_host(bj_comm* comm, const uint64_t* h_send, uint64_t* h_recv, uint64_t n_u64_per_rank);
+BJ_API int32_t bj_comm_broadcast_host(bj_comm* comm, uint64_t* h_buf, uint64_t n_u64, uint32_t root);
+
 /* ---- device memory (GoodAllocator hook, src/cs/traits/mod.rs:13-15) ---- */
 BJ_API int32_t bj_alloc(bj_ctx* ctx, size_t bytes, void** d_ptr);
 BJ_API int32_t bj_free(bj_ctx* ctx, void* d_ptr);

@@ -142,6 +142,101 @@ def test_coset_sharded_prover_equals_single_gpu(env, world, log_n, V, lde, cap, 
         assert json.dumps(proof, sort_keys=True) == json.dumps(ref, sort_keys=True)
 
 
+def _prove_native_sharded_threads(bj, synthetic, prover, world, log_n, V, lde, cap, seed, lookup, hasher="poseidon2", transcript="poseidon2",
+                                  public_inputs=()):
+    """the library's own sharded driver (bj_setup_create / bj_prove on contexts that carry a bj_comm): `world` ranks as threads
+    on one GPU over the local transport; returns every rank's (cap, proof)."""
+    import threading
+    group = bj.Comm.local_group(world)
+    out, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            ctx = bj.Context(0)
+            comm = bj.Comm.local(ctx, group, rank, world, lde)
+            gen = synthetic.generate(ctx, log_n, V, seed=seed, lookup=lookup)
+            lk = gen[5] if lookup else None
+            variables, sigmas, constants, gates, Q = gen[:5]
+            cfg = prover.ProofConfig(fri_lde_factor=lde, merkle_tree_cap_size=cap, security_level=100, hasher=hasher, transcript=transcript)
+            nat = ctx.native_setup(sigmas.contiguous(), constants.contiguous(), gates, Q, cfg, lookup=lk, public_inputs=public_inputs)
+            proof = nat.prove(variables.contiguous(), lk["multiplicities"] if lk else None)
+            out[rank] = (nat.get_cap(), proof)
+            ctx.synchronize()
+            nat.close()
+            comm.close()
+            ctx.close()
+        except BaseException as e:
+            errs.append(e)
+
+    ts = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=600) for t in ts]
+    if errs:
+        raise errs[0]
+    assert all(o is not None for o in out), "a rank did not finish"
+    bj.Comm.destroy_local_group(group)
+    return out
+
+
+@pytest.mark.parametrize("world,log_n,V,lde,cap,lookup,hasher,transcript", [
+    (2, 9, 20, 8, 16, False, "poseidon2", "poseidon2"), (4, 8, 60, 8, 16, True, "poseidon2", "poseidon"),
+    (8, 8, 20, 8, 16, False, "blake2s", "blake2s"), (2, 10, 60, 4, 8, True, "blake2s", "blake2s"), (8, 9, 60, 8, 32, True, "poseidon2", "poseidon2")])
+def test_native_sharded_prover_equals_single_gpu(env, world, log_n, V, lde, cap, lookup, hasher, transcript):
+    """bj_prove on coset-sharded contexts (communicator: local transport, the NCCL transport takes the same code path) returns
+    on every rank exactly the single-GPU proof - world 2 / 4 / 8 incl. world > quotient degree (ranks that own no quotient
+    coset), lookup argument, public inputs, both hashers."""
+    bj, ctx, prover, synthetic = env
+    gen = synthetic.generate(ctx, log_n, V, seed=3, lookup=lookup)
+    lk = gen[5] if lookup else None
+    variables, sigmas, constants, gates, Q = gen[:5]
+    pis = [(1, 3), (5, 3)] if world == 4 else []
+    cfg = prover.ProofConfig(fri_lde_factor=lde, merkle_tree_cap_size=cap, security_level=100, hasher=hasher, transcript=transcript)
+    nat = ctx.native_setup(sigmas.contiguous(), constants.contiguous(), gates, Q, cfg, lookup=lk, public_inputs=pis)
+    ref = nat.prove(variables.contiguous(), lk["multiplicities"] if lk else None)
+    assert OV.verify(nat.vk(), ref)
+    ref_cap = nat.get_cap()
+    nat.close()
+    res = _prove_native_sharded_threads(bj, synthetic, prover, world, log_n, V, lde, cap, 3, lookup, hasher, transcript, pis)
+    for cap_r, proof in res:
+        assert np.array_equal(cap_r, ref_cap)
+        assert json.dumps(proof, sort_keys=True) == json.dumps(ref, sort_keys=True)
+
+
+def test_comm_collectives_local_transport(env):
+    """bj_comm_all_gather / all_gather_host / broadcast_host over the local transport (4 thread-ranks on one GPU)."""
+    import threading
+    import torch
+    bj, ctx, prover, synthetic = env
+    world = 4
+    group = bj.Comm.local_group(world)
+    res, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            c = bj.Context(0)
+            comm = bj.Comm.local(c, group, rank, world, 8)
+            send = torch.full((1000,), rank + 1, dtype=torch.int64, device="cuda:0")
+            recv = torch.zeros((world, 1000), dtype=torch.int64, device="cuda:0")
+            comm.all_gather(send, recv)
+            host = comm.all_gather_host(np.array([rank * 10, rank * 10 + 1], dtype=np.uint64))
+            b = comm.broadcast_host(np.array([7, 8, 9] if rank == 2 else [0, 0, 0], dtype=np.uint64), root=2)
+            res[rank] = (recv.cpu().numpy(), host, b)
+            comm.close()
+            c.close()
+        except BaseException as e:
+            errs.append(e)
+
+    ts = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=120) for t in ts]
+    assert not errs, errs
+    for recv, host, b in res:
+        assert all((recv[r] == r + 1).all() for r in range(world))
+        assert host.tolist() == [[r * 10, r * 10 + 1] for r in range(world)]
+        assert b.tolist() == [7, 8, 9]
+    bj.Comm.destroy_local_group(group)
+
+
 def test_local_comm_python_fri_equals_cxx_driver(env):
     """world of one through the communicator path (Python-level FRI loop) == bj_do_fri driver."""
     bj, ctx, prover, synthetic = env

@@ -7,7 +7,8 @@ KEYS = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dra
         'smsp__inst_executed.sum', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.sum',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'lts__t_bytes.sum', 'sm__cycles_elapsed.max']
+        'lts__t_bytes.sum', 'sm__cycles_elapsed.max', 'launch__occupancy_limit_blocks', 'sm__maximum_warps_per_active_cycle_pct',
+        'smsp__inst_executed_per_warp', 'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic']
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
