@@ -427,11 +427,11 @@ def main():
         from era_boojum_b200 import parallel, prover, synthetic
         comm, pctx = None, ctx
         if world > 1:
-            # coset-sharded proving: rank r keeps the LDE cosets j = r (mod world) of every committed polynomial; caps, the
-            # quotient cosets (one NCCL all-reduce), the openings and the query answers are exchanged (parallel.py)
+            # coset-sharded proving by the library's own C++ driver: rank r keeps the LDE cosets j = r (mod world) of every committed
+            # polynomial; caps, the quotient cosets (one ncclAllGather), the openings and the query answers are exchanged through
+            # a bj_comm over NCCL (csrc/comm.cu); torch.distributed only hands the 128-byte NCCL unique id to the ranks
             pctx = bj.Context.on_current_stream(local_rank)
-            pctx.set_coset_shard(rank, world, 8)
-            comm = parallel.TorchDistComm(dist)
+            comm = bj.Comm.from_torch_distributed(pctx, dist, 8)
         variables, sigmas, constants, gates, Q, lk = synthetic.generate(pctx, args.prove_log_n, 60, seed=42, lookup=True)
         # "H2D of the witness reported separately" - the witness columns (variables + multiplicities) from pinned
         # host memory to the device, timed with CUDA events (the trace itself is generated on the device, so the copy is not
@@ -454,13 +454,10 @@ def main():
         def prove_once(hasher, transcript):
             """one timed proof of the synthetic SHA-shaped circuit with the given tree hasher (H) and transcript (TR)"""
             cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher=hasher, transcript=transcript)
-            if world == 1:
-                # one GPU: the host driver is the library's own C++ (bj_setup_create / bj_prove), proof returned as serde JSON
-                setup = pctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk)
-                run_prove = lambda tm: setup.prove(variables, lk["multiplicities"], timings=tm)
-            else:
-                setup = prover.Setup(pctx, sigmas, constants, gates, Q, cfg, lookup=lk, comm=comm)
-                run_prove = lambda tm: prover.prove(pctx, setup, variables, timings=tm, multiplicities=lk["multiplicities"])
+            # the host driver is the library's own C++ (bj_setup_create / bj_prove), sharded over the communicator when world > 1;
+            # the proof comes back as serde JSON
+            setup = pctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk)
+            run_prove = lambda tm: setup.prove(variables, lk["multiplicities"], timings=tm)
             run_prove(None)  # warm-up (tables, allocator)
             best = None
             for _ in range(2):  # two timed proofs, the faster one is reported (max over ranks each)
@@ -504,7 +501,7 @@ def main():
 
         common = {"circuit": "synthetic sha256-bench-shaped: 60 gp columns + 8 lookup sub-arguments of width 4 (92 copy-permutation columns, 1 multiplicity column), ConstantsAllocator/Fma/Reduction<4>, Q=4, L=8, cap 16",
                   "scaling": "strong (one proof, LDE cosets sharded over the GPUs)" if world > 1 else "single GPU",
-                  "driver": "python + torch.distributed over the C-ABI (era_boojum_b200/prover.py)" if world > 1 else "bj_prove (host C++ in libboojum_b200.so), JSON proof parsed inside the timed region",
+                  "driver": "bj_prove (host C++ in libboojum_b200.so%s), JSON proof parsed inside the timed region" % (", coset-sharded over bj_comm / NCCL" if world > 1 else ""),
                   "note": "best of 2 timed proofs after one warm-up; the witness H2D (pinned host -> device, CUDA events) is reported as h2d_witness_s and added in seconds_with_witness_h2d; `verified` = the last timed proof accepted by oracle/verifier.py after the timed region; wall clock, max over ranks"}
         # BASELINE configs[4] = run_sha256_prover_recursive_mode_poseidon2 (src/gadgets/sha256/mod.rs:286-293): Poseidon2 tree hasher +
         # GoldilocksPoisedonTranscript (the Poseidon v1 sponge transcript); configs[3] = run_sha256_prover_non_recursive (:264-271):

@@ -1,20 +1,23 @@
-// Openings: evaluate committed polynomials at an Fp2 point from their values on the first LDE coset.
+// Openings: evaluate committed polynomials at an Fp2 point from their values on the first LDE coset this context holds.
 // Reference: precompute_for_barycentric_evaluation_in_extension + barycentric_evaluate_*_at_extension_for_bitreversed_parallel
 // (src/cs/implementations/utils.rs:907-1243), driven from prove_cpu_basic (prover.rs:1519-1802).  f(at) is a field
 // element fixed by f alone, so only the value matters:  with x_i = 7 w_n^{bitrev(i)} (coset 0 of the LDE, bit-reversed),
 //   f(at) = (at^n - 7^n) / (n 7^n) * sum_i f(x_i) * x_i / (at - x_i).
 // Fp2-valued polynomials are stored as two base columns and are evaluated column by column (f = f0 + u f1).
+// On a coset-sharded context (multi-GPU) local slot 0 is the global coset j = rank with shift c = 7 w_{nL}^{bitrev_L(j)}
+// instead of 7: the same formula with c in place of 7 gives the same f(at), so every rank can open any column from the
+// coset it owns and the columns are split over the ranks.
 #include <vector>
 #include "ctx.hpp"
 
 namespace bj {
 
 // den[i] = at - x_i  (Fp2), and xs[i] = x_i
-__global__ void __launch_bounds__(256) bary_denominators_kernel(const u64* __restrict__ tab, u64 n, gl::e2 at, u64* __restrict__ d0,
+__global__ void __launch_bounds__(256) bary_denominators_kernel(const u64* __restrict__ tab, u64 n, gl::e2 at, u64 shift, u64* __restrict__ d0,
                                                                  u64* __restrict__ d1, u64* __restrict__ xs) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  u64 x = gl::mul(n > 1 ? __ldg(tab + (i >> 1)) : 1, gl::MULT_GEN);
+  u64 x = gl::mul(n > 1 ? __ldg(tab + (i >> 1)) : 1, shift);
   if (i & 1) x = gl::neg(x);
   xs[i] = x;
   d0[i] = gl::canon(gl::sub(at.c0, x));
@@ -85,14 +88,21 @@ extern "C" int32_t bj_barycentric_evaluate(bj_ctx* ctx, const uint64_t* const* h
   bj::DeviceGuard device_guard(ctx);
   if (!ctx || !h_cols || !h_at || !h_out || n_cols == 0 || log_n > 32)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_barycentric_evaluate: bad argument");
-  if (ctx->shard.first != 0) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_barycentric_evaluate: coset 0 belongs to shard rank 0");
   const u64 n = 1ull << log_n;
+  // shift of the coset in local slot 0: 7 * w_{nL}^{bitrev_L(first)} (7 itself without a shard / on rank 0)
+  u64 shift = gl::MULT_GEN;
+  if (ctx->shard.first) {
+    const u32 ll = ctx->shard_log_lde;
+    u64 jr = 0;
+    for (u32 b = 0; b < ll; b++) jr |= (u64)((ctx->shard.first >> b) & 1) << (ll - 1 - b);
+    shift = gl::mul(gl::MULT_GEN, gl::pow(gl::omega(log_n + ll), jr));
+  }
   BJ_TRY(ensure_twiddles(ctx, (int)log_n));
   const gl::e2 at = {gl::canon(h_at[0]), gl::canon(h_at[1])};
-  // scale = (at^n - 7^n) / (n * 7^n)
+  // scale = (at^n - c^n) / (n * c^n), c = shift
   gl::e2 atn = at;
   for (u32 i = 0; i < log_n; i++) atn = gl::e2_sqr(atn);
-  const u64 cn = gl::pow(gl::MULT_GEN, n);
+  const u64 cn = gl::pow(shift, n);
   gl::e2 scale = {gl::canon(gl::sub(atn.c0, cn)), atn.c1};
   scale = gl::e2_mul_base(scale, gl::inv(gl::mul(gl::canon(n % gl::P), cn)));
   const u32 gx = (u32)std::min<u64>((n + DOT_T - 1) / DOT_T, 4 * (u64)ctx->sm_count);
@@ -103,7 +113,7 @@ extern "C" int32_t bj_barycentric_evaluate(bj_ctx* ctx, const uint64_t* const* h
   u64* xs = w1 + n;
   u64* partial = xs + n;
   const unsigned blocks = (unsigned)((n + 255) / 256);
-  bary_denominators_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->tw_fwd, n, at, w0, w1, xs);
+  bary_denominators_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->tw_fwd, n, at, shift, w0, w1, xs);
   BJ_LAUNCH_CHECK(ctx);
   BJ_TRY(bj_batch_inverse_ext(ctx, (uint64_t*)w0, (uint64_t*)w1, n));
   bary_weights_kernel<<<blocks, 256, 0, ctx->stream>>>(w0, w1, xs, n, scale);

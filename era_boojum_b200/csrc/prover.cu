@@ -76,6 +76,32 @@ static int32_t oracle_build(bj_ctx* ctx, Oracle& o, u64 n_leaves, u32 cap_size, 
   return comm_assemble_cap(ctx, local.data(), cap_global, lde_factor, o.cap.data());
 }
 
+// LDE of trace-domain columns (Lagrange values, natural order) onto this context's cosets.  One GPU: bj_lde.  Sharded: the
+// two natural partitions meet here - the iNTT is independent per COLUMN, so rank r interpolates the block of
+// columns [r * per, (r + 1) * per) only, ONE all-gather hands every rank all the monomials (8 * n * n_cols bytes in total), and
+// each rank then evaluates them on its own cosets.  Without it every rank would repeat all the iNTTs (1/9 of the LDE work,
+// which stops scaling).  Columns must be contiguous (stride n).
+static int32_t lde_columns(bj_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, u32 log_n, u32 log_l, u32 n_cols) {
+  const u32 world = comm_world(ctx), rank = comm_rank(ctx);
+  const u64 n = 1ull << log_n;
+  if (world == 1 || n_cols < 2) return bj_lde(ctx, d_in, n, d_out, log_n, log_l, n_cols, 0);
+  const u32 per = (n_cols + world - 1) / world;
+  DevMem mono;
+  BJ_TRY(mono.alloc(ctx, (size_t)world * per * n));
+  const u32 first = std::min(rank * per, n_cols), cnt = std::min(per, n_cols - first);
+  u64* mine = mono.p + (size_t)rank * per * n;
+  if (cnt) {
+    BJ_CUDA(ctx, cudaMemcpyAsync(mine, d_in + (size_t)first * n, sizeof(u64) * cnt * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    BJ_TRY(bj_intt_natural_to_natural(ctx, (uint64_t*)mine, log_n, cnt, n, 1));
+  }
+  if (cnt < per) BJ_CUDA(ctx, cudaMemsetAsync(mine + (size_t)cnt * n, 0, sizeof(u64) * (per - cnt) * n, ctx->stream));
+  BJ_TRY(comm_all_gather(ctx->comm, mine, mono.p, (u64)per * n));  // in place: my block is my slot of the gathered array
+  return bj_lde(ctx, (const uint64_t*)mono.p, n, d_out, log_n, log_l, n_cols, 1);
+}
+
+int32_t copy_permutation_stage2_sharded(bj_ctx* ctx, const uint64_t* const* h_variable_cols, const uint64_t* const* h_sigma_cols, u32 n_cols,
+                                        const uint64_t* h_non_residues, gl::e2 beta, gl::e2 gamma, u32 log_n, u32 chunk_size, u64* d_out);  // stage2.cu
+
 struct GateCopy {
   std::vector<bj_gate_relation> relations;
   std::vector<bj_gate_index> writes;
@@ -231,9 +257,9 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
   const u64 n = 1ull << log_n;
   s->col_len = (n << log_l) / comm_world(ctx);
   BJ_TRY(s->lde.alloc(ctx, (size_t)(V + C + T) * s->col_len));
-  BJ_TRY(bj_lde(ctx, d_sigmas, n, (uint64_t*)s->lde.p, log_n, log_l, V, 0));
-  if (C) BJ_TRY(bj_lde(ctx, d_constants, n, (uint64_t*)s->lde.p + (size_t)V * s->col_len, log_n, log_l, C, 0));
-  if (T) BJ_TRY(bj_lde(ctx, d_lookup_tables, n, (uint64_t*)s->lde.p + (size_t)(V + C) * s->col_len, log_n, log_l, T, 0));
+  BJ_TRY(lde_columns(ctx, d_sigmas, (uint64_t*)s->lde.p, log_n, log_l, V));
+  if (C) BJ_TRY(lde_columns(ctx, d_constants, (uint64_t*)s->lde.p + (size_t)V * s->col_len, log_n, log_l, C));
+  if (T) BJ_TRY(lde_columns(ctx, d_lookup_tables, (uint64_t*)s->lde.p + (size_t)(V + C) * s->col_len, log_n, log_l, T));
   for (uint32_t j = 0; j < V + C + T; j++) s->tree.cols.push_back(s->col(j));
   BJ_TRY(oracle_build(ctx, s->tree, n << log_l, circuit->merkle_tree_cap_size, circuit->tree_hasher, circuit->fri_lde_factor));
   *out = s.release();
@@ -310,7 +336,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   // ---- round 1: witness commitment ----
   DevMem w_lde, m_lde;
   BJ_TRY(w_lde.alloc(ctx, (size_t)V * nL));
-  BJ_TRY(bj_lde(ctx, d_variables, n, (uint64_t*)w_lde.p, log_n, log_l, V, 0));
+  BJ_TRY(lde_columns(ctx, d_variables, (uint64_t*)w_lde.p, log_n, log_l, V));
   std::vector<const uint64_t*> w_cols(V);
   for (uint32_t j = 0; j < V; j++) w_cols[j] = (const uint64_t*)w_lde.p + (size_t)j * nL;
   Oracle w_or;
@@ -345,8 +371,11 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     std::vector<uint64_t> nr(V);
     BJ_TRY(bj_non_residues_for_copy_permutation(n, V, nr.data()));
     const uint64_t b[2] = {beta.c0, beta.c1}, g[2] = {gamma.c0, gamma.c1};
-    BJ_TRY(bj_copy_permutation_stage2(ctx, vp.data(), sp.data(), V, nr.data(), b, g, log_n, Q, (uint64_t*)st2.p, (uint64_t*)st2.p + n,
-                                      (uint64_t*)st2.p + 2 * n));
+    if (world > 1 && n >= (u64)world * 16)  // rows split over the ranks, one all-gather (stage2.cu)
+      BJ_TRY(copy_permutation_stage2_sharded(ctx, vp.data(), sp.data(), V, nr.data(), beta, gamma, log_n, Q, st2.p));
+    else
+      BJ_TRY(bj_copy_permutation_stage2(ctx, vp.data(), sp.data(), V, nr.data(), b, g, log_n, Q, (uint64_t*)st2.p, (uint64_t*)st2.p + n,
+                                        (uint64_t*)st2.p + 2 * n));
     if (lk) {
       std::vector<const uint64_t*> lc(wdt * nsub), tc(T);
       for (uint32_t i = 0; i < wdt * nsub; i++) lc[i] = d_variables + (size_t)(voff + i) * n;
@@ -357,7 +386,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     }
   }
   BJ_TRY(s2_lde.alloc(ctx, (size_t)n_s2 * nL));
-  BJ_TRY(bj_lde(ctx, (const uint64_t*)st2.p, n, (uint64_t*)s2_lde.p, log_n, log_l, n_s2, 0));
+  BJ_TRY(lde_columns(ctx, (const uint64_t*)st2.p, (uint64_t*)s2_lde.p, log_n, log_l, n_s2));
   st2.release();
   std::vector<const uint64_t*> s2_cols(n_s2);
   for (uint32_t j = 0; j < n_s2; j++) s2_cols[j] = (const uint64_t*)s2_lde.p + (size_t)j * nL;
@@ -515,7 +544,17 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     if (flat.empty()) return BJ_OK;
     std::vector<uint64_t> ev(2 * flat.size());
     const uint64_t a[2] = {at.c0, at.c1};
-    BJ_TRY(bj_barycentric_evaluate(ctx, flat.data(), (uint32_t)flat.size(), log_n, a, ev.data()));
+    if (world == 1) {
+      BJ_TRY(bj_barycentric_evaluate(ctx, flat.data(), (uint32_t)flat.size(), log_n, a, ev.data()));
+    } else {
+      // the columns are split over the ranks (every rank opens its block from the coset it owns), results are gathered
+      const size_t per = (flat.size() + world - 1) / world, first = std::min(flat.size(), (size_t)rank * per);
+      const size_t cnt = std::min(per, flat.size() - first);
+      std::vector<uint64_t> mine(2 * per, 0), all(2 * per * world);
+      if (cnt) BJ_TRY(bj_barycentric_evaluate(ctx, flat.data() + first, (uint32_t)cnt, log_n, a, mine.data()));
+      BJ_TRY(comm_all_gather_host(ctx->comm, (const u64*)mine.data(), (u64*)all.data(), 2 * per));
+      memcpy(ev.data(), all.data(), sizeof(uint64_t) * ev.size());   // rank blocks are contiguous: [r][per] == flat order
+    }
     size_t k = 0;
     for (const auto& s : srcs) {
       if (s.c1) {  // f0 + u f1 at an Fp2 point (u^2 = 7)
@@ -530,37 +569,9 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     return BJ_OK;
   };
   std::vector<Src> z_omega_sources{{s2_cols[0], s2_cols[1]}};
-  if (rank == 0) {  // the barycentric evaluation reads coset 0, which rank 0 owns
-    BJ_TRY(open_at(sources, z, pf->values_at_z));
-    BJ_TRY(open_at(z_omega_sources, z_omega, pf->values_at_z_omega));
-    BJ_TRY(open_at(zero_sources, gl::e2{0, 0}, pf->values_at_0));
-  }
-  if (world > 1) {
-    const size_t n_open = sources.size() + z_omega_sources.size() + zero_sources.size();
-    std::vector<u64> flat(2 * n_open);
-    if (rank == 0) {
-      size_t k = 0;
-      for (const auto* vs : {&pf->values_at_z, &pf->values_at_z_omega, &pf->values_at_0})
-        for (const auto& v : *vs) {
-          flat[k++] = v.c0;
-          flat[k++] = v.c1;
-        }
-    }
-    BJ_TRY(comm_broadcast_host(ctx->comm, flat.data(), flat.size(), 0));
-    if (rank != 0) {
-      size_t k = 0;
-      auto take = [&](std::vector<gl::e2>& dst, size_t cnt) {
-        dst.resize(cnt);
-        for (auto& v : dst) {
-          v.c0 = flat[k++];
-          v.c1 = flat[k++];
-        }
-      };
-      take(pf->values_at_z, sources.size());
-      take(pf->values_at_z_omega, z_omega_sources.size());
-      take(pf->values_at_0, zero_sources.size());
-    }
-  }
+  BJ_TRY(open_at(sources, z, pf->values_at_z));
+  BJ_TRY(open_at(z_omega_sources, z_omega, pf->values_at_z_omega));
+  BJ_TRY(open_at(zero_sources, gl::e2{0, 0}, pf->values_at_0));
   for (const auto* vs : {&pf->values_at_z, &pf->values_at_z_omega, &pf->values_at_0})
     for (const auto& v : *vs) {
       const uint64_t e[2] = {v.c0, v.c1};

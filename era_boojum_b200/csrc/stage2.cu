@@ -20,7 +20,8 @@ struct CopyPermParams {
   u32 n_cols;
   u32 chunk;                 // columns per chunk (quotient degree)
   u32 n_chunks;
-  u64 n;
+  u64 n;                     // rows handled by this launch (the whole domain, or one rank's block of rows)
+  u64 row0;                  // global index of the first row (the column pointers are already advanced by row0)
   gl::e2 beta, gamma;
   const u64* xw_lo;          // omega^i = xw_lo[i & mask] * xw_hi[i >> split]
   const u64* xw_hi;
@@ -33,7 +34,8 @@ struct CopyPermParams {
 __global__ void __launch_bounds__(128) copy_perm_ratios_kernel(const CopyPermParams p) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
-  const u64 x = gl::mul(__ldg(p.xw_lo + (i & ((1ull << p.xw_split) - 1))), __ldg(p.xw_hi + (i >> p.xw_split)));
+  const u64 gi = i + p.row0;
+  const u64 x = gl::mul(__ldg(p.xw_lo + (gi & ((1ull << p.xw_split) - 1))), __ldg(p.xw_hi + (gi >> p.xw_split)));
   const gl::e2 bx = {gl::mul(p.beta.c0, x), gl::mul(p.beta.c1, x)};  // beta * x
   gl::e2 num[CP_MAX_CHUNKS], den[CP_MAX_CHUNKS];
   u32 col = 0;
@@ -191,7 +193,110 @@ __global__ void __launch_bounds__(256) copy_perm_partials_kernel(const u64* __re
   }
 }
 
+// v[i] *= s (Fp2), for the row-sharded grand product: the local exclusive prefix times the product of the earlier blocks
+__global__ void __launch_bounds__(256) e2_scale_kernel(u64* __restrict__ c0, u64* __restrict__ c1, u64 n, gl::e2 s) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const gl::e2 r = gl::e2_mul({c0[i], c1[i]}, s);
+  c0[i] = gl::canon(r.c0);
+  c1[i] = gl::canon(r.c1);
+}
+
 int32_t get_pow_tables_public(bj_ctx* ctx, u64 c, int log_n, u64 scale, PowTab* out);  // ntt.cu
+
+// compute_partial_products_in_extension with the ROWS of the trace domain split over the ranks of the context's communicator
+// (multi-GPU): rank r computes the chunk ratios, its exclusive prefix product and the partial products for rows
+// [r * n / world, (r + 1) * n / world); the block totals (one Fp2 each) are exchanged so that every block starts from the
+// product of the earlier ones (and the grand product is checked to be one), then ONE all-gather gives every rank all rows.
+// d_out: [2 + 2 * (n_chunks - 1)][n]  = z.c0, z.c1, then (c0, c1) of every partial product, natural row order.
+int32_t copy_permutation_stage2_sharded(bj_ctx* ctx, const uint64_t* const* h_variable_cols, const uint64_t* const* h_sigma_cols, u32 n_cols,
+                                        const uint64_t* h_non_residues, gl::e2 beta, gl::e2 gamma, u32 log_n, u32 chunk_size, u64* d_out) {
+  const u32 world = comm_world(ctx), rank = comm_rank(ctx);
+  const u64 n = 1ull << log_n;
+  const u32 n_chunks = (n_cols + chunk_size - 1) / chunk_size;
+  if (n_chunks > CP_MAX_CHUNKS) BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "copy permutation: more than 48 chunks");
+  if (n % world || n / world < 1) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "copy permutation: fewer rows than ranks");
+  const u64 rows = n / world, row0 = (u64)rank * rows;
+  const u32 n_out = 2 + 2 * (n_chunks - 1);
+  CopyPermParams p{};
+  void* d;
+  std::vector<const u64*> vp(n_cols), sp(n_cols);
+  for (u32 j = 0; j < n_cols; j++) {
+    vp[j] = (const u64*)h_variable_cols[j] + row0;
+    sp[j] = (const u64*)h_sigma_cols[j] + row0;
+  }
+  BJ_TRY(param_upload(ctx, vp.data(), sizeof(u64*) * n_cols, &d));
+  p.vars = (const u64* const*)d;
+  BJ_TRY(param_upload(ctx, sp.data(), sizeof(u64*) * n_cols, &d));
+  p.sigmas = (const u64* const*)d;
+  std::vector<u64> nr(n_cols);
+  for (u32 i = 0; i < n_cols; i++) nr[i] = gl::canon(h_non_residues[i]);
+  BJ_TRY(param_upload(ctx, nr.data(), sizeof(u64) * n_cols, &d));
+  p.non_residues = (const u64*)d;
+  p.n_cols = n_cols;
+  p.chunk = chunk_size;
+  p.n_chunks = n_chunks;
+  p.n = rows;
+  p.row0 = row0;
+  p.beta = beta;
+  p.gamma = gamma;
+  PowTab pt;
+  BJ_TRY(get_pow_tables_public(ctx, log_n ? gl::omega(log_n) : 1, (int)log_n, 1, &pt));
+  p.xw_lo = pt.lo;
+  p.xw_hi = pt.hi;
+  p.xw_split = pt.split;
+  const u64 per_block = (u64)SCAN_T * SCAN_E;
+  const u32 n_blocks = (u32)((rows + per_block - 1) / per_block);
+  // scratch: ratios [n_chunks][2][rows] | almost_z [2][rows] | block products | total | local result [n_out][rows] | gathered
+  const size_t local_out = (size_t)n_out * rows;
+  const size_t need = sizeof(u64) * ((size_t)n_chunks * 2 * rows + 2 * rows + 2 * (size_t)n_blocks + 2 + local_out + (size_t)world * local_out);
+  BJ_TRY(ensure_scratch(ctx, need));
+  u64* ratios = (u64*)ctx->scratch;
+  u64* az0 = ratios + (size_t)n_chunks * 2 * rows;
+  u64* az1 = az0 + rows;
+  u64* bp = az1 + rows;
+  u64* grand = bp + 2 * (size_t)n_blocks;
+  u64* loc = grand + 2;                 // [n_out][rows]
+  u64* all = loc + local_out;           // [world][n_out][rows]
+  p.ratios = ratios;
+  p.az_c0 = az0;
+  p.az_c1 = az1;
+  copy_perm_ratios_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(p);
+  BJ_LAUNCH_CHECK(ctx);
+  scan_block_products_kernel<<<n_blocks, SCAN_T, 0, ctx->stream>>>(az0, az1, rows, bp);
+  BJ_LAUNCH_CHECK(ctx);
+  scan_of_block_products_kernel<<<1, SCAN_T, 0, ctx->stream>>>(bp, n_blocks, grand);
+  BJ_LAUNCH_CHECK(ctx);
+  scan_apply_kernel<<<n_blocks, SCAN_T, 0, ctx->stream>>>(az0, az1, rows, bp, loc, loc + rows);
+  BJ_LAUNCH_CHECK(ctx);
+  u64 h_total[2];
+  BJ_CUDA(ctx, cudaMemcpyAsync(h_total, grand, sizeof(h_total), cudaMemcpyDeviceToHost, ctx->stream));
+  BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<u64> totals(2 * (size_t)world);
+  BJ_TRY(comm_all_gather_host(ctx->comm, h_total, totals.data(), 2));
+  gl::e2 offset{1, 0}, all_prod{1, 0};
+  for (u32 r = 0; r < world; r++) {
+    const gl::e2 t{gl::canon(totals[2 * r]), gl::canon(totals[2 * r + 1])};
+    if (r < rank) offset = gl::e2_mul(offset, t);
+    all_prod = gl::e2_mul(all_prod, t);
+  }
+  if (gl::canon(all_prod.c0) != 1 || gl::canon(all_prod.c1) != 0)
+    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_copy_permutation_stage2: grand product != 1 (copy constraints are not satisfied)");
+  if (rank) {
+    e2_scale_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(loc, loc + rows, rows, {gl::canon(offset.c0), gl::canon(offset.c1)});
+    BJ_LAUNCH_CHECK(ctx);
+  }
+  if (n_chunks > 1) {
+    copy_perm_partials_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(loc, loc + rows, ratios, n_chunks, rows, loc + 2 * rows);
+    BJ_LAUNCH_CHECK(ctx);
+  }
+  BJ_TRY(comm_all_gather(ctx->comm, loc, all, (u64)local_out));
+  // [rank][col][rows] -> [col][n]
+  for (u32 r = 0; r < world; r++)
+    BJ_CUDA(ctx, cudaMemcpy2DAsync(d_out + (size_t)r * rows, sizeof(u64) * n, all + (size_t)r * local_out, sizeof(u64) * rows, sizeof(u64) * rows, n_out,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+  return BJ_OK;
+}
 
 }  // namespace bj
 

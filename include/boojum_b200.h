@@ -60,7 +60,8 @@ BJ_API int32_t bj_ctx_synchronize(bj_ctx* ctx);
  * bj_quotient_divide_by_vanishing, bj_deep_quotient_group and bj_fri_fold take local buffers (sizes in their signatures
  * stay the GLOBAL domain sizes) and use the domain points of the owned cosets.  Merkle trees are built per rank over the
  * local leaves (a coset is a contiguous subtree: leaf index = coset * n + row, src/cs/implementations/proof.rs:89-91),
- * so caps and query paths are gathered by the caller.  bj_barycentric_evaluate reads coset 0 and is valid on rank 0 only.
+ * so caps and query paths are gathered by the caller.  bj_barycentric_evaluate reads local slot 0 (the global coset `rank`) and
+ * uses that coset's shift, so any rank can open any column - the same value comes out.
  * The reference has no counterpart (its Worker is one machine's thread pool).  Default: rank 0 of 1. */
 BJ_API int32_t bj_ctx_set_coset_shard(bj_ctx* ctx, uint32_t rank, uint32_t world, uint32_t log_lde);
 BJ_API const char* bj_last_error(const bj_ctx* ctx);
@@ -288,7 +289,8 @@ BJ_API int32_t bj_quotient_divide_by_vanishing(bj_ctx* ctx, uint64_t* d_q_c0, ui
 /* ---- openings: values of n_cols base-field polynomials at the Fp2 point `at`, from their first LDE coset
  *      (barycentric evaluation, src/cs/implementations/utils.rs:907-1243; prover.rs:1519-1802).
  * h_cols: host array of device pointers to LDE columns (only the first 2^log_n values, coset 0, are read).
- * h_out: n_cols (c0, c1) pairs.  `at` must not lie on the coset 7<w_n>.  Synchronises. */
+ * h_out: n_cols (c0, c1) pairs.  `at` must not lie on the coset 7<w_n> (on a sharded context: on the coset of local slot 0).
+ * Synchronises. */
 BJ_API int32_t bj_barycentric_evaluate(bj_ctx* ctx, const uint64_t* const* h_cols, uint32_t n_cols, uint32_t log_n,
                                 const uint64_t h_at[2], uint64_t* h_out);
 

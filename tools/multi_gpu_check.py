@@ -68,4 +68,33 @@ if rank == 0:
     from oracle import verifier as OV
     print({"world": world, "prove_log_n": p_log_n, "sharded_proof_equals_single_gpu_proof_on_every_rank": bool(flag.item()),
            "oracle_verifier_accepts": bool(OV.verify(setup.vk(), sharded))})
+del setup, sctx
+torch.cuda.empty_cache()
+
+# ---- the library's own sharded driver: bj_prove on contexts that carry a bj_comm over NCCL (csrc/comm.cu) ----
+nctx = bj.Context.on_current_stream(local)
+comm = bj.Comm.from_torch_distributed(nctx, dist, 8)
+for hasher, transcript in (("poseidon2", "poseidon"), ("blake2s", "blake2s")):
+    cfg = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher=hasher, transcript=transcript)
+    ref = ctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk)
+    want = ref.prove(variables, lk["multiplicities"])
+    ref_cap = ref.get_cap()
+    ref.close()
+    nat = nctx.native_setup(sigmas, constants, gates, Q, cfg, lookup=lk)
+    nat.prove(variables, lk["multiplicities"])
+    torch.cuda.synchronize(); dist.barrier()
+    tm = {}
+    t0 = time.perf_counter()
+    got = nat.prove(variables, lk["multiplicities"], timings=tm)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    same = json.dumps(want, sort_keys=True) == json.dumps(got, sort_keys=True) and np.array_equal(ref_cap, nat.get_cap())
+    flag = torch.tensor([1 if same else 0], device="cuda:%d" % local)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print({"world": world, "native_nccl_sharded_bj_prove": hasher + "+" + transcript, "equals_single_gpu_proof_on_every_rank": bool(flag.item()),
+               "oracle_verifier_accepts": bool(OV.verify(nat.vk(), got)), "seconds": round(dt, 4),
+               "stages_s": {k: round(v, 4) for k, v in tm.items()}})
+    nat.close()
+comm.close()
 dist.destroy_process_group()
