@@ -299,19 +299,24 @@ int32_t bj_fri_oracles_get_challenges(const bj_fri_oracles* o, uint64_t* h_out) 
 // earlier steps exactly as in prover.rs:2236-2262): leaf elements (2 * 2^k u64) and the Merkle path.
 int32_t bj_fri_oracles_query(bj_fri_oracles* o, uint32_t oracle_idx, uint64_t leaf_index, uint64_t* h_leaf_elements,
                              uint64_t* h_path, uint32_t* path_len) {
-  if (!o || oracle_idx >= o->levels.size() || !h_leaf_elements || !h_path || !path_len) return BJ_ERR_INVALID_ARG;
+  return bj_fri_oracles_query_batch(o, oracle_idx, &leaf_index, 1, h_leaf_elements, h_path, path_len);
+}
+
+// the same for n leaves of one oracle with two device round trips in total: h_leaf_elements [n][2 * 2^k], h_paths [n][depth][4]
+int32_t bj_fri_oracles_query_batch(bj_fri_oracles* o, uint32_t oracle_idx, const uint64_t* h_leaf_indices, uint32_t n_indices,
+                                   uint64_t* h_leaf_elements, uint64_t* h_paths, uint32_t* path_len) {
+  if (!o || oracle_idx >= o->levels.size() || !h_leaf_indices || !h_leaf_elements || !h_paths || !path_len) return BJ_ERR_INVALID_ARG;
   bj_ctx* ctx = o->ctx;
   bj::DeviceGuard device_guard(ctx);
   const FriLevel& lv = o->levels[oracle_idx];
   const u64 n_leaves = 1ull << (lv.log_size - lv.log_fold);
-  if (leaf_index >= n_leaves) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_fri_oracles_query: leaf index out of range");
   const uint64_t* srcs[2] = {(const uint64_t*)lv.c0, (const uint64_t*)lv.c1};
-  BJ_TRY(bj_query_leaf_elements(ctx, srcs, 2, 1u << lv.log_fold, n_leaves, &leaf_index, 1, h_leaf_elements));
+  BJ_TRY(bj_query_leaf_elements(ctx, srcs, 2, 1u << lv.log_fold, n_leaves, h_leaf_indices, n_indices, h_leaf_elements));
   const u32 cap_local = o->cap_size / comm_world(ctx);  // the level's tree covers this rank's cosets
   u32 depth = 0;
   while ((n_leaves >> depth) > cap_local) depth++;
   *path_len = depth;
-  return bj_merkle_paths(ctx, (const uint64_t*)lv.leaf_hashes->p, (const uint64_t*)lv.nodes->p, n_leaves, cap_local, &leaf_index, 1, h_path);
+  return bj_merkle_paths(ctx, (const uint64_t*)lv.leaf_hashes->p, (const uint64_t*)lv.nodes->p, n_leaves, cap_local, h_leaf_indices, n_indices, h_paths);
 }
 
 }  // extern "C"

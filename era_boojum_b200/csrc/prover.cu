@@ -721,20 +721,16 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     for (uint32_t lvl = 0; lvl < sched_len; lvl++) {
       const uint32_t k = sched[lvl];
       const size_t le_len = (size_t)2 << k;
-      std::vector<uint64_t> les((size_t)num_queries * le_len, 0), paths((size_t)num_queries * 4 * 40, 0);
-      uint32_t plen = 0;
+      std::vector<uint64_t> les((size_t)num_queries * le_len, 0), locals(num_queries);
       for (uint32_t q = 0; q < num_queries; q++) {
         const uint64_t j = sub[q] >> log_len, i = sub[q] & ((1ull << log_len) - 1);
-        const uint64_t local = owner[q] == rank ? ((((j / world) << log_len) | i) >> k) : 0;
-        uint32_t pl = 0;
-        BJ_TRY(bj_fri_oracles_query(fri, lvl, local, les.data() + (size_t)q * le_len, paths.data() + (size_t)q * 4 * 40, &pl));
-        plen = pl;
+        locals[q] = owner[q] == rank ? ((((j / world) << log_len) | i) >> k) : 0;
         sub[q] >>= k;
       }
-      // compact the paths to [num_queries][plen * 4] before the exchange
-      std::vector<uint64_t> tight((size_t)num_queries * std::max<uint32_t>(plen, 1) * 4, 0);
-      for (uint32_t q = 0; q < num_queries; q++)
-        memcpy(tight.data() + (size_t)q * plen * 4, paths.data() + (size_t)q * 4 * 40, sizeof(uint64_t) * plen * 4);
+      uint32_t plen = 0;
+      std::vector<uint64_t> tight((size_t)num_queries * 40 * 4, 0);  // [num_queries][plen][4] after the call
+      BJ_TRY(bj_fri_oracles_query_batch(fri, lvl, locals.data(), num_queries, les.data(), tight.data(), &plen));
+      tight.resize((size_t)num_queries * std::max<uint32_t>(plen, 1) * 4);
       BJ_TRY(exchange(les, le_len));
       if (plen) BJ_TRY(exchange(tight, (size_t)plen * 4));
       for (uint32_t q = 0; q < num_queries; q++) {

@@ -355,6 +355,9 @@ BJ_API int32_t bj_fri_oracles_get_challenges(const bj_fri_oracles* o, uint64_t* 
  * c0 values then c1 values) and the sibling path (path_len digests, bottom-up, cap level excluded). */
 BJ_API int32_t bj_fri_oracles_query(bj_fri_oracles* o, uint32_t oracle_idx, uint64_t leaf_index, uint64_t* h_leaf_elements,
                              uint64_t* h_path, uint32_t* path_len);
+/* n leaves of one oracle at once (two device round trips): h_leaf_elements [n][2 * 2^k], h_paths [n][*path_len][4] */
+BJ_API int32_t bj_fri_oracles_query_batch(bj_fri_oracles* o, uint32_t oracle_idx, const uint64_t* h_leaf_indices, uint32_t n_indices,
+                                   uint64_t* h_leaf_elements, uint64_t* h_paths, uint32_t* path_len);
 /* Query helpers for the base oracles (witness / stage 2 / quotient / setup): gather the leaf preimages of n_indices
  * leaves (h_out[q][s * elems_per_leaf + e]) and their Merkle paths (h_out[q][depth][4]); both synchronise.  Every source
  * column holds n_leaves * elems_per_leaf elements; an index >= n_leaves is rejected with BJ_ERR_INVALID_ARG (no launch). */
