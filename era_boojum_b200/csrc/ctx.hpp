@@ -79,6 +79,7 @@ struct bj_ctx {
   int ntt_pass1_w = -1;
   int ntt_chunk_mb = 0;
   int ntt_full_pow = 1;          // BJ_NTT_FULL_POW=0 keeps the two-level coset power tables only
+  int ntt_bulk = 0;              // BJ_NTT_BULK=1: experiment, bulk-copy (TMA) staged contiguous pass (ntt_v2.cuh)
   cudaMemPool_t pool = nullptr;  // private stream-ordered pool of the prover driver (keeps freed blocks: no OS round trips per proof)
   bj::CosetShard shard;  // bj_ctx_set_coset_shard; default = the whole domain
   uint32_t shard_log_lde = 0;  // LDE factor the shard was declared for (locates the coset bits of flat indices)

@@ -390,7 +390,10 @@ static int32_t launch_pass(bj_ctx* ctx, const NttPass& p, u32 n_cols) {
   // specialised kernel when one is instantiated for this tile shape and the buffers allow 128-bit accesses
   V2Launch v2;
   const bool aligned = ((((uintptr_t)p.src | (uintptr_t)p.dst) & 15) == 0) && ((p.src_col_stride | p.dst_col_stride) & 1) == 0;
-  if (ctx->ntt_use_v2 && aligned && v2_lookup(p.t, p.w, p.kind, &v2)) {
+  // experiment: bulk-copy (TMA) staged contiguous pass, BJ_NTT_BULK=1 (ntt_v2.cuh)
+  const bool bulk_ok = ctx->ntt_bulk && aligned && p.kind == PASS_TILE && p.w == 0 && p.scale_mode == SCALE_NONE &&
+                       p.log_n - p.r0 - p.t == 0 && ((p.src_col_stride | p.dst_col_stride) & 15) == 0;
+  if (ctx->ntt_use_v2 && aligned && ((bulk_ok && v2_bulk_lookup(p.t, &v2)) || v2_lookup(p.t, p.w, p.kind, &v2))) {
     bool known = false;
     for (void* f : ctx->attr_done) known |= (f == (void*)v2.fn);
     if (!known) {

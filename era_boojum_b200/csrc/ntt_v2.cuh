@@ -256,6 +256,78 @@ __global__ void __launch_bounds__(V2Cfg<T, W>::THREADS, 4) ntt_pass_v2_kernel_r6
   ntt_pass_v2_body<T, W, KIND>(p);
 }
 
+// ---- experiment (north_star: "TMA bulk copies into shared memory for the butterfly tiles"): the contiguous pass (W = 0, no
+// scaling) with its tile moved by the bulk-copy engine instead of through registers.  One elected thread arms an mbarrier with
+// the tile's byte count and issues ONE cp.async.bulk (global -> shared, UBLKCP in SASS); the tile lands densely in a staging
+// buffer, is re-laid into the padded layout the conflict-free register stages need (the bulk engine cannot produce the 17/16
+// padding), and after the stages it is packed back and leaves with one cp.async.bulk (shared -> global).  BJ_NTT_BULK=1 selects
+// it; measured against the register-staged kernel in profiles/r2_ntt_bulk_experiment.txt.
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+template <int T>
+__global__ void __launch_bounds__(V2Cfg<T, 0>::THREADS) ntt_pass_bulk_kernel(const NttPass p) {
+  using C = V2Cfg<T, 0>;
+  extern __shared__ __align__(128) u64 sm[];
+  constexpr int PADDED = (C::E + (C::E >> 4) + 2 + 15) & ~15;   // staging starts 128-byte aligned
+  u64* stage = sm + PADDED;
+  __shared__ __align__(8) unsigned long long bar;
+  const int tid = threadIdx.x;
+  const u32 tile = blockIdx.x;
+  const u64* __restrict__ src = p.src + (u64)blockIdx.y * p.src_col_stride + ((u64)tile << T);
+  u64* __restrict__ dst = p.dst + (u64)blockIdx.y * p.dst_col_stride + ((u64)tile << T);
+  constexpr u32 BYTES = (u32)(sizeof(u64) << T);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(stage)), "l"(src),
+                 "r"(BYTES), "r"(smem_u32(&bar))
+                 : "memory");
+  }
+  {  // every thread waits for the bytes (phase 0)
+    u32 done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+  }
+#pragma unroll 4
+  for (int pi = tid; pi < C::E / 2; pi += C::THREADS) {
+    const ulonglong2 v = reinterpret_cast<const ulonglong2*>(stage)[pi];
+    const int pe = v2_phys(2 * pi);
+    sm[pe] = v.x;
+    sm[pe + 1] = v.y;
+  }
+  __syncthreads();
+  if (p.r0 == 0) v2_stage<T, 0, PASS_TILE, 0, true>(sm, p.tab, tid, tile, tile, p.r0);
+  else v2_stage<T, 0, PASS_TILE, 0, false>(sm, p.tab, tid, tile, tile, p.r0);
+#pragma unroll 4
+  for (int pi = tid; pi < C::E / 2; pi += C::THREADS) {
+    const int pe = v2_phys(2 * pi);
+    ulonglong2 v;
+    v.x = sm[pe];
+    v.y = sm[pe + 1];
+    if (p.canon_out) {
+      v.x = gl::canon(v.x);
+      v.y = gl::canon(v.y);
+    }
+    reinterpret_cast<ulonglong2*>(stage)[pi] = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes visible to the bulk-copy (async) proxy
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stage)), "r"(BYTES) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer must outlive the copy's reads
+  }
+}
+
+template <int T>
+struct V2BulkCfg {
+  static constexpr size_t SMEM = sizeof(u64) * (size_t)(((V2Cfg<T, 0>::E + (V2Cfg<T, 0>::E >> 4) + 2 + 15) & ~15) + V2Cfg<T, 0>::E);
+};
+
 typedef void (*V2KernelPtr)(const NttPass);
 
 template <int T, int W, int KIND>
@@ -281,6 +353,19 @@ struct V2Launch {
     out->smem = V2Cfg<TT, WW>::SMEM;                                                         \
     return true;                                                                             \
   }
+
+static bool v2_bulk_lookup(int t, V2Launch* out) {
+#define BJ_V2_BULK_CASE(TT)                        \
+  if (t == TT) {                                   \
+    out->fn = ntt_pass_bulk_kernel<TT>;            \
+    out->threads = V2Cfg<TT, 0>::THREADS;          \
+    out->smem = V2BulkCfg<TT>::SMEM;               \
+    return true;                                   \
+  }
+  BJ_V2_BULK_CASE(10) BJ_V2_BULK_CASE(11) BJ_V2_BULK_CASE(12) BJ_V2_BULK_CASE(13)
+#undef BJ_V2_BULK_CASE
+  return false;
+}
 
 // instantiation menu (see make_plan): contiguous last passes, strided front passes, transposed last passes
 static bool v2_lookup(int t, int w, int kind, V2Launch* out) {

@@ -92,6 +92,28 @@ def test_ntt_config1_2pow16_forward_inverse(bj, ctx):
         assert np.array_equal(bj.to_numpy(d), a % np.uint64(P))
 
 
+@pytest.mark.parametrize("log_n", [14, 20, 22, 24])
+def test_ntt_bulk_copy_staged_pass_matches_oracle(bj, log_n, monkeypatch):
+    """BJ_NTT_BULK=1: the contiguous pass moved by cp.async.bulk + mbarrier (the TMA experiment, ntt_v2.cuh) gives the same
+    transform bit for bit (forward with and without coset, inverse, LDE)."""
+    monkeypatch.setenv("BJ_NTT_BULK", "1")
+    c = bj.Context.on_current_stream(0)
+    try:
+        a = O.random_field(rng(900 + log_n), (2, 1 << log_n))
+        for coset in (1, 7):
+            d = bj.to_device(a)
+            c.fft_natural_to_bitreversed(d, coset)
+            assert np.array_equal(bj.to_numpy(d), O.ntt_n2b(a, coset))
+        d = bj.to_device(a)
+        c.ifft_natural_to_natural(d, 7)
+        assert np.array_equal(bj.to_numpy(d), O.intt_n2n(a, 7))
+        if log_n <= 20:
+            assert np.array_equal(bj.to_numpy(c.transform_raw_storages_to_lde(bj.to_device(a), 4)), O.lde(a, 2))
+    finally:
+        c.synchronize()
+        c.close()
+
+
 def test_ntt_strided_batch(bj, ctx):
     """columns separated by a stride larger than n (col_stride argument of the C-ABI)."""
     import ctypes

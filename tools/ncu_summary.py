@@ -24,4 +24,14 @@ for r in rows[2:]:
             if v >= 3:
                 stalls.append((v, h.replace('smsp__warp_issue_stalled_', '').replace('_per_warp_active.pct', '')))
     print('stalls(% of warp-active cycles):', ', '.join('%s=%.0f' % (n, v) for v, n in sorted(stalls, reverse=True)))
+    per_issue = []
+    for i, h in enumerate(hdr):
+        if 'issue_stalled' in h and h.endswith('_per_issue_active.ratio'):
+            try:
+                v = float(r[i])
+            except ValueError:
+                continue
+            if v >= 0.3:
+                per_issue.append((v, h.split('issue_stalled_')[1].replace('_per_issue_active.ratio', '')))
+    print('stalls (warps per issue):', ', '.join('%s %.2f' % (n, v) for v, n in sorted(per_issue, reverse=True)))
     print('---')

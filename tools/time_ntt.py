@@ -32,6 +32,13 @@ for m in (20, 21, 22, 23, 24):
     r["inv_coset7"] = el / timed(lambda: ctx.ifft_natural_to_natural(d, 7)) / 1e6
     res["2^%d" % m] = {k: round(v, 2) for k, v in r.items()}
     del d
+# the same transform on a batch that fits in L2 (2 columns of 2^22 = 64 MiB < 126 MB): if the kernel waited for HBM this would
+# be much faster than the 1 GiB batch above - it is not (the passes are bound by the integer pipes)
+m = 22
+d = torch.randint(0, 2**63 - 1, (2, 1 << m), dtype=torch.int64, device="cuda:0")
+res["2^22_l2_resident_2cols"] = {"fwd_plain": round((2 << m) / timed(lambda: ctx.fft_natural_to_bitreversed(d, 1), reps=50) / 1e6, 2),
+                                 "fwd_coset7": round((2 << m) / timed(lambda: ctx.fft_natural_to_bitreversed(d, 7), reps=50) / 1e6, 2)}
+del d
 for m in (20, 22):
     cols = 1 << (24 - m)
     d = torch.randint(0, 2**63 - 1, (cols, 1 << m), dtype=torch.int64, device="cuda:0")
