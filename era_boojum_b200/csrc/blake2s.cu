@@ -13,18 +13,25 @@ using gl::u32;
 __constant__ u32 c_blake2s_iv[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
 __device__ __forceinline__ u32 rotr32(u32 x, int r) { return __funnelshift_r(x, x, r); }
 
-#define BJ_B2S_G(a, b, c, d, x, y) \
-  a = a + b + (x);                 \
-  d = rotr32(d ^ a, 16);           \
-  c = c + d;                       \
-  b = rotr32(b ^ c, 12);           \
-  a = a + b + (y);                 \
-  d = rotr32(d ^ a, 8);            \
-  c = c + d;                       \
+// Pipe balance (ncu, profiles/r2_ncu_b2s_summary.txt): the G function is xor / rotate / add only, all of which ptxas issues on
+// the ALU pipe (LOP3, SHF, IADD3: ALU 90 % busy, FMA 10 %) except half of the adds.  An addition is also a multiply-add by 1,
+// which runs on the FMA pipe; ptxas folds a literal 1 back into IADD3, so the 1 arrives as a kernel parameter (`one`) it cannot
+// see through.  All six two-input additions of a G then issue as IMAD: ALU 16 cycles per G instead of 20.
+__device__ __forceinline__ u32 add_fma(u32 a, u32 b, u32 one) { return a * one + b; }
+
+#define BJ_B2S_G(a, b, c, d, x, y)                  \
+  a = add_fma(b, add_fma(x, a, one), one);          \
+  d = rotr32(d ^ a, 16);                            \
+  c = add_fma(d, c, one);                           \
+  b = rotr32(b ^ c, 12);                            \
+  a = add_fma(b, add_fma(y, a, one), one);          \
+  d = rotr32(d ^ a, 8);                             \
+  c = add_fma(d, c, one);                           \
   b = rotr32(b ^ c, 7);
 
-// one compression: h updated in place; m = 16 message words, t = byte counter (low 32 bits suffice up to 4 GiB), last flag
-__device__ __forceinline__ void blake2s_compress(u32 (&h)[8], const u32 (&m)[16], u32 t_lo, u32 t_hi, bool last) {
+// one compression: h updated in place; m = 16 message words, t = byte counter (low 32 bits suffice up to 4 GiB), last flag;
+// one == 1 (opaque to the compiler, see above)
+__device__ __forceinline__ void blake2s_compress(u32 (&h)[8], const u32 (&m)[16], u32 t_lo, u32 t_hi, bool last, u32 one = 1) {
   u32 v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
   u32 v8 = c_blake2s_iv[0], v9 = c_blake2s_iv[1], v10 = c_blake2s_iv[2], v11 = c_blake2s_iv[3];
   u32 v12 = c_blake2s_iv[4] ^ t_lo, v13 = c_blake2s_iv[5] ^ t_hi;
@@ -70,7 +77,7 @@ __device__ __forceinline__ void blake2s_store(const u32 (&h)[8], u64* out) {
 
 // leaf m absorbs source_s[m*epl + e] (8 LE bytes of the canonical value each), s = 0..n_src-1, e = 0..epl-1
 __global__ void __launch_bounds__(128) blake2s_leaf_kernel(const u64* const* __restrict__ srcs, u32 n_src, u64 n_leaves, int log_epl,
-                                                            u64* __restrict__ digests) {
+                                                            u64* __restrict__ digests, u32 one) {
   const u64 leaf = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (leaf >= n_leaves) return;
   u32 h[8];
@@ -91,12 +98,12 @@ __global__ void __launch_bounds__(128) blake2s_leaf_kernel(const u64* const* __r
     }
     const bool last = blk + 1 == n_blocks;
     const u64 t = last ? total * 8 : (blk + 1) * 64;
-    blake2s_compress(h, m, (u32)t, (u32)(t >> 32), last);
+    blake2s_compress(h, m, (u32)t, (u32)(t >> 32), last, one);
   }
   blake2s_store(h, digests + 4 * leaf);
 }
 
-__global__ void __launch_bounds__(128) blake2s_node_kernel(const u64* __restrict__ prev, u64 n_out, u64* __restrict__ next) {
+__global__ void __launch_bounds__(128) blake2s_node_kernel(const u64* __restrict__ prev, u64 n_out, u64* __restrict__ next, u32 one) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
   u32 h[8], m[16];
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(128) blake2s_node_kernel(const u64* __restrict
     m[2 * k] = (u32)v;
     m[2 * k + 1] = (u32)(v >> 32);
   }
-  blake2s_compress(h, m, 64u, 0u, true);
+  blake2s_compress(h, m, 64u, 0u, true, one);
   blake2s_store(h, next + 4 * i);
 }
 
@@ -129,14 +136,14 @@ extern "C" int32_t bj_merkle_build_blake2s(bj_ctx* ctx, const uint64_t* const* h
   int log_epl = 0;
   while ((1u << log_epl) < elems_per_leaf) log_epl++;
   blake2s_leaf_kernel<<<(unsigned)((n_leaves + 127) / 128), 128, 0, ctx->stream>>>((const u64* const*)d_src, n_sources, n_leaves, log_epl,
-                                                                                   (u64*)d_leaf_hashes);
+                                                                                   (u64*)d_leaf_hashes, ctx->one);
   BJ_LAUNCH_CHECK(ctx);
   const u64* prev = (const u64*)d_leaf_hashes;
   u64 cnt = n_leaves, written = 0;
   while (cnt > cap_size) {
     const u64 next = cnt / 2;
     u64* dst = (u64*)d_nodes + 4 * written;
-    blake2s_node_kernel<<<(unsigned)((next + 127) / 128), 128, 0, ctx->stream>>>(prev, next, dst);
+    blake2s_node_kernel<<<(unsigned)((next + 127) / 128), 128, 0, ctx->stream>>>(prev, next, dst, ctx->one);
     BJ_LAUNCH_CHECK(ctx);
     prev = dst;
     written += next;

@@ -84,6 +84,18 @@ struct bj_comm {
   bj_comm_group* group = nullptr;
   bj::u64* stage = nullptr;  // device staging for the host-buffer collectives
   size_t stage_u64 = 0;
+  // second stream for collectives that overlap with compute on the context's stream (NCCL transport)
+  cudaStream_t aux = nullptr;
+  std::vector<cudaEvent_t> events;  // pool, grown on demand
+  size_t next_event = 0;
+  cudaEvent_t event() {
+    if (next_event == events.size()) {
+      cudaEvent_t e = nullptr;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      events.push_back(e);
+    }
+    return events[next_event++ % events.size()];
+  }
 };
 
 namespace bj {
@@ -134,6 +146,36 @@ int32_t comm_all_gather(bj_comm* c, const u64* d_send, u64* d_recv, u64 n) {
       BJ_CUDA(ctx, cudaMemcpyAsync(d_recv + (size_t)r * n, g->slots[r], sizeof(u64) * n, cudaMemcpyDeviceToDevice, ctx->stream));
   BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   g->barrier();  // every rank has read every send buffer: they may be reused
+  return BJ_OK;
+}
+
+// The same all-gather issued on the communicator's auxiliary stream: it starts when the work enqueued so far on the context's
+// stream is done, and returns an event the caller makes the context's stream wait for (comm_wait) right before it consumes
+// d_recv - compute enqueued in between overlaps with the transfer.  The local transport has no streams to overlap: it runs
+// the blocking all-gather and returns a null event.
+int32_t comm_all_gather_overlapped(bj_comm* c, const u64* d_send, u64* d_recv, u64 n, cudaEvent_t* done) {
+  *done = nullptr;
+  if (c->world == 1 || !c->nccl) return comm_all_gather(c, d_send, d_recv, n);
+  bj_ctx* ctx = c->ctx;
+  if (!c->aux) BJ_CUDA(ctx, cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+  if (c->events.size() < 64) {
+    while (c->events.size() < 64) {
+      cudaEvent_t e = nullptr;
+      BJ_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->events.push_back(e);
+    }
+  }
+  cudaEvent_t ready = c->event(), fin = c->event();
+  BJ_CUDA(ctx, cudaEventRecord(ready, ctx->stream));
+  BJ_CUDA(ctx, cudaStreamWaitEvent(c->aux, ready, 0));
+  BJ_NCCL(c, nccl_api().AllGather(d_send, d_recv, (size_t)n, NCCL_UINT64, c->nccl, c->aux));
+  BJ_CUDA(ctx, cudaEventRecord(fin, c->aux));
+  *done = fin;
+  return BJ_OK;
+}
+int32_t comm_wait(bj_comm* c, cudaEvent_t done) {
+  if (!done) return BJ_OK;
+  BJ_CUDA(c->ctx, cudaStreamWaitEvent(c->ctx->stream, done, 0));
   return BJ_OK;
 }
 
@@ -290,8 +332,11 @@ int32_t bj_comm_destroy(bj_comm* c) {
   bj_ctx* ctx = c->ctx;
   bj::DeviceGuard device_guard(ctx);
   cudaStreamSynchronize(ctx->stream);
+  if (c->aux) cudaStreamSynchronize(c->aux);
   if (c->nccl) nccl_api().CommDestroy(c->nccl);
   if (c->stage) cudaFree(c->stage);
+  for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+  if (c->aux) cudaStreamDestroy(c->aux);
   if (ctx->comm == c) {
     ctx->comm = nullptr;
     bj_ctx_set_coset_shard(ctx, 0, 1, ctx->shard_log_lde);

@@ -79,6 +79,7 @@ struct bj_ctx {
   int ntt_pass1_w = -1;
   int ntt_chunk_mb = 0;
   int ntt_full_pow = 1;          // BJ_NTT_FULL_POW=0 keeps the two-level coset power tables only
+  uint32_t one = 1;              // a 1 the compiler cannot see (passed as a kernel parameter): additions written as multiply-adds by it issue on the FMA pipe (blake2s.cu)
   int ntt_bulk = 0;              // BJ_NTT_BULK=1: experiment, bulk-copy (TMA) staged contiguous pass (ntt_v2.cuh)
   cudaMemPool_t pool = nullptr;  // private stream-ordered pool of the prover driver (keeps freed blocks: no OS round trips per proof)
   bj::CosetShard shard;  // bj_ctx_set_coset_shard; default = the whole domain
@@ -140,6 +141,8 @@ int32_t ensure_scratch(bj_ctx* ctx, size_t bytes);
 // collectives of the sharded prover (comm.cu); all no-ops / plain copies for a world of one
 int32_t comm_all_gather(bj_comm* c, const u64* d_send, u64* d_recv, u64 n);
 int32_t comm_all_gather_host(bj_comm* c, const u64* h_send, u64* h_recv, u64 n);
+int32_t comm_all_gather_overlapped(bj_comm* c, const u64* d_send, u64* d_recv, u64 n, cudaEvent_t* done);
+int32_t comm_wait(bj_comm* c, cudaEvent_t done);
 int32_t comm_broadcast_host(bj_comm* c, u64* h_buf, u64 n, uint32_t root);
 uint32_t comm_world(const bj_ctx* ctx);
 uint32_t comm_rank(const bj_ctx* ctx);

@@ -85,18 +85,45 @@ static int32_t lde_columns(bj_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, u
   const u32 world = comm_world(ctx), rank = comm_rank(ctx);
   const u64 n = 1ull << log_n;
   if (world == 1 || n_cols < 2) return bj_lde(ctx, d_in, n, d_out, log_n, log_l, n_cols, 0);
-  const u32 per = (n_cols + world - 1) / world;
-  DevMem mono;
-  BJ_TRY(mono.alloc(ctx, (size_t)world * per * n));
-  const u32 first = std::min(rank * per, n_cols), cnt = std::min(per, n_cols - first);
-  u64* mine = mono.p + (size_t)rank * per * n;
-  if (cnt) {
-    BJ_CUDA(ctx, cudaMemcpyAsync(mine, d_in + (size_t)first * n, sizeof(u64) * cnt * n, cudaMemcpyDeviceToDevice, ctx->stream));
-    BJ_TRY(bj_intt_natural_to_natural(ctx, (uint64_t*)mine, log_n, cnt, n, 1));
+  // software pipeline over groups of columns: while the all-gather of group g travels over NVLink (auxiliary stream), this
+  // rank interpolates its share of group g + 1 and evaluates group g - 1 on its cosets
+  const u64 out_stride = (n << log_l) / world;
+  const u32 group = std::max<u32>(world, ((n_cols + 3) / 4 + world - 1) / world * world);  // <= 4 groups, a multiple of world
+  struct Group {
+    u32 c0, cnt, per;
+    DevMem mono;
+    cudaEvent_t gathered = nullptr;
+  };
+  std::vector<std::unique_ptr<Group>> groups;
+  for (u32 c0 = 0; c0 < n_cols; c0 += group) {
+    groups.emplace_back(new Group());
+    groups.back()->c0 = c0;
+    groups.back()->cnt = std::min(group, n_cols - c0);
+    groups.back()->per = (groups.back()->cnt + world - 1) / world;
   }
-  if (cnt < per) BJ_CUDA(ctx, cudaMemsetAsync(mine + (size_t)cnt * n, 0, sizeof(u64) * (per - cnt) * n, ctx->stream));
-  BJ_TRY(comm_all_gather(ctx->comm, mine, mono.p, (u64)per * n));  // in place: my block is my slot of the gathered array
-  return bj_lde(ctx, (const uint64_t*)mono.p, n, d_out, log_n, log_l, n_cols, 1);
+  auto start = [&](Group& g) -> int32_t {
+    BJ_TRY(g.mono.alloc(ctx, (size_t)world * g.per * n));
+    const u32 first = std::min(rank * g.per, g.cnt), cnt = std::min(g.per, g.cnt - first);
+    u64* mine = g.mono.p + (size_t)rank * g.per * n;
+    if (cnt) {
+      BJ_CUDA(ctx, cudaMemcpyAsync(mine, d_in + (size_t)(g.c0 + first) * n, sizeof(u64) * cnt * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      BJ_TRY(bj_intt_natural_to_natural(ctx, (uint64_t*)mine, log_n, cnt, n, 1));
+    }
+    if (cnt < g.per) BJ_CUDA(ctx, cudaMemsetAsync(mine + (size_t)cnt * n, 0, sizeof(u64) * (g.per - cnt) * n, ctx->stream));
+    // in place: my block is my slot of the gathered array
+    return comm_all_gather_overlapped(ctx->comm, mine, g.mono.p, (u64)g.per * n, &g.gathered);
+  };
+  auto finish = [&](Group& g) -> int32_t {
+    BJ_TRY(comm_wait(ctx->comm, g.gathered));
+    BJ_TRY(bj_lde(ctx, (const uint64_t*)g.mono.p, n, d_out + (size_t)g.c0 * out_stride, log_n, log_l, g.cnt, 1));
+    g.mono.release();
+    return BJ_OK;
+  };
+  for (size_t i = 0; i < groups.size(); i++) {
+    BJ_TRY(start(*groups[i]));
+    if (i) BJ_TRY(finish(*groups[i - 1]));
+  }
+  return finish(*groups.back());
 }
 
 int32_t copy_permutation_stage2_sharded(bj_ctx* ctx, const uint64_t* const* h_variable_cols, const uint64_t* const* h_sigma_cols, u32 n_cols,
@@ -108,11 +135,20 @@ struct GateCopy {
   std::vector<uint8_t> path;
 };
 
+static inline void json_u64(std::string& s, u64 v) {  // decimal digits straight into the string (std::to_string allocates)
+  char buf[24];
+  int k = 24;
+  do {
+    buf[--k] = (char)('0' + v % 10);
+    v /= 10;
+  } while (v);
+  s.append(buf + k, 24 - k);
+}
 static void json_u64_list(std::string& s, const u64* v, size_t n) {
   s += '[';
   for (size_t i = 0; i < n; i++) {
     if (i) s += ',';
-    s += std::to_string(v[i]);
+    json_u64(s, v[i]);
   }
   s += ']';
 }
@@ -129,7 +165,7 @@ static void json_digests(std::string& s, const u64* v, size_t n_digests, bool as
     s += '[';
     for (int b = 0; b < 32; b++) {
       if (b) s += ',';
-      s += std::to_string((unsigned)((v[4 * i + b / 8] >> (8 * (b % 8))) & 0xff));
+      json_u64(s, (v[4 * i + b / 8] >> (8 * (b % 8))) & 0xff);
     }
     s += ']';
   }
@@ -139,7 +175,11 @@ static void json_ext_list(std::string& s, const std::vector<gl::e2>& v) {
   s += '[';
   for (size_t i = 0; i < v.size(); i++) {
     if (i) s += ',';
-    s += "{\"coeffs\":[" + std::to_string(v[i].c0) + "," + std::to_string(v[i].c1) + "],\"_marker\":null}";
+    s += "{\"coeffs\":[";
+    json_u64(s, v[i].c0);
+    s += ',';
+    json_u64(s, v[i].c1);
+    s += "],\"_marker\":null}";
   }
   s += ']';
 }
