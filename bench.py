@@ -121,6 +121,29 @@ def run_reference(args, rank, world):
     }))
 
 
+def host_cpu_quota():
+    """CPUs this process may actually use: the affinity mask, capped by the cgroup CPU quota when one is set (a container
+    that sees 128 logical CPUs but is throttled to a few cores runs 128 threads no faster than 8)."""
+    allowed = len(os.sched_getaffinity(0))
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                                  # cgroup v2
+            q, period = f.read().split()
+        if q != "max":
+            quota = float(q) / float(period)
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:                 # cgroup v1
+                q = float(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                period = float(f.read())
+            if q > 0:
+                quota = q / period
+        except Exception:
+            pass
+    return allowed, quota
+
+
 def cpu_baseline_sample():
     """the oracle port (one serial radix-2 NTT per column, columns over a thread pool) on the box's host
     cores; rows for 8 threads (the reference bench pins Worker::new_with_num_threads(8), src/gadgets/sha256/mod.rs:307) and for
@@ -157,13 +180,14 @@ def cpu_baseline_sample():
                      "sample": "%d x (%d columns of 2^22, forward NTT coset 7, tables built once per batch), %.1f s" % (reps, cols, dt)})
         del a
     best = max(rows, key=lambda r: r["value"])
+    _, quota = host_cpu_quota()
     return {"value": best["value"], "unit": "Gelem/s", "cores": best["cores"], "kind": "port", "sample": best["sample"],
-            "rows": rows, "twiddle_assert_loop_s_per_stage_2^22": round(t_assert, 4),
+            "cgroup_cpu_quota_cores": quota, "rows": rows, "twiddle_assert_loop_s_per_stage_2^22": round(t_assert, 4),
             "note": "rows: 8 threads = Worker::new_with_num_threads(8) of the reference bench, all cores = Worker::new(); "
                     "value_with_reference_twiddle_recompute adds the serial assert loop of precompute_twiddles_for_fft per batch call"}
 
 
-def cpu_prove_stage_baseline(log_n=22, total_cols=93, budget_cols=24):
+def cpu_prove_stage_baseline(log_n=22, total_cols=93, budget_cols=12):
     """CPU beside the proof seconds (BASELINE.md section 3 'Prove: seconds per stage'): the oracle port's witness-commit stage
     (LDE to 8 cosets + Poseidon2 leaf/node hashing, cap 16), one DEEP group over those columns and the FRI fold chain, for the
     2^22-row shape, all allowed host threads.  To stay within a bounded sample the LDE / tree / DEEP run over `budget_cols`

@@ -129,6 +129,7 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
   ctx->ntt_use_v2 = env_int("BJ_NTT_V2", 1);
   ctx->ntt_full_pow = env_int("BJ_NTT_FULL_POW", 1);
   ctx->ntt_bulk = env_int("BJ_NTT_BULK", 0);
+  ctx->ntt_l2_persist = env_int("BJ_NTT_L2_PERSIST", 1);
   ctx->ntt_chunk_mb = env_int("BJ_NTT_CHUNK_MB", 0);
   {
     // the prover driver allocates tens of GB per proof: a private pool that never trims keeps the second and later
