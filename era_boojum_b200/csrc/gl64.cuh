@@ -93,6 +93,30 @@ __host__ __device__ __forceinline__ u64 sub(u64 a, u64 b) {
   return sub_c(a, b);
 #endif
 }
+// add() with the wrap correction on the ALU pipe (negate + add chain) instead of the FMA pipe (multiply-add by EPS).
+// The NTT butterfly is FMA-pipe bound with every "* EPS" written as a multiply-add (50 FMA-pipe vs 38 ALU-pipe cycles per
+// warp-butterfly, profiles/r1_ubench_integer_pipes.txt); moving ONE of its four corrections back to the ALU pipe balances the
+// two pipes (44 / 44).  Same contract as add(): a lazy, b <= p -> lazy.
+__host__ __device__ __forceinline__ u64 add_alu(u64 a, u64 b) {
+#ifdef BJ_GL_PTX
+  u32 a0, a1, b0, b1, lo, hi;
+  unpack2(a, a0, a1);
+  unpack2(b, b0, b1);
+  asm("{\n\t.reg .u32 c, m;\n\t"
+      "add.cc.u32 %0, %2, %4;\n\t"
+      "addc.cc.u32 %1, %3, %5;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "neg.s32 m, c;\n\t"            // m = carry ? 0xffffffff : 0  (= carry * EPS, the low word; the high word of EPS is 0)
+      "add.cc.u32 %0, %0, m;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(lo), "=&r"(hi)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return pack2(lo, hi);
+#else
+  return add_c(a, b);
+#endif
+}
 __host__ __device__ __forceinline__ u64 add_lazy(u64 a, u64 b) { return add(a, canon(b)); }
 __host__ __device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) { return sub(a, canon(b)); }
 __host__ __device__ __forceinline__ u64 neg(u64 a) {

@@ -6,6 +6,11 @@
 #pragma once
 #include "ntt.cuh"
 
+// pipe balance of the butterfly: 1 = the sum's wrap correction on the ALU pipe (gl::add_alu), 0 = on the FMA pipe (gl::add)
+#ifndef BJ_NTT_ADD_ALU
+#define BJ_NTT_ADD_ALU 1
+#endif
+
 namespace bj {
 
 using gl::u32;
@@ -72,7 +77,11 @@ __device__ __forceinline__ void v2_round(u64 (&x)[16], const u64* __restrict__ t
     if (FIRST && (j0 >> (4 - Q)) == 0) v = gl::canon(x[j1]);
     else v = gl::mul(x[j1], tw[j0 >> (4 - Q)]);
     x[j1] = gl::sub(x[j0], v);
+#if BJ_NTT_ADD_ALU
+    x[j0] = gl::add_alu(x[j0], v);
+#else
     x[j0] = gl::add(x[j0], v);
+#endif
   }
 }
 
