@@ -442,6 +442,13 @@ class Context:
         self._check(lib.bj_pow_blake2s(self._h, seed, len(seed_bytes), pow_bits, ctypes.byref(out)))
         return int(out.value)
 
+    def pow_keccak256(self, seed_bytes, pow_bits):
+        """impl PoWRunner for Keccak256 (cs/implementations/pow.rs:140-230)."""
+        seed = (ctypes.c_uint8 * max(1, len(seed_bytes)))(*seed_bytes)
+        out = ctypes.c_uint64()
+        self._check(lib.bj_pow_keccak256(self._h, seed, len(seed_bytes), pow_bits, ctypes.byref(out)))
+        return int(out.value)
+
     # ---- setup / witness materialisation ----
     def materialize_variables_polynomials_from_dense_hint(self, all_values, hint, log_n):
         """witness.rs:325-385.  all_values: [n_values] CUDA tensor; hint: [n_cols, hint_rows] CUDA tensor of reference

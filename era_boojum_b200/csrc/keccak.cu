@@ -103,4 +103,63 @@ void bj_host_keccak256(const uint8_t* data, size_t n, uint8_t out[32]) {
   h.finalize_reset(out);
 }
 
+// ---- proof of work: impl PoWRunner for Keccak256 (src/cs/implementations/pow.rs:140-230): find a u64 `challenge` such that the
+// first 8 bytes (LE) of Keccak-256(seed || challenge.to_le_bytes()) have >= pow_bits trailing zero bits.  Same scheme as the
+// Blake2s runner (bj_pow_blake2s): one thread per candidate, 2^24 candidates per launch, the smallest hit of the first
+// successful batch is returned.  seed || nonce (<= 120 bytes) is a single rate block.
 }  // extern "C"
+
+namespace bj {
+__global__ void __launch_bounds__(256) keccak_pow_kernel(const uint8_t* __restrict__ seed, u32 seed_len, u64 base, u32 pow_bits,
+                                                          unsigned long long* __restrict__ best) {
+  const u64 nonce = base + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  uint8_t msg[136];
+#pragma unroll 1
+  for (int i = 0; i < 136; i++) msg[i] = 0;
+  for (u32 i = 0; i < seed_len; i++) msg[i] = seed[i];
+  for (int k = 0; k < 8; k++) msg[seed_len + k] = (uint8_t)(nonce >> (8 * k));
+  msg[seed_len + 8] |= 0x01;
+  msg[135] |= 0x80;
+  uint64_t st[25];
+#pragma unroll
+  for (int i = 0; i < 25; i++) st[i] = 0;
+  for (int i = 0; i < 17; i++) {
+    uint64_t w = 0;
+    for (int k = 0; k < 8; k++) w |= (uint64_t)msg[8 * i + k] << (8 * k);
+    st[i] = w;
+  }
+  keccak_f1600(st);
+  const bool ok = pow_bits == 0 || (st[0] << (64 - pow_bits)) == 0;
+  if (ok) atomicMin(best, (unsigned long long)nonce);
+}
+}  // namespace bj
+
+extern "C" int32_t bj_pow_keccak256(bj_ctx* ctx, const uint8_t* h_seed, uint32_t seed_len, uint32_t pow_bits, uint64_t* h_challenge) {
+  bj::DeviceGuard device_guard(ctx);
+  if (!ctx || (!h_seed && seed_len) || !h_challenge || pow_bits > 32 || seed_len > 120)
+    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_pow_keccak256: bad argument (pow_bits <= 32, seed <= 120 bytes)");
+  uint8_t padded[128] = {0};
+  memcpy(padded, h_seed, seed_len);
+  void* d_seed;
+  BJ_TRY(param_upload(ctx, padded, sizeof(padded), &d_seed));
+  struct Best {
+    unsigned long long* d = nullptr;
+    ~Best() {
+      if (d) cudaFree(d);
+    }
+  } best_buf;
+  BJ_CUDA(ctx, cudaMalloc(&best_buf.d, sizeof(unsigned long long)));
+  const unsigned long long none = ~0ull;
+  const u64 batch = 1ull << 24;
+  unsigned long long best = none;
+  for (u64 base = 0; best == none; base += batch) {
+    if (base >= (1ull << 40)) BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "bj_pow_keccak256: no solution found");
+    BJ_CUDA(ctx, cudaMemcpyAsync(best_buf.d, &none, sizeof(none), cudaMemcpyHostToDevice, ctx->stream));
+    keccak_pow_kernel<<<(unsigned)(batch / 256), 256, 0, ctx->stream>>>((const uint8_t*)d_seed, seed_len, base, pow_bits, best_buf.d);
+    BJ_LAUNCH_CHECK(ctx);
+    BJ_CUDA(ctx, cudaMemcpyAsync(&best, best_buf.d, sizeof(best), cudaMemcpyDeviceToHost, ctx->stream));
+    BJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  *h_challenge = best;
+  return BJ_OK;
+}

@@ -97,9 +97,11 @@ SIGNATURES = {
     "bj_fri_oracles_get_monomials": (_i32, [_vp, _vp, _vp]),
     "bj_fri_oracles_get_challenges": (_i32, [_vp, _vp]),
     "bj_fri_oracles_query": (_i32, [_vp, _u32, _u64, _vp, _vp, _vp]),
+    "bj_fri_oracles_query_batch": (_i32, [_vp, _u32, _vp, _u32, _vp, _vp, _vp]),
     "bj_query_leaf_elements": (_i32, [_vp, _vp, _u32, _u32, _u64, _vp, _u32, _vp]),
     "bj_merkle_paths": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _u32, _vp]),
     "bj_pow_blake2s": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "bj_pow_keccak256": (_i32, [_vp, _vp, _u32, _u32, _vp]),
     "bj_materialize_columns": (_i32, [_vp, _vp, _u64, _vp, _u32, _u64, _u32, _vp]),
     "bj_create_permutation_polys": (_i32, [_vp, _vp, _u32, _u32, _vp]),
     "bj_comm_unique_id": (_i32, [_vp]),

@@ -372,6 +372,8 @@ BJ_API int32_t bj_merkle_paths(bj_ctx* ctx, const uint64_t* d_leaf_hashes, const
  * string of run_from_field_elements (the LE bytes of the reduced field elements; 5 challenges = 40 bytes in
  * prove_cpu_basic, prover.rs:2109-2126).  Synchronises. */
 BJ_API int32_t bj_pow_blake2s(bj_ctx* ctx, const uint8_t* h_seed, uint32_t seed_len, uint32_t pow_bits, uint64_t* h_challenge);
+/* impl PoWRunner for Keccak256 (pow.rs:140-230): the same search with Keccak-256 (seed <= 120 bytes) */
+BJ_API int32_t bj_pow_keccak256(bj_ctx* ctx, const uint8_t* h_seed, uint32_t seed_len, uint32_t pow_bits, uint64_t* h_challenge);
 
 /* ---- setup / witness materialisation on the device (what feeds bj_setup_create and bj_prove) ----
  * Variable encoding as in the reference (src/cs/mod.rs:44-47, :155-180): a u64 whose bit 63 marks a placeholder and whose

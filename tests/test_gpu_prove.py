@@ -445,6 +445,23 @@ def test_pow_blake2s_kernel_and_proof_with_pow_bits(env):
         OV.verify(setup.vk(), bad)
 
 
+def test_pow_keccak256_kernel(env):
+    """PoWRunner for Keccak256 (pow.rs:140-230) on the GPU against the pure-Python Keccak-256 of the oracle: the nonce solves
+    the puzzle and, for the serial range of the reference (<= 16 bits), is the smallest one."""
+    from oracle.keccak import keccak256
+    bj, ctx, prover, synthetic = env
+    for seed, bits in ((b"", 1), (bytes(range(40)), 10), (bytes(range(7)), 18), (bytes(range(120)), 6), (b"abc", 0)):
+        nonce = ctx.pow_keccak256(seed, bits)
+        first = int.from_bytes(keccak256(seed + nonce.to_bytes(8, "little"))[:8], "little")
+        assert first & ((1 << bits) - 1) == 0
+        if bits <= 10:
+            for c in range(nonce):
+                f = int.from_bytes(keccak256(seed + c.to_bytes(8, "little"))[:8], "little")
+                assert f & ((1 << bits) - 1) != 0
+    with pytest.raises(bj.BoojumError):
+        ctx.pow_keccak256(bytes(121), 4)
+
+
 def test_keccak256_hasher_and_transcript(env):
     """H = Keccak256, TR = Keccak256Transcript (the third TreeHasher / transcript pair of the reference): both drivers agree
     and the oracle verifier (pure-Python Keccak-256) accepts."""
