@@ -117,6 +117,28 @@ __host__ __device__ __forceinline__ u64 add_alu(u64 a, u64 b) {
   return add_c(a, b);
 #endif
 }
+// sub() with the borrow correction written as multiply-adds (FMA pipe): t - EPS == t + 0xFFFFFFFF00000001 (mod 2^64), i.e.
+// lo += bb, hi += bb * 0xffffffff + carry with bb = 1 on borrow.  Same contract as sub(): a lazy, b <= p -> lazy.
+__host__ __device__ __forceinline__ u64 sub_fma(u64 a, u64 b) {
+#ifdef BJ_GL_PTX
+  u32 a0, a1, b0, b1, lo, hi;
+  unpack2(a, a0, a1);
+  unpack2(b, b0, b1);
+  asm("{\n\t.reg .u32 m, bb;\n\t"
+      "sub.cc.u32 %0, %2, %4;\n\t"
+      "subc.cc.u32 %1, %3, %5;\n\t"
+      "subc.u32 m, 0, 0;\n\t"          // m = borrow ? 0xffffffff : 0
+      "and.b32 bb, m, 1;\n\t"
+      "mad.lo.cc.u32 %0, bb, 0x1, %0;\n\t"
+      "madc.lo.u32 %1, bb, 0xffffffff, %1;\n\t"
+      "}"
+      : "=&r"(lo), "=&r"(hi)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+  return pack2(lo, hi);
+#else
+  return sub_c(a, b);
+#endif
+}
 __host__ __device__ __forceinline__ u64 add_lazy(u64 a, u64 b) { return add(a, canon(b)); }
 __host__ __device__ __forceinline__ u64 sub_lazy(u64 a, u64 b) { return sub(a, canon(b)); }
 __host__ __device__ __forceinline__ u64 neg(u64 a) {
@@ -298,6 +320,61 @@ __host__ __device__ __forceinline__ u64 w96_reduce(w96 a) {
   u64 r = a.lo + t1;
   if (r < t1) r += EPS;  // hi * EPS < 2^64 - 2^33, so the wrapped sum + EPS cannot wrap again
   return r;
+#endif
+}
+
+// a * k for a 32-bit k, exact, as a 96-bit value: two 32x32->64 multiply-adds instead of the four of a full product.
+// Further small terms can be added with w96_add64 before the single w96_reduce (the sum must stay below 2^96).
+__host__ __device__ __forceinline__ w96 mul_u32_wide(u64 a, u32 k) {
+  const u64 p0 = (u64)(u32)a * k;
+  const u64 p1 = (u64)(u32)(a >> 32) * k + (p0 >> 32);  // < 2^64: (2^32-1)^2 + 2^32 - 1
+  return {(p1 << 32) | (u32)p0, (u32)(p1 >> 32)};
+}
+
+// a * b + c (all lazy) -> lazy: the addend enters the 128-bit product before its single reduction (a*b + c < 2^128)
+__host__ __device__ __forceinline__ u64 fma_lazy(u64 a, u64 b, u64 c) {
+#ifdef BJ_GL_PTX
+  u32 a0, a1, b0, b1, c0, c1, v0, v1;
+  unpack2(a, a0, a1);
+  unpack2(b, b0, b1);
+  unpack2(c, c0, c1);
+  asm("{\n\t"
+      ".reg .u64 p0, p1, p2, p3, z;\n\t"
+      ".reg .u32 r0, r1, r2, r3, x, y, w, c, bb;\n\t"
+      "mul.wide.u32 p0, %2, %4;\n\t"
+      "mov.b64 {r0, x}, p0;\n\t"
+      "cvt.u64.u32 z, x;\n\t"
+      "mad.wide.u32 p1, %2, %5, z;\n\t"
+      "mov.b64 {x, y}, p1;\n\t"
+      "cvt.u64.u32 z, x;\n\t"
+      "mad.wide.u32 p2, %3, %4, z;\n\t"
+      "mov.b64 {r1, w}, p2;\n\t"
+      "cvt.u64.u32 z, y;\n\t"
+      "mad.wide.u32 p3, %3, %5, z;\n\t"
+      "cvt.u64.u32 z, w;\n\t"
+      "add.u64 p3, p3, z;\n\t"
+      "mov.b64 {r2, r3}, p3;\n\t"
+      // + c into the four limbs
+      "add.cc.u32 r0, r0, %6;\n\t"
+      "addc.cc.u32 r1, r1, %7;\n\t"
+      "addc.cc.u32 r2, r2, 0;\n\t"
+      "addc.u32 r3, r3, 0;\n\t"
+      "mad.lo.cc.u32 %0, r2, 0xffffffff, r0;\n\t"
+      "madc.hi.cc.u32 %1, r2, 0xffffffff, r1;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "mad.lo.cc.u32 %0, c, 0xffffffff, %0;\n\t"
+      "madc.hi.u32 %1, c, 0xffffffff, %1;\n\t"
+      "sub.cc.u32 %0, %0, r3;\n\t"
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 bb, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, bb;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=&r"(v0), "=&r"(v1)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c0), "r"(c1));
+  return pack2(v0, v1);
+#else
+  return add_c(mul_c(a, b), canon(c));
 #endif
 }
 

@@ -6,9 +6,15 @@
 #pragma once
 #include "ntt.cuh"
 
-// pipe balance of the butterfly: 1 = the sum's wrap correction on the ALU pipe (gl::add_alu), 0 = on the FMA pipe (gl::add)
+// Pipe balance of the butterfly (A/B builds, profiles/r2_ntt_bulk_experiment.txt section D):
+//   BJ_NTT_ADD_ALU = 1: the sum's wrap correction on the ALU pipe (gl::add_alu) instead of the FMA pipe (gl::add): measured
+//                       0.5-1 % SLOWER (ncu: the ALU pipe is the busier one, 63-66 % vs 39 %), so 0 is shipped;
+//   BJ_NTT_SUB_FMA = 1: the difference's borrow correction as multiply-adds (gl::sub_fma) instead of the sub chain (gl::sub).
 #ifndef BJ_NTT_ADD_ALU
-#define BJ_NTT_ADD_ALU 1
+#define BJ_NTT_ADD_ALU 0
+#endif
+#ifndef BJ_NTT_SUB_FMA
+#define BJ_NTT_SUB_FMA 0
 #endif
 
 namespace bj {
@@ -76,7 +82,11 @@ __device__ __forceinline__ void v2_round(u64 (&x)[16], const u64* __restrict__ t
     u64 v;
     if (FIRST && (j0 >> (4 - Q)) == 0) v = gl::canon(x[j1]);
     else v = gl::mul(x[j1], tw[j0 >> (4 - Q)]);
+#if BJ_NTT_SUB_FMA
+    x[j1] = gl::sub_fma(x[j0], v);
+#else
     x[j1] = gl::sub(x[j0], v);
+#endif
 #if BJ_NTT_ADD_ALU
     x[j0] = gl::add_alu(x[j0], v);
 #else

@@ -66,16 +66,22 @@ __global__ void __launch_bounds__(128) quotient_copy_perm_kernel(const QCopyPerm
     lhs = {gl::canon(lhs.c0), gl::canon(lhs.c1)};
     rhs = {gl::canon(rhs.c0), gl::canon(rhs.c1)};
     for (u32 j = 0; j < p.chunk && col < p.n_cols; j++, col++) {
-      const u64 w = gl::canon(p.vars[col][t]);
+      const u64 w = p.vars[col][t];
       const u64 s = p.sigmas[col][t];
       const u64 k = __ldg(p.non_residues + col);
-      gl::e2 b = {gl::mul(p.beta.c0, s), gl::mul(p.beta.c1, s)};
-      b.c0 = gl::canon(gl::add(gl::add(b.c0, w), p.gamma.c0));
-      b.c1 = gl::canon(gl::add(b.c1, p.gamma.c1));
+      const u64 wg = gl::add_lazy(p.gamma.c0, w);                      // w + gamma.c0 (lazy), shared by both factors
+      // w + beta sigma + gamma: the addend rides in the product's 128 bits (one reduction per component)
+      const gl::e2 b = {gl::fma_lazy(p.beta.c0, s, wg), gl::fma_lazy(p.beta.c1, s, p.gamma.c1)};
       lhs = gl::e2_mul(lhs, b);
-      gl::e2 a = {gl::mul(bx.c0, k), gl::mul(bx.c1, k)};
-      a.c0 = gl::canon(gl::add(gl::add(a.c0, w), p.gamma.c0));
-      a.c1 = gl::canon(gl::add(a.c1, p.gamma.c1));
+      // w + (beta x) k + gamma: the non-residues are small integers (make_non_residues counts up from 2, utils.rs:636-688), so
+      // the product is a 64 x 32 bit one kept in 96 bits together with the addend; full product for an unexpectedly large k
+      gl::e2 a;
+      if (k >> 31) {
+        a = {gl::fma_lazy(bx.c0, k, wg), gl::fma_lazy(bx.c1, k, p.gamma.c1)};
+      } else {
+        a = {gl::w96_reduce(gl::w96_add64(gl::mul_u32_wide(bx.c0, (u32)k), wg)),
+             gl::w96_reduce(gl::w96_add64(gl::mul_u32_wide(bx.c1, (u32)k), p.gamma.c1))};
+      }
       rhs = gl::e2_mul(rhs, a);
     }
     gl::e2 d = {gl::canon(gl::sub(lhs.c0, rhs.c0)), gl::canon(gl::sub(lhs.c1, rhs.c1))};

@@ -42,17 +42,20 @@ __global__ void __launch_bounds__(128) copy_perm_ratios_kernel(const CopyPermPar
   for (u32 c = 0; c < p.n_chunks; c++) {
     gl::e2 nu = {1, 0}, de = {1, 0};
     for (u32 j = 0; j < p.chunk && col < p.n_cols; j++, col++) {
-      const u64 w = gl::canon(p.vars[col][i]);
+      const u64 w = p.vars[col][i];
       const u64 s = p.sigmas[col][i];
       const u64 k = __ldg(p.non_residues + col);
-      // w + beta k x + gamma
-      gl::e2 a = {gl::mul(bx.c0, k), gl::mul(bx.c1, k)};
-      a.c0 = gl::canon(gl::add(gl::add(a.c0, w), p.gamma.c0));
-      a.c1 = gl::canon(gl::add(a.c1, p.gamma.c1));
-      // w + beta sigma + gamma
-      gl::e2 b = {gl::mul(p.beta.c0, s), gl::mul(p.beta.c1, s)};
-      b.c0 = gl::canon(gl::add(gl::add(b.c0, w), p.gamma.c0));
-      b.c1 = gl::canon(gl::add(b.c1, p.gamma.c1));
+      const u64 wg = gl::add_lazy(p.gamma.c0, w);  // w + gamma.c0 (lazy), shared by numerator and denominator
+      // w + beta k x + gamma: k is a small integer (make_non_residues), 64 x 32 bit product kept in 96 bits with the addend
+      gl::e2 a;
+      if (k >> 31) {
+        a = {gl::fma_lazy(bx.c0, k, wg), gl::fma_lazy(bx.c1, k, p.gamma.c1)};
+      } else {
+        a = {gl::w96_reduce(gl::w96_add64(gl::mul_u32_wide(bx.c0, (u32)k), wg)),
+             gl::w96_reduce(gl::w96_add64(gl::mul_u32_wide(bx.c1, (u32)k), p.gamma.c1))};
+      }
+      // w + beta sigma + gamma: the addend rides in the product's 128 bits
+      const gl::e2 b = {gl::fma_lazy(p.beta.c0, s, wg), gl::fma_lazy(p.beta.c1, s, p.gamma.c1)};
       nu = gl::e2_mul(nu, a);
       de = gl::e2_mul(de, b);
     }
