@@ -412,6 +412,10 @@ def main():
         e2e = {"value": round(world * elems_per_step / (e_ms * 1e-3) / 1e9, 4), "unit": "Gelem/s",
                "h2d_bytes_per_step": 8 * elems_per_step, "d2h_bytes_per_step": 8 * elems_per_step,
                "ms_per_step": round(e_ms, 3), "steps": k, "host_affinity": numa}
+        if world > 1:   # every rank's CPU binding (the e2e path is host-memory bound: placement per rank matters)
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, numa)
+            e2e["host_affinity_per_rank"] = per_rank
         del host
 
     out = {
@@ -538,6 +542,34 @@ def main():
         # Blake2s256 tree hasher + Blake2sTranscript
         out["prove"] = dict(common, **prove_once("poseidon2", "poseidon"))
         out["prove_non_recursive"] = dict(common, **prove_once("blake2s", "blake2s"))
+        if world > 1:
+            # strong scaling of the proof, measured in this run: rank 0 proves the same circuit alone (its own unsharded context)
+            # while the other ranks wait; efficiency = t(1 GPU) / (N * t(N GPUs))
+            single = {}
+            if rank == 0:
+                sctx = bj.Context.on_current_stream(local_rank)
+                for key, (hasher, transcript) in (("prove", ("poseidon2", "poseidon")), ("prove_non_recursive", ("blake2s", "blake2s"))):
+                    cfg1 = prover.ProofConfig(fri_lde_factor=8, merkle_tree_cap_size=16, security_level=100, hasher=hasher, transcript=transcript)
+                    s1 = sctx.native_setup(sigmas, constants, gates, Q, cfg1, lookup=lk)
+                    s1.prove(variables, lk["multiplicities"], as_json=True)
+                    best1 = None
+                    for _ in range(2):
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        s1.prove(variables, lk["multiplicities"], as_json=True)
+                        torch.cuda.synchronize()
+                        dt1 = time.perf_counter() - t0
+                        best1 = dt1 if best1 is None else min(best1, dt1)
+                    single[key] = best1
+                    s1.close()
+                    torch.cuda.empty_cache()
+                sctx.close()
+            barrier()
+            if rank == 0:
+                for key, t1 in single.items():
+                    out[key]["single_gpu_seconds_same_run"] = round(t1, 4)
+                    out[key]["speedup_vs_single_gpu"] = round(t1 / out[key]["seconds"], 2)
+                    out[key]["strong_scaling_efficiency"] = round(t1 / out[key]["seconds"] / world, 3)
         del variables, sigmas, constants, lk
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_sample()

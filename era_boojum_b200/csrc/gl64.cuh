@@ -423,6 +423,13 @@ __host__ __device__ __forceinline__ e2 e2_mul(e2 a, e2 b) {
   u64 c0 = canon(add(v0, mul7(v1)));
   return {c0, c1};
 }
+// Fp2 product with LAZY inputs and LAZY outputs (for chains of products whose end is canonicalised once): the two closing
+// canonicalisations are dropped and 7 v1 + v0 is one 64 x 3 bit product kept in 96 bits with the addend (one reduction).
+__host__ __device__ __forceinline__ e2 e2_mul_lazy(e2 a, e2 b) {
+  const u64 v0 = mul(a.c0, b.c0), v1 = mul(a.c1, b.c1);
+  const u64 s = mul(add_lazy(a.c0, a.c1), add_lazy(b.c0, b.c1));
+  return {w96_reduce(w96_add64(mul_u32_wide(v1, 7u), v0)), sub(sub(s, v0), v1)};
+}
 __host__ __device__ __forceinline__ e2 e2_mul_base(e2 a, u64 b) { return {mul(a.c0, b), mul(a.c1, b)}; }
 __host__ __device__ __forceinline__ e2 e2_sqr(e2 a) { return e2_mul(a, a); }
 __host__ __device__ inline e2 e2_inv(e2 a) {

@@ -724,36 +724,25 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     owner[q] = (uint32_t)(j % world);
     loc_idx[q] = owner[q] == rank ? (((j / world) << log_n) | i) : 0;
   }
-  auto exchange = [&](std::vector<uint64_t>& buf, size_t rec_len) -> int32_t {  // buf: [num_queries][rec_len]
-    if (world == 1) return BJ_OK;
-    std::vector<uint64_t> all((size_t)world * buf.size());
-    BJ_TRY(comm_all_gather_host(ctx->comm, (const u64*)buf.data(), (u64*)all.data(), buf.size()));
-    for (uint32_t q = 0; q < num_queries; q++)
-      memcpy(buf.data() + (size_t)q * rec_len, all.data() + (size_t)owner[q] * buf.size() + (size_t)q * rec_len, sizeof(uint64_t) * rec_len);
-    return BJ_OK;
+  // every answer part (leaf elements / path of one oracle) is gathered locally first; ONE exchange then carries all of them
+  struct Part {
+    std::vector<uint64_t> data;  // [num_queries][rec_len]
+    size_t rec_len;
   };
+  std::vector<Part> parts;  // order: (rows, path) of the 4 base oracles, then (leaf elements, path) of every FRI level
   const Oracle* base[4] = {&w_or, &s2_or, &qt_or, &setup->tree};
   for (const Oracle* o : base) {
     const size_t row_len = o->cols.size();
     uint32_t depth = 0;
     while ((o->n_leaves >> depth) > o->cap_size) depth++;
-    const size_t plen = (size_t)(depth ? depth : 1) * 4;
-    std::vector<uint64_t> rows((size_t)num_queries * row_len), paths((size_t)num_queries * plen);
-    BJ_TRY(bj_query_leaf_elements(ctx, o->cols.data(), (uint32_t)row_len, 1, o->n_leaves, loc_idx.data(), num_queries, rows.data()));
-    if (depth) {
-      std::vector<uint64_t> tight((size_t)num_queries * depth * 4);
+    Part rows{std::vector<uint64_t>((size_t)num_queries * row_len), row_len};
+    Part path{std::vector<uint64_t>((size_t)num_queries * depth * 4), (size_t)depth * 4};
+    BJ_TRY(bj_query_leaf_elements(ctx, o->cols.data(), (uint32_t)row_len, 1, o->n_leaves, loc_idx.data(), num_queries, rows.data.data()));
+    if (depth)
       BJ_TRY(bj_merkle_paths(ctx, (const uint64_t*)o->leaf_hashes.p, (const uint64_t*)o->nodes.p, o->n_leaves, o->cap_size, loc_idx.data(),
-                             num_queries, tight.data()));
-      paths = tight;
-    }
-    BJ_TRY(exchange(rows, row_len));
-    if (depth) BJ_TRY(exchange(paths, (size_t)depth * 4));
-    for (uint32_t q = 0; q < num_queries; q++) {
-      QueryAnswer a;
-      a.leaf_elements.assign(rows.begin() + (size_t)q * row_len, rows.begin() + (size_t)(q + 1) * row_len);
-      a.path.assign(paths.begin() + (size_t)q * depth * 4, paths.begin() + (size_t)(q + 1) * depth * 4);
-      pf->queries[q].push_back(std::move(a));
-    }
+                             num_queries, path.data.data()));
+    parts.push_back(std::move(rows));
+    parts.push_back(std::move(path));
   }
   {
     uint32_t log_len = log_n;  // coset length of the level's codeword
@@ -761,25 +750,48 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     for (uint32_t lvl = 0; lvl < sched_len; lvl++) {
       const uint32_t k = sched[lvl];
       const size_t le_len = (size_t)2 << k;
-      std::vector<uint64_t> les((size_t)num_queries * le_len, 0), locals(num_queries);
+      std::vector<uint64_t> locals(num_queries);
       for (uint32_t q = 0; q < num_queries; q++) {
         const uint64_t j = sub[q] >> log_len, i = sub[q] & ((1ull << log_len) - 1);
         locals[q] = owner[q] == rank ? ((((j / world) << log_len) | i) >> k) : 0;
         sub[q] >>= k;
       }
       uint32_t plen = 0;
-      std::vector<uint64_t> tight((size_t)num_queries * 40 * 4, 0);  // [num_queries][plen][4] after the call
-      BJ_TRY(bj_fri_oracles_query_batch(fri, lvl, locals.data(), num_queries, les.data(), tight.data(), &plen));
-      tight.resize((size_t)num_queries * std::max<uint32_t>(plen, 1) * 4);
-      BJ_TRY(exchange(les, le_len));
-      if (plen) BJ_TRY(exchange(tight, (size_t)plen * 4));
-      for (uint32_t q = 0; q < num_queries; q++) {
-        QueryAnswer a;
-        a.leaf_elements.assign(les.begin() + (size_t)q * le_len, les.begin() + (size_t)(q + 1) * le_len);
-        a.path.assign(tight.begin() + (size_t)q * plen * 4, tight.begin() + (size_t)(q + 1) * plen * 4);
-        pf->queries[q].push_back(std::move(a));
-      }
+      Part les{std::vector<uint64_t>((size_t)num_queries * le_len, 0), le_len};
+      Part path{std::vector<uint64_t>((size_t)num_queries * 40 * 4, 0), 0};  // [num_queries][plen][4] after the call
+      BJ_TRY(bj_fri_oracles_query_batch(fri, lvl, locals.data(), num_queries, les.data.data(), path.data.data(), &plen));
+      path.rec_len = (size_t)plen * 4;
+      path.data.resize((size_t)num_queries * path.rec_len);
+      parts.push_back(std::move(les));
+      parts.push_back(std::move(path));
       log_len -= k;
+    }
+  }
+  if (world > 1) {
+    size_t total = 0;
+    for (const auto& pt : parts) total += pt.data.size();
+    std::vector<uint64_t> mine(total), all((size_t)world * total);
+    size_t off = 0;
+    for (const auto& pt : parts) {
+      if (!pt.data.empty()) memcpy(mine.data() + off, pt.data.data(), sizeof(uint64_t) * pt.data.size());
+      off += pt.data.size();
+    }
+    BJ_TRY(comm_all_gather_host(ctx->comm, (const u64*)mine.data(), (u64*)all.data(), total));
+    off = 0;
+    for (auto& pt : parts) {
+      for (uint32_t q = 0; q < num_queries && pt.rec_len; q++)
+        memcpy(pt.data.data() + (size_t)q * pt.rec_len, all.data() + (size_t)owner[q] * total + off + (size_t)q * pt.rec_len,
+               sizeof(uint64_t) * pt.rec_len);
+      off += pt.data.size();
+    }
+  }
+  for (size_t o = 0; o + 1 < parts.size(); o += 2) {
+    const Part &le = parts[o], &pa = parts[o + 1];
+    for (uint32_t q = 0; q < num_queries; q++) {
+      QueryAnswer a;
+      a.leaf_elements.assign(le.data.begin() + (size_t)q * le.rec_len, le.data.begin() + (size_t)(q + 1) * le.rec_len);
+      a.path.assign(pa.data.begin() + (size_t)q * pa.rec_len, pa.data.begin() + (size_t)(q + 1) * pa.rec_len);
+      pf->queries[q].push_back(std::move(a));
     }
   }
   BJ_TRY(mark(5));

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) quotient_copy_perm_kernel(const QCopyPerm
       const u64 wg = gl::add_lazy(p.gamma.c0, w);                      // w + gamma.c0 (lazy), shared by both factors
       // w + beta sigma + gamma: the addend rides in the product's 128 bits (one reduction per component)
       const gl::e2 b = {gl::fma_lazy(p.beta.c0, s, wg), gl::fma_lazy(p.beta.c1, s, p.gamma.c1)};
-      lhs = gl::e2_mul(lhs, b);
+      lhs = gl::e2_mul_lazy(lhs, b);
       // w + (beta x) k + gamma: the non-residues are small integers (make_non_residues counts up from 2, utils.rs:636-688), so
       // the product is a 64 x 32 bit one kept in 96 bits together with the addend; full product for an unexpectedly large k
       gl::e2 a;
@@ -82,9 +82,9 @@ __global__ void __launch_bounds__(128) quotient_copy_perm_kernel(const QCopyPerm
         a = {gl::w96_reduce(gl::w96_add64(gl::mul_u32_wide(bx.c0, (u32)k), wg)),
              gl::w96_reduce(gl::w96_add64(gl::mul_u32_wide(bx.c1, (u32)k), p.gamma.c1))};
       }
-      rhs = gl::e2_mul(rhs, a);
+      rhs = gl::e2_mul_lazy(rhs, a);
     }
-    gl::e2 d = {gl::canon(gl::sub(lhs.c0, rhs.c0)), gl::canon(gl::sub(lhs.c1, rhs.c1))};
+    gl::e2 d = {gl::canon(gl::sub_lazy(lhs.c0, rhs.c0)), gl::canon(gl::sub_lazy(lhs.c1, rhs.c1))};
     d = gl::e2_mul(d, {__ldg(p.alphas + 2 * (c + 1)), __ldg(p.alphas + 2 * (c + 1) + 1)});
     q = {gl::canon(gl::add(q.c0, d.c0)), gl::canon(gl::add(q.c1, d.c1))};
   }

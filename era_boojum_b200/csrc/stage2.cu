@@ -56,11 +56,11 @@ __global__ void __launch_bounds__(128) copy_perm_ratios_kernel(const CopyPermPar
       }
       // w + beta sigma + gamma: the addend rides in the product's 128 bits
       const gl::e2 b = {gl::fma_lazy(p.beta.c0, s, wg), gl::fma_lazy(p.beta.c1, s, p.gamma.c1)};
-      nu = gl::e2_mul(nu, a);
-      de = gl::e2_mul(de, b);
+      nu = gl::e2_mul_lazy(nu, a);
+      de = gl::e2_mul_lazy(de, b);
     }
-    num[c] = nu;
-    den[c] = de;
+    num[c] = gl::e2_canon(nu);
+    den[c] = gl::e2_canon(de);
   }
   // invert all chunk denominators with one inversion (Montgomery trick inside the thread)
   gl::e2 pre[CP_MAX_CHUNKS];
