@@ -187,7 +187,7 @@ def cpu_baseline_sample():
                     "value_with_reference_twiddle_recompute adds the serial assert loop of precompute_twiddles_for_fft per batch call"}
 
 
-def cpu_prove_stage_baseline(log_n=22, total_cols=93, budget_cols=12):
+def cpu_prove_stage_baseline(log_n=22, total_cols=93, budget_cols=8):
     """CPU beside the proof seconds (BASELINE.md section 3 'Prove: seconds per stage'): the oracle port's witness-commit stage
     (LDE to 8 cosets + Poseidon2 leaf/node hashing, cap 16), one DEEP group over those columns and the FRI fold chain, for the
     2^22-row shape, all allowed host threads.  To stay within a bounded sample the LDE / tree / DEEP run over `budget_cols`
