@@ -2,10 +2,13 @@
 """bench.py - headline measurement for the Boojum polynomial-commitment hot path on B200.
 
 metric  : Goldilocks NTT G-elements/s (BASELINE.json metric, first half).  The second half, proof-generation seconds
-          at 2^22 rows at N GPUs, is reported in the extra objects "prove" (Poseidon2 tree + Poseidon transcript: configs[4]) and
-          "prove_non_recursive" (Blake2s tree + transcript: configs[3]) on a synthetic SHA-256-bench-shaped circuit (the
-          real circuit needs the Rust synthesiser); one GPU runs the library's C++ driver bj_prove, several GPUs the
-          coset-sharded prover over NCCL.  "merkle" reports configs[2]; "ntt_family" the inverse / LDE figures of configs[1].
+          at 2^22 rows at N GPUs, is reported in the extra objects "prove" (configs[4]'s type parameters: Poseidon2 tree hasher +
+          Poseidon (v1) sponge transcript) and "prove_non_recursive" (configs[3]: Blake2s tree + Blake2sTranscript) on a synthetic
+          SHA-256-bench-shaped circuit (the real circuit needs the Rust synthesiser); the library's C++ driver bj_prove runs on
+          one GPU or coset-sharded over a bj_comm (NCCL) on N; every timed proof is checked by the oracle's restated verifier
+          after the timed region ("verified"), the witness H2D is reported beside it, and on N > 1 GPUs rank 0 also times the
+          single-GPU proof in the same run ("strong_scaling_efficiency").  "merkle" reports configs[2]; "ntt_family" the inverse /
+          LDE figures of configs[1]; "prove.cpu_baseline_s" the CPU port's stage times.
 workload: BASELINE.json configs[1] "2^20-2^24 Goldilocks NTT/LDE sweep on 1xB200": one step = forward
           natural->bit-reversed NTT on coset 7 (benches/benchmarks.rs:541 uses coset 7) of five resident batches,
           n = 2^20..2^24 with 128/64/32/16/8 columns (1 GiB each, SURVEY.md 8(d) cfg 2), in place, through the
