@@ -86,12 +86,19 @@ __host__ __device__ __forceinline__ u64 p2_pow7(u64 x) {
 
 // s <- (diag(2^sh) + J) s + constants of layer `layer`; `x7` = new s[0] (S-box output), rest_sum = s[1] + ... + s[11]
 // (computed by the caller before the S-box so that it is off the critical path)
+// ALL12 = false: only element 0 takes a constant (the layer is followed by another partial round: 21 of the 22 internal
+// layers), which drops 11 constant loads + 96-bit additions per layer; ALL12 = true: the layer before the first closing full
+// round (layer 26) adds all twelve.
+template <bool ALL12>
 __host__ __device__ __forceinline__ void p2_internal(u64 (&s)[12], gl::w96 rest_sum, int layer) {
   constexpr unsigned SH[12] = {4, 14, 11, 8, 0, 5, 2, 9, 13, 6, 3, 12};
   const u64 sr = gl::w96_reduce(gl::w96_add64(rest_sum, s[0]));
 #pragma unroll
-  for (int i = 0; i < 12; i++)
-    s[i] = gl::w96_reduce(gl::w96_add64(gl::w96_add64(gl::w96_from_shl(s[i], SH[i]), sr), BJ_P2_LRC(layer * 12 + i)));
+  for (int i = 0; i < 12; i++) {
+    gl::w96 t = gl::w96_add64(gl::w96_from_shl(s[i], SH[i]), sr);
+    if (ALL12 || i == 0) t = gl::w96_add64(t, BJ_P2_LRC(layer * 12 + i));
+    s[i] = gl::w96_reduce(t);
+  }
 }
 
 // 30 rounds (4 full, 22 partial, 4 full; state_generic_impl.rs:219-233) as ONE loop with two bodies so that the code
@@ -113,7 +120,8 @@ __host__ __device__ __forceinline__ void poseidon2_permutation(u64 (&s)[12]) {
       rest2 = gl::w96_add64(gl::w96_add(rest2, rest3), s[11]);
       rest = gl::w96_add(gl::w96_add(rest, rest2), rest4);
       s[0] = p2_pow7(s[0]);
-      p2_internal(s, rest, r + 1);
+      if (r == 25) p2_internal<true>(s, rest, r + 1);
+      else p2_internal<false>(s, rest, r + 1);
     }
   }
 }
