@@ -598,8 +598,10 @@ int32_t bj_lde(bj_ctx* ctx, const uint64_t* d_in, uint64_t in_col_stride, uint64
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_lde: bad argument");
   if (n_cols == 0) return BJ_OK;
   const u64 n = 1ull << log_n, L = 1ull << log_lde;
-  if (ctx->shard.log_stride && log_lde != ctx->shard_log_lde)
-    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_lde: LDE factor differs from the one the coset shard was declared for");
+  // a coset shard owns the cosets j = first (mod world) of ANY factor >= world (the first L cosets of a larger domain are the
+  // factor-L domain), so the quotient's wider evaluation domain shards the same way as the committed one
+  if (ctx->shard.log_stride > log_lde)
+    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_lde: LDE factor smaller than the number of shards");
   const u64 L_loc = ctx->shard.local_cosets(L);  // cosets owned by this context (all of them without a shard)
   const int m = (int)log_n;
   // per chunk of columns: monomials (natural order) in scratch, then one forward transform per coset that

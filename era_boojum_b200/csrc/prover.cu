@@ -199,13 +199,22 @@ struct bj_setup {
   std::vector<uint32_t> pi_cols, pi_rows;
   const uint64_t *sigmas = nullptr, *constants = nullptr, *tables = nullptr;  // borrowed, natural row order
   uint32_t n_tables = 0;
-  bj::DevMem lde;  // [V + C + T][L][n]
+  bj::DevMem lde;  // [V + C + T][D][n], D = max(L, quotient degree): the tree commits to the first L cosets of every column
   bj::Oracle tree;
-  uint64_t col_len = 0;  // elements of one LDE column held by this context: n * (L / world)
+  uint64_t col_len = 0;  // elements of one LDE column held by this context: n * (D / world)
   const uint64_t* col(uint32_t j) const { return (const uint64_t*)lde.p + (size_t)j * col_len; }
   uint32_t log_l() const {
     uint32_t l = 0;
     while ((1u << l) < c.fri_lde_factor) l++;
+    return l;
+  }
+  // log2 of the LDE factor the columns are evaluated at.  The reference evaluates at max(fri_lde_factor, quotient degree) and
+  // commits to the subset of the first fri_lde_factor cosets (prover.rs:178-196 `used_lde_degree`, `subset_for_degree`): in the
+  // bit-reversed coset order the first L cosets of the factor-D domain ARE the factor-L domain, so the trees, DEEP, FRI and
+  // the queries work on the prefix [0, n * L) of every column and only the quotient stage reads the cosets beyond it.
+  uint32_t log_d() const {
+    uint32_t l = log_l();
+    while ((1u << l) < c.quotient_degree) l++;
     return l;
   }
 };
@@ -235,7 +244,7 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
   bj::DeviceGuard device_guard(ctx);
   if (!ctx || !circuit || !d_sigmas || !out || circuit->num_variables == 0 || circuit->log_n == 0 || circuit->log_n > 28 ||
       !is_pow2(circuit->fri_lde_factor) || !is_pow2(circuit->merkle_tree_cap_size) || !is_pow2(circuit->quotient_degree) ||
-      circuit->quotient_degree > circuit->fri_lde_factor || (circuit->num_constants && !d_constants) ||
+      (circuit->num_constants && !d_constants) ||
       (circuit->n_gates && !circuit->gates) || circuit->tree_hasher > BJ_HASHER_KECCAK256 || circuit->transcript > 3)
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_setup_create: bad argument");
   if (circuit->lookup_width && (!d_lookup_tables || circuit->lookup_table_id_column >= circuit->num_constants ||
@@ -293,13 +302,13 @@ int32_t bj_setup_create(bj_ctx* ctx, const bj_circuit* circuit, const uint64_t* 
   s->tables = d_lookup_tables;
   s->n_tables = circuit->lookup_width ? circuit->lookup_width + 1 : 0;
   const uint32_t V = circuit->num_variables, C = circuit->num_constants, T = s->n_tables;
-  const uint32_t log_n = circuit->log_n, log_l = s->log_l();
+  const uint32_t log_n = circuit->log_n, log_l = s->log_l(), log_d = s->log_d();
   const u64 n = 1ull << log_n;
-  s->col_len = (n << log_l) / comm_world(ctx);
+  s->col_len = (n << log_d) / comm_world(ctx);
   BJ_TRY(s->lde.alloc(ctx, (size_t)(V + C + T) * s->col_len));
-  BJ_TRY(lde_columns(ctx, d_sigmas, (uint64_t*)s->lde.p, log_n, log_l, V));
-  if (C) BJ_TRY(lde_columns(ctx, d_constants, (uint64_t*)s->lde.p + (size_t)V * s->col_len, log_n, log_l, C));
-  if (T) BJ_TRY(lde_columns(ctx, d_lookup_tables, (uint64_t*)s->lde.p + (size_t)(V + C) * s->col_len, log_n, log_l, T));
+  BJ_TRY(lde_columns(ctx, d_sigmas, (uint64_t*)s->lde.p, log_n, log_d, V));
+  if (C) BJ_TRY(lde_columns(ctx, d_constants, (uint64_t*)s->lde.p + (size_t)V * s->col_len, log_n, log_d, C));
+  if (T) BJ_TRY(lde_columns(ctx, d_lookup_tables, (uint64_t*)s->lde.p + (size_t)(V + C) * s->col_len, log_n, log_d, T));
   for (uint32_t j = 0; j < V + C + T; j++) s->tree.cols.push_back(s->col(j));
   BJ_TRY(oracle_build(ctx, s->tree, n << log_l, circuit->merkle_tree_cap_size, circuit->tree_hasher, circuit->fri_lde_factor));
   *out = s.release();
@@ -330,15 +339,16 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
   pf->c = c;
   pf->c.gates = nullptr;
   const uint32_t V = c.num_variables, C = c.num_constants, Q = c.quotient_degree, L = c.fri_lde_factor, cap = c.merkle_tree_cap_size;
-  const uint32_t log_n = c.log_n, log_l = setup->log_l();
+  const uint32_t log_n = c.log_n, log_l = setup->log_l(), log_d = setup->log_d();
   uint32_t log_q = 0;
   while ((1u << log_q) < Q) log_q++;
   const u64 n = 1ull << log_n, nQ = n << log_q;
   // coset shard (multi-GPU): this context holds L / world cosets of every LDE column and Q_loc of the first Q cosets
   const uint32_t world = comm_world(ctx), rank = comm_rank(ctx);
-  const u64 nL = (n << log_l) / world;                                   // LOCAL length of an LDE column
+  const u64 nL = (n << log_l) / world;                                   // LOCAL length of the committed part of an LDE column
+  const u64 nD = (n << log_d) / world;                                   // LOCAL length (= stride) of an LDE column, D = max(L, Q)
   const u64 nQl = ctx->shard.local_cosets(Q) << log_n;                    // LOCAL quotient points
-  if (setup->col_len != nL) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_prove: the setup was built with a different shard");
+  if (setup->col_len != nD) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_prove: the setup was built with a different shard");
   const uint32_t T = setup->n_tables, wdt = c.lookup_width, nsub = c.lookup_num_repetitions, voff = c.lookup_variables_offset;
   auto t_prev = std::chrono::steady_clock::now();
   auto mark = [&](int stage) -> int32_t {
@@ -375,15 +385,15 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
 
   // ---- round 1: witness commitment ----
   DevMem w_lde, m_lde;
-  BJ_TRY(w_lde.alloc(ctx, (size_t)V * nL));
-  BJ_TRY(lde_columns(ctx, d_variables, (uint64_t*)w_lde.p, log_n, log_l, V));
+  BJ_TRY(w_lde.alloc(ctx, (size_t)V * nD));
+  BJ_TRY(lde_columns(ctx, d_variables, (uint64_t*)w_lde.p, log_n, log_d, V));
   std::vector<const uint64_t*> w_cols(V);
-  for (uint32_t j = 0; j < V; j++) w_cols[j] = (const uint64_t*)w_lde.p + (size_t)j * nL;
+  for (uint32_t j = 0; j < V; j++) w_cols[j] = (const uint64_t*)w_lde.p + (size_t)j * nD;
   Oracle w_or;
   w_or.cols = w_cols;
   if (lk) {
-    BJ_TRY(m_lde.alloc(ctx, nL));
-    BJ_TRY(bj_lde(ctx, d_multiplicities, n, (uint64_t*)m_lde.p, log_n, log_l, 1, 0));
+    BJ_TRY(m_lde.alloc(ctx, nD));
+    BJ_TRY(bj_lde(ctx, d_multiplicities, n, (uint64_t*)m_lde.p, log_n, log_d, 1, 0));
     w_or.cols.push_back((const uint64_t*)m_lde.p);  // variables | witness (none) | multiplicities
   }
   BJ_TRY(oracle_build(ctx, w_or, n << log_l, cap, c.tree_hasher, L));
@@ -425,11 +435,11 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
                                          d_multiplicities, lb, lg, log_n, (uint64_t*)st2.p + (size_t)(2 + 2 * n_partial) * n));
     }
   }
-  BJ_TRY(s2_lde.alloc(ctx, (size_t)n_s2 * nL));
-  BJ_TRY(lde_columns(ctx, (const uint64_t*)st2.p, (uint64_t*)s2_lde.p, log_n, log_l, n_s2));
+  BJ_TRY(s2_lde.alloc(ctx, (size_t)n_s2 * nD));
+  BJ_TRY(lde_columns(ctx, (const uint64_t*)st2.p, (uint64_t*)s2_lde.p, log_n, log_d, n_s2));
   st2.release();
   std::vector<const uint64_t*> s2_cols(n_s2);
-  for (uint32_t j = 0; j < n_s2; j++) s2_cols[j] = (const uint64_t*)s2_lde.p + (size_t)j * nL;
+  for (uint32_t j = 0; j < n_s2; j++) s2_cols[j] = (const uint64_t*)s2_lde.p + (size_t)j * nD;
   Oracle s2_or;
   s2_or.cols = s2_cols;
   BJ_TRY(oracle_build(ctx, s2_or, n << log_l, cap, c.tree_hasher, L));
@@ -490,7 +500,7 @@ int32_t bj_prove(bj_ctx* ctx, const bj_setup* setup, const uint64_t* d_variables
     const uint64_t b[2] = {beta.c0, beta.c1}, g[2] = {gamma.c0, gamma.c1};
     BJ_TRY(bj_quotient_copy_permutation(ctx, w_cols.data(), sigma_cols.data(), V, nr.data(), s2_cols[0], s2_cols[1],
                                         n_partial ? s2_cols.data() + 2 : nullptr, b, g, powers.data() + 2 * (size_t)(n_lk_terms + n_gate_terms),
-                                        log_n, log_l, log_q, Q, q0, q1));
+                                        log_n, log_d, log_q, Q, q0, q1));
   }
   BJ_TRY(bj_quotient_divide_by_vanishing(ctx, q0, q1, log_n, log_q));
   }  // nQl

@@ -91,11 +91,15 @@ class Setup:
         self.sigmas = sigmas                    # [V, n] natural order (needed by stage 2)
         self.constants_natural = constants      # [C, n] natural order (table-id column of the lookup argument)
         L = config.fri_lde_factor
+        # columns are evaluated at D = max(L, quotient degree) cosets; the oracle commits to the first L of them (the reference's
+        # used_lde_degree / subset_for_degree, prover.rs:178-196): in bit-reversed coset order they ARE the factor-L domain
+        D = max(L, quotient_degree)
+        self.committed_len = (sigmas.shape[1] * L) // world
         self.lookup = lookup
         parts = [sigmas, constants] + ([lookup["tables"]] if lookup else [])
         cols = torch.cat(parts, dim=0).contiguous()
-        self.lde = ctx.transform_raw_storages_to_lde(cols, L)      # [V + C, L / world, n]
-        self.tree = ctx.merkle_tree_construct([self.lde[c].reshape(-1) for c in range(cols.shape[0])],
+        self.lde = ctx.transform_raw_storages_to_lde(cols, D)      # [V + C, D / world, n]
+        self.tree = ctx.merkle_tree_construct([self.lde[c].reshape(-1)[:self.committed_len] for c in range(cols.shape[0])],
                                               config.merkle_tree_cap_size // world, hasher=config.hasher)
         self.cap = self.tree.get_cap()
         if comm:
@@ -190,6 +194,10 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     log_n, log_q = setup.log_n, Q.bit_length() - 1
     n = 1 << log_n
     L_loc = L // world
+    D = max(L, Q)                      # evaluation domain of the committed columns (the quotient needs Q cosets of each)
+    log_D = D.bit_length() - 1
+    ncm = n * L_loc                    # committed prefix of every LDE column
+    cm = lambda cols: [c[:ncm] for c in cols]
     Q_loc = Q // world if Q >= world else (1 if rank < Q else 0)     # owned cosets among the first Q
     dev = variables.device
     tm = timings if timings is not None else {}
@@ -208,13 +216,13 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     # ---- round 1: witness commitment (prover.rs:313-353) ----
     t0 = time.perf_counter()
     lk = setup.lookup
-    w_lde = ctx.transform_raw_storages_to_lde(variables, L)                  # [V, L_loc, n]
+    w_lde = ctx.transform_raw_storages_to_lde(variables, D)                  # [V, D_loc, n]
     w_cols = [flat(w_lde[c]) for c in range(V)]
     m_col = None
     if lk:
-        m_lde = ctx.transform_raw_storages_to_lde(multiplicities.reshape(1, -1).contiguous(), L)
+        m_lde = ctx.transform_raw_storages_to_lde(multiplicities.reshape(1, -1).contiguous(), D)
         m_col = flat(m_lde[0])
-    w_tree, w_cap = _commit(ctx, comm, w_cols + ([m_col] if lk else []), L, cap, cfg.hasher)   # variables | witness (none) | multiplicities
+    w_tree, w_cap = _commit(ctx, comm, cm(w_cols + ([m_col] if lk else [])), L, cap, cfg.hasher)   # variables | witness (none) | multiplicities
     tr.witness_merkle_tree_cap(w_cap)
     mark("1_witness_lde_commit", t0)
     # ---- round 2: copy-permutation products (prover.rs:360-554); the trace-domain part is replicated on every rank ----
@@ -234,9 +242,9 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
             [lk["tables"][j] for j in range(wdt + 1)], multiplicities, lookup_beta, lookup_gamma)
         lk_polys = [t for pr in a_polys for t in pr] + [b_poly[0], b_poly[1]]
     st2 = torch.stack([z0, z1] + [t for pr in partials for t in pr] + lk_polys).contiguous()
-    s2_lde = ctx.transform_raw_storages_to_lde(st2, L)
+    s2_lde = ctx.transform_raw_storages_to_lde(st2, D)
     s2_cols = [flat(s2_lde[c]) for c in range(st2.shape[0])]
-    s2_tree, s2_cap = _commit(ctx, comm, s2_cols, L, cap, cfg.hasher)
+    s2_tree, s2_cap = _commit(ctx, comm, cm(s2_cols), L, cap, cfg.hasher)
     tr.witness_merkle_tree_cap(s2_cap)
     n_partial = len(partials)
     mark("2_stage2_products_lde_commit", t0)
@@ -267,7 +275,7 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
                                                         powers[n_lk_terms:n_lk_terms + n_gate_terms], q0, q1)
         part_ldes = [(s2_cols[2 + 2 * c], s2_cols[3 + 2 * c]) for c in range(n_partial)]
         ctx.quotient_copy_permutation(w_cols, [setup.sigma_lde(j) for j in range(V)], (s2_cols[0], s2_cols[1]), part_ldes, beta, gamma,
-                                      powers[n_lk_terms + n_gate_terms:], log_n, log_L, log_q, Q, q0, q1)
+                                      powers[n_lk_terms + n_gate_terms:], log_n, log_D, log_q, Q, q0, q1)
         ctx.divide_by_vanishing(q0, q1, log_n, log_q)
         for k in range(Q_loc):                                              # local slot k = global coset k * world + rank
             qq[0, k * world + rank] = q0[k * n:(k + 1) * n]
@@ -383,8 +391,8 @@ def prove(ctx, setup, variables, timings=None, multiplicities=None):
     max_bits = log_n + log_L
     idxs = [tr.get_index_bits(max_bits, max_bits) for _ in range(nq.value)]
     setup_cols = [setup.lde[c].reshape(-1) for c in range(setup.lde.shape[0])]
-    oracles = [("witness_query", w_cols + ([m_col] if lk else []), w_tree), ("stage_2_query", s2_cols, s2_tree), ("quotient_query", qt_cols, qt_tree),
-               ("setup_query", setup_cols, setup.tree)]
+    oracles = [("witness_query", cm(w_cols + ([m_col] if lk else [])), w_tree), ("stage_2_query", cm(s2_cols), s2_tree),
+               ("quotient_query", qt_cols, qt_tree), ("setup_query", cm(setup_cols), setup.tree)]
     mine = [(qi, idx) for qi, idx in enumerate(idxs) if local_leaf_index(idx, log_n, world)[0] == rank]
     loc = [local_leaf_index(idx, log_n, world)[1] for _, idx in mine]
     rows = {name: (ctx.query_leaf_elements(cols, loc), ctx.merkle_paths(tree, loc)) for name, cols, tree in oracles} if mine else {}

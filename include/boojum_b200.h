@@ -402,7 +402,9 @@ typedef struct bj_circuit {
   uint32_t log_n;            /* trace length 2^log_n */
   uint32_t num_variables;    /* columns under the copy permutation (general purpose + specialised lookup columns) */
   uint32_t num_constants;
-  uint32_t quotient_degree;  /* power of two */
+  uint32_t quotient_degree;  /* power of two; may exceed fri_lde_factor (production: factor 2, degree 8) - columns are then evaluated
+                              * at max(fri_lde_factor, quotient_degree) cosets and the oracles commit to the first fri_lde_factor
+                              * of them (prover.rs:178-196 used_lde_degree / subset_for_degree) */
   uint32_t fri_lde_factor, merkle_tree_cap_size, security_level, pow_bits; /* ProofConfig (prover.rs:55-73) */
   const bj_gate_desc* gates;
   uint32_t n_gates;

@@ -180,7 +180,8 @@ def _prove_native_sharded_threads(bj, synthetic, prover, world, log_n, V, lde, c
 
 @pytest.mark.parametrize("world,log_n,V,lde,cap,lookup,hasher,transcript", [
     (2, 9, 20, 8, 16, False, "poseidon2", "poseidon2"), (4, 8, 60, 8, 16, True, "poseidon2", "poseidon"),
-    (8, 8, 20, 8, 16, False, "blake2s", "blake2s"), (2, 10, 60, 4, 8, True, "blake2s", "blake2s"), (8, 9, 60, 8, 32, True, "poseidon2", "poseidon2")])
+    (8, 8, 20, 8, 16, False, "blake2s", "blake2s"), (2, 10, 60, 4, 8, True, "blake2s", "blake2s"), (8, 9, 60, 8, 32, True, "poseidon2", "poseidon2"),
+    (2, 10, 60, 2, 16, True, "poseidon2", "poseidon2")])   # last: LDE factor 2 < quotient degree 4 (the shape of the reference's proof.json)
 def test_native_sharded_prover_equals_single_gpu(env, world, log_n, V, lde, cap, lookup, hasher, transcript):
     """bj_prove on coset-sharded contexts (communicator: local transport, the NCCL transport takes the same code path) returns
     on every rank exactly the single-GPU proof - world 2 / 4 / 8 incl. world > quotient degree (ranks that own no quotient
@@ -267,6 +268,42 @@ def test_native_cxx_prover_equals_python_driver(env, log_n, lookup):
     assert OV.verify(setup.vk(), got)
     assert len(timings) == 6 and all(v >= 0 for v in timings.values())
     nat.close()
+
+
+@pytest.mark.parametrize("log_n,lde,cap,lookup,hasher", [(10, 2, 16, False, "poseidon2"), (10, 2, 16, True, "blake2s"), (9, 2, 4, True, "poseidon2")])
+def test_quotient_degree_above_fri_lde_factor(env, log_n, lde, cap, lookup, hasher):
+    """fri_lde_factor < quotient degree - the production shape (the reference's own proof.json has fri_lde_factor 2 with
+    quotient degree 8): columns are evaluated at max(L, Q) cosets, the oracles commit to the first L (prover.rs:178-196
+    `used_lde_degree`, `subset_for_degree`).  Both drivers agree, the verifier accepts, a tampered opening is rejected, and
+    the committed caps equal those of a plain factor-L evaluation (the committed subset IS the factor-L domain)."""
+    bj, ctx, prover, synthetic = env
+    gen = synthetic.generate(ctx, log_n, 60, seed=21, lookup=lookup)
+    lk = gen[5] if lookup else None
+    variables, sigmas, constants, gates, Q = gen[:5]
+    assert Q > lde
+    cfg = prover.ProofConfig(fri_lde_factor=lde, merkle_tree_cap_size=cap, security_level=100, hasher=hasher,
+                             transcript="blake2s" if hasher == "blake2s" else "poseidon2")
+    setup = prover.Setup(ctx, sigmas, constants, gates, Q, cfg, lookup=lk)
+    m = lk["multiplicities"] if lk else None
+    ref = prover.prove(ctx, setup, variables, multiplicities=m)
+    nat = ctx.native_setup(sigmas.contiguous(), constants.contiguous(), gates, Q, cfg, lookup=lk)
+    assert np.array_equal(nat.get_cap(), setup.cap)
+    got = nat.prove(variables.contiguous(), m)
+    nat.close()
+    assert json.dumps(got, sort_keys=True) == json.dumps(ref, sort_keys=True)
+    assert got["proof_config"]["fri_lde_factor"] == lde and len(got["values_at_z"]) > 0
+    assert OV.verify(setup.vk(), got)
+    bad = json.loads(json.dumps(got))
+    bad["values_at_z"][3]["coeffs"][0] ^= 1
+    with pytest.raises(AssertionError):
+        OV.verify(setup.vk(), bad)
+    # the witness cap is the cap of a tree over the factor-L LDE of the same columns
+    cols = [variables] + ([m.reshape(1, -1)] if lk else [])
+    import torch
+    plain = ctx.transform_raw_storages_to_lde(torch.cat(cols, dim=0).contiguous(), lde)
+    tree = ctx.merkle_tree_construct([plain[c].reshape(-1) for c in range(plain.shape[0])], cap, hasher=hasher)
+    want = prover._digests(tree.get_cap(), hasher)
+    assert got["witness_oracle_cap"] == want
 
 
 def test_recursive_mode_poseidon2_type_parameters(env):
