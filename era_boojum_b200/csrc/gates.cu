@@ -17,8 +17,8 @@
 // The gate itself is data: the SSA program the reference's own GPU hook records (gpu_synthesizer::GPUDataCapture,
 // src/gpu_synthesizer/mod.rs:115-133, 354-443) - Index::{VariablePoly, WitnessPoly, ConstantPoly, TemporaryValue,
 // ConstantValue} and Relation::{Add, Double, Sub, Negate, Mul, Square, Inverse} - so any evaluator the reference can
-// capture runs here unchanged.  One thread owns one (coset, row) point and interprets the programs; the row's columns
-// are read once (coalesced across threads), temporaries live in thread-local memory.
+// capture runs here unchanged.  One thread owns up to four (coset, row) points and interprets the programs for all of them at
+// once (one decode per step); column loads are coalesced across threads, temporaries live in thread-local memory.
 #include <vector>
 #include "ctx.hpp"
 
@@ -50,75 +50,181 @@ struct DevGate {
   u32 term_base;  // index of the gate's first alpha power
 };
 
+// Device form of one program step (32 bytes, read with two 128-bit uniform loads).  The host lowers the recorded program to
+// it: operand kinds collapse to three classes - T: temporary slot, L: column of the unified table [variables | witnesses |
+// constants] (index of repetition 0 plus a per-repetition stride), I: immediate field element - and the opcode carries the
+// classes, so the interpreter decodes ONE dense switch per step and the step bodies contain no operand dispatch.
+struct PackedOp {
+  u32 code_dst;  // code (8 bits) | destination slot, or term index of a push (24 bits)
+  u32 strides;   // per-repetition column stride of operand a (low 16 bits) and b (high 16 bits)
+  u64 a, b;      // slot / column index / immediate
+  u64 pad;
+};
+static_assert(sizeof(PackedOp) == 32, "PackedOp is read as two uint4");
+constexpr int KIND_T = 0, KIND_L = 1, KIND_I = 2;
+// dense numbering (a jump table): ADD 0-8, SUB 9-17, MUL 18-26 by (class a, class b); DOUBLE, NEGATE, SQUARE, INVERSE, PUSH 27-41 by class a
+__host__ __device__ constexpr u32 gate_code(u32 op, int ka, int kb) {
+  return op == BJ_REL_ADD ? (u32)(ka * 3 + kb)
+       : op == BJ_REL_SUB ? 9u + (u32)(ka * 3 + kb)
+       : op == BJ_REL_MUL ? 18u + (u32)(ka * 3 + kb)
+       : op == BJ_REL_DOUBLE ? 27u + (u32)ka
+       : op == BJ_REL_NEGATE ? 30u + (u32)ka
+       : op == BJ_REL_SQUARE ? 33u + (u32)ka
+       : op == BJ_REL_INVERSE ? 36u + (u32)ka
+       : 39u + (u32)ka;
+}
+
 struct GateEvalParams {
   const DevGate* gates;
   u32 n_gates;
-  const DevOp* ops;
-  const u64* const* vars;
-  const u64* const* wits;
-  const u64* const* consts;
-  const u64* alphas;  // (c0, c1) per term
+  const PackedOp* ops;
+  const u64* const* cols;  // [variables | witnesses | constants]
+  u32 consts_base;         // index of constant column 0 in `cols` (the selector path reads constants 0 .. path_len - 1)
+  const u64* alphas;       // (c0, c1) per term
   u64 n_rows;
   u64* q_c0;
   u64* q_c1;
 };
 
-__device__ __forceinline__ u64 gate_fetch(const DevOperand& o, const u64* tmp, const GateEvalParams& p, u64 t, u32 vbase,
-                                          u32 wbase, u32 cbase, u32 cshared) {
-  switch (o.kind) {
-    case BJ_IDX_VARIABLE: return p.vars[vbase + (u32)o.value][t];
-    case BJ_IDX_WITNESS: return p.wits[wbase + (u32)o.value][t];
-    case BJ_IDX_CONSTANT_POLY: return p.consts[cbase + (u32)o.value][t];
-    case BJ_IDX_CONSTANT_POLY_SHARED: return p.consts[cshared + (u32)o.value][t];
-    case BJ_IDX_TEMPORARY: return tmp[(u32)o.value];
-    default: return o.value;  // BJ_IDX_CONSTANT_VALUE
+// Temporaries of the K points of a thread live in thread-local memory, [slot][point] (32 bytes per slot for K = 4: two 128-bit
+// accesses).  A shared-memory slab was tried instead (profiles/r2_time_gates_smem_experiment.json): the slab limits the block
+// residency to 4 per SM and the interpreter then waits on latencies it cannot hide - 2.6x slower than the L1-cached local array.
+template <int K>
+struct GateSlots {
+  u64 (*v)[K];
+  __device__ __forceinline__ void load(u32 slot, u64 (&out)[K]) const {
+#pragma unroll
+    for (int k = 0; k < K; k++) out[k] = v[slot][k];
+  }
+  __device__ __forceinline__ void store(u32 slot, const u64 (&r)[K]) const {
+#pragma unroll
+    for (int k = 0; k < K; k++) v[slot][k] = r[k];
+  }
+};
+
+template <int KIND, int K>
+__device__ __forceinline__ void gate_operand(u64 (&out)[K], u64 raw, u32 stride, u32 rep, const GateSlots<K>& tmp, const u64* const* cols,
+                                             const u64 (&pt)[K]) {
+  if (KIND == KIND_T) {
+    tmp.load((u32)raw, out);
+  } else if (KIND == KIND_L) {
+    const u64* col = cols[(u32)raw + rep * stride];
+#pragma unroll
+    for (int k = 0; k < K; k++) out[k] = __ldg(col + pt[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; k++) out[k] = raw;
   }
 }
 
+// One step for the K points of the thread.  Values in the slots are LAZY (any u64 congruent to the value): products skip the
+// final canonicalisation, sums canonicalise their second operand only - the term is canonicalised when it is pushed.
+template <int OP, int KA, int KB, int K>
+__device__ __forceinline__ void gate_step(const uint4* op, u32 dst, u32 strides, u64 a_raw, u32 rep, const GateSlots<K>& tmp,
+                                          const u64* const* cols, const u64 (&pt)[K], gl::e2 (&acc)[K], const u64* alpha_rep) {
+  u64 a[K], b[K];
+  gate_operand<KA, K>(a, a_raw, strides & 0xffffu, rep, tmp, cols, pt);
+  if (OP == BJ_REL_ADD || OP == BJ_REL_SUB || OP == BJ_REL_MUL) {
+    const uint4 wb = __ldg(op + 1);
+    gate_operand<KB, K>(b, ((u64)wb.y << 32) | wb.x, strides >> 16, rep, tmp, cols, pt);
+  }
+  if (OP == (int)GATE_OP_PUSH) {  // push_evaluation_result: the term times its alpha power goes into the gate's accumulator
+    const u64 a0 = __ldg(alpha_rep + 2 * dst), a1 = __ldg(alpha_rep + 2 * dst + 1);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      acc[k].c0 = gl::add(acc[k].c0, gl::mul(a[k], a0));
+      acc[k].c1 = gl::add(acc[k].c1, gl::mul(a[k], a1));
+    }
+  } else {
+    u64 r[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (OP == BJ_REL_ADD) r[k] = gl::add_lazy(a[k], b[k]);
+      else if (OP == BJ_REL_DOUBLE) r[k] = gl::add_lazy(a[k], a[k]);
+      else if (OP == BJ_REL_SUB) r[k] = gl::sub_lazy(a[k], b[k]);
+      else if (OP == BJ_REL_NEGATE) r[k] = gl::neg(a[k]);
+      else if (OP == BJ_REL_MUL) r[k] = gl::mul_lazy(a[k], b[k]);
+      else if (OP == BJ_REL_SQUARE) r[k] = gl::mul_lazy(a[k], a[k]);
+      else r[k] = gl_inv_chain(gl::canon(a[k]));  // BJ_REL_INVERSE
+    }
+    tmp.store(dst, r);
+  }
+}
+
+#define GATE_CASE(OP, KA, KB) \
+  case gate_code(OP, KA, KB): gate_step<(int)(OP), KA, KB, K>(op, dst, w.y, a_raw, rep, tmp, p.cols, pt, acc, alpha_rep); break;
+#define GATE_CASES_UNARY(OP) GATE_CASE(OP, KIND_T, 0) GATE_CASE(OP, KIND_L, 0) GATE_CASE(OP, KIND_I, 0)
+#define GATE_CASES_BINARY(OP)                                                                     \
+  GATE_CASE(OP, KIND_T, KIND_T) GATE_CASE(OP, KIND_T, KIND_L) GATE_CASE(OP, KIND_T, KIND_I)      \
+  GATE_CASE(OP, KIND_L, KIND_T) GATE_CASE(OP, KIND_L, KIND_L) GATE_CASE(OP, KIND_L, KIND_I)      \
+  GATE_CASE(OP, KIND_I, KIND_T) GATE_CASE(OP, KIND_I, KIND_L) GATE_CASE(OP, KIND_I, KIND_I)
+
+// One thread owns K points (block b: points b * 128 * K + k * 128 + thread, so every column load is coalesced).  Decoding a
+// step costs the same for K points as for one (the one-point interpreter is bound by the instruction issue rate).  Tried and
+// dropped (profiles/r2_gate_interpreter_experiments.txt): fetching the next step's words ahead (-16 %), a register budget of
+// 128 with half the resident blocks (no change), temporaries in shared memory (2.6x slower).
+template <int K, int S>
 __global__ void __launch_bounds__(128) gate_eval_kernel(const GateEvalParams p) {
-  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.n_rows) return;
-  u64 tmp[GATE_MAX_TMP];
-  gl::e2 q = {0, 0};
+  u64 slots[S][K];
+  const GateSlots<K> tmp{slots};
+  const u64 first = (u64)blockIdx.x * (128 * K) + threadIdx.x;
+  u64 pt[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) pt[k] = min(first + (u64)k * 128, p.n_rows - 1);  // out-of-range points repeat the last one, not stored
+  gl::e2 q[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) q[k] = {0, 0};
   for (u32 g = 0; g < p.n_gates; g++) {
     const DevGate gate = p.gates[g];
-    gl::e2 acc = {0, 0};
-    for (u32 rep = 0; rep < gate.num_repetitions; rep++) {
-      const u32 vbase = gate.var_base + rep * gate.var_offset, wbase = gate.wit_base + rep * gate.wit_offset;
-      const u32 cshared = gate.const_placement, cbase = cshared + rep * gate.const_offset;
-      const u64* alpha_rep = p.alphas + 2 * (size_t)(gate.term_base + rep * gate.n_writes);
-      for (u32 i = 0; i < gate.n_ops; i++) {
-        const DevOp op = p.ops[gate.ops_begin + i];
-        const u64 a = gate_fetch(op.a, tmp, p, t, vbase, wbase, cbase, cshared);
-        u64 r;
-        switch (op.op) {
-          case BJ_REL_ADD: r = gl::add_lazy(a, gate_fetch(op.b, tmp, p, t, vbase, wbase, cbase, cshared)); break;
-          case BJ_REL_DOUBLE: r = gl::add_lazy(a, a); break;
-          case BJ_REL_SUB: r = gl::sub_lazy(a, gate_fetch(op.b, tmp, p, t, vbase, wbase, cbase, cshared)); break;
-          case BJ_REL_NEGATE: r = gl::neg(a); break;
-          case BJ_REL_MUL: r = gl::mul(a, gate_fetch(op.b, tmp, p, t, vbase, wbase, cbase, cshared)); break;
-          case BJ_REL_SQUARE: r = gl::sqr(a); break;
-          case BJ_REL_INVERSE: r = gl_inv_chain(gl::canon(a)); break;
-          default: {  // GATE_OP_PUSH: push_evaluation_result - the term times its alpha power goes into the gate's accumulator
-            const u64 a0 = __ldg(alpha_rep + 2 * op.dst), a1 = __ldg(alpha_rep + 2 * op.dst + 1);
-            acc.c0 = gl::add(acc.c0, gl::mul(a, a0));
-            acc.c1 = gl::add(acc.c1, gl::mul(a, a1));
-            continue;
+    gl::e2 acc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = {0, 0};
+    if (gate.n_ops) {
+      for (u32 rep = 0; rep < gate.num_repetitions; rep++) {
+        const u64* alpha_rep = p.alphas + 2 * (size_t)(gate.term_base + rep * gate.n_writes);
+        const uint4* op = reinterpret_cast<const uint4*>(p.ops + gate.ops_begin);
+        for (u32 i = 0; i < gate.n_ops; i++, op += 2) {
+          const uint4 w = __ldg(op);  // code | dst, strides, operand a; operand b is fetched by the binary steps only
+          const u32 dst = w.x >> 8;
+          const u64 a_raw = ((u64)w.w << 32) | w.z;
+          switch (w.x & 0xffu) {
+            GATE_CASES_BINARY(BJ_REL_ADD)
+            GATE_CASES_BINARY(BJ_REL_SUB)
+            GATE_CASES_BINARY(BJ_REL_MUL)
+            GATE_CASES_UNARY(BJ_REL_DOUBLE)
+            GATE_CASES_UNARY(BJ_REL_NEGATE)
+            GATE_CASES_UNARY(BJ_REL_SQUARE)
+            GATE_CASES_UNARY(BJ_REL_INVERSE)
+            GATE_CASES_UNARY(GATE_OP_PUSH)
+            default: break;
           }
         }
-        tmp[op.dst] = r;
       }
     }
-    u64 sel = 1;
-    for (u32 i = 0; i < gate.path_len; i++) {
-      const u64 c = gl::canon(p.consts[i][t]);
-      sel = gl::mul(sel, ((gate.path_bits >> i) & 1) ? c : gl::canon(gl::sub(1, c)));
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      u64 sel = 1;
+      for (u32 i = 0; i < gate.path_len; i++) {
+        const u64 c = gl::canon(__ldg(p.cols[p.consts_base + i] + pt[k]));
+        sel = gl::mul(sel, ((gate.path_bits >> i) & 1) ? c : gl::canon(gl::sub(1, c)));
+      }
+      q[k].c0 = gl::add(q[k].c0, gl::mul(acc[k].c0, sel));
+      q[k].c1 = gl::add(q[k].c1, gl::mul(acc[k].c1, sel));
     }
-    q.c0 = gl::add(q.c0, gl::mul(acc.c0, sel));
-    q.c1 = gl::add(q.c1, gl::mul(acc.c1, sel));
   }
-  p.q_c0[t] = gl::canon(gl::add(p.q_c0[t], gl::canon(q.c0)));
-  p.q_c1[t] = gl::canon(gl::add(p.q_c1[t], gl::canon(q.c1)));
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const u64 t = first + (u64)k * 128;
+    if (t < p.n_rows) {
+      p.q_c0[t] = gl::canon(gl::add(p.q_c0[t], gl::canon(q[k].c0)));
+      p.q_c1[t] = gl::canon(gl::add(p.q_c1[t], gl::canon(q[k].c1)));
+    }
+  }
+}
+
+template <int K, int S>
+static void gate_eval_launch(const GateEvalParams& p, cudaStream_t stream) {
+  gate_eval_kernel<K, S><<<(unsigned)((p.n_rows + 128 * K - 1) / (128 * K)), 128, 0, stream>>>(p);
 }
 
 }  // namespace bj
@@ -135,7 +241,8 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
   if (!ctx || !h_gates || n_gates == 0 || !d_q_c0 || !d_q_c1 || n_points == 0 || (!h_alpha_powers && n_alpha_powers))
     BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_quotient_gates_general_purpose: bad argument");
   std::vector<DevGate> gates;
-  std::vector<DevOp> ops;
+  std::vector<PackedOp> ops;
+  uint32_t max_slots = 0;
   uint64_t total_terms = 0;
   // operand range checks against the columns the caller passed (all repetitions)
   auto check_index = [&](const bj_gate_index& ix, const bj_gate_desc& g, DevOperand* out) -> bool {
@@ -271,9 +378,39 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
         o.dst = sl;
         if (last_use[t_dst] < 0) free_slots.push_back(sl);  // defined but never read
       }
+      max_slots = std::max(max_slots, next_slot);
+    }
+    // 3. lowering to the device form: operand classes T / L / I, column operands as indices into the unified table
+    //    [variables | witnesses | constants] of repetition 0 plus the per-repetition stride (PerChunkOffset)
+    {
+      auto lower = [&](const DevOperand& o, u64* raw, u32* stride) -> int {
+        *stride = 0;
+        switch (o.kind) {
+          case BJ_IDX_TEMPORARY: *raw = o.value; return KIND_T;
+          case BJ_IDX_CONSTANT_VALUE: *raw = o.value; return KIND_I;
+          case BJ_IDX_VARIABLE: *raw = (u64)g.variables_initial_offset + o.value; *stride = g.variables_offset; return KIND_L;
+          case BJ_IDX_WITNESS: *raw = (u64)n_variables + g.witnesses_initial_offset + o.value; *stride = g.witnesses_offset; return KIND_L;
+          case BJ_IDX_CONSTANT_POLY:
+            *raw = (u64)n_variables + n_witnesses + g.constants_placement_offset + o.value;
+            *stride = g.constants_offset;
+            return KIND_L;
+          default: *raw = (u64)n_variables + n_witnesses + g.constants_placement_offset + o.value; return KIND_L;  // row-shared constant
+        }
+      };
+      if (g.variables_offset > 0xffffu || g.witnesses_offset > 0xffffu || g.constants_offset > 0xffffu || g.n_writes >= (1u << 24))
+        BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "gate descriptor: per-repetition offset beyond 65535 or more than 2^24 terms");
+      for (const DevOp& o : prog) {
+        PackedOp po{};
+        u32 sa = 0, sb = 0;
+        const int ka = lower(o.a, &po.a, &sa);
+        const bool binary = o.op == BJ_REL_ADD || o.op == BJ_REL_SUB || o.op == BJ_REL_MUL;
+        const int kb = binary ? lower(o.b, &po.b, &sb) : 0;
+        po.code_dst = gate_code(o.op, ka, kb) | (o.dst << 8);
+        po.strides = sa | (sb << 16);
+        ops.push_back(po);
+      }
     }
     d.n_ops = (u32)prog.size();
-    ops.insert(ops.end(), prog.begin(), prog.end());
     total_terms += (uint64_t)g.n_writes * g.num_repetitions;
     gates.push_back(d);
   }
@@ -285,11 +422,11 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
   BJ_TRY(param_upload(ctx, gates.data(), sizeof(DevGate) * gates.size(), &d));
   p.gates = (const DevGate*)d;
   p.n_gates = n_gates;
-  static const DevOp dummy_op{};
+  static const PackedOp dummy_op{};
   // small programs ride in the parameter arena; a long one (the Poseidon2 flattened gate is ~9k relations) gets its own
   // stream-ordered buffer, released behind the kernel
   void* big_program = nullptr;
-  const size_t ops_bytes = sizeof(DevOp) * std::max<size_t>(ops.size(), 1);
+  const size_t ops_bytes = sizeof(PackedOp) * std::max<size_t>(ops.size(), 1);
   if (ops_bytes > (128u << 10)) {
     BJ_CUDA(ctx, cudaMallocAsync(&big_program, ops_bytes, ctx->stream));
     const cudaError_t e = cudaMemcpyAsync(big_program, ops.data(), ops_bytes, cudaMemcpyHostToDevice, ctx->stream);
@@ -308,21 +445,34 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
       if (p) cudaFreeAsync(p, s);
     }
   } program_guard{big_program, ctx->stream};
-  p.ops = (const DevOp*)d;
-  static const u64* const null_ptr = nullptr;
-  BJ_TRY(param_upload(ctx, n_variables ? (const void*)h_variable_cols : (const void*)&null_ptr, sizeof(u64*) * std::max(n_variables, 1u), &d));
-  p.vars = (const u64* const*)d;
-  BJ_TRY(param_upload(ctx, n_witnesses ? (const void*)h_witness_cols : (const void*)&null_ptr, sizeof(u64*) * std::max(n_witnesses, 1u), &d));
-  p.wits = (const u64* const*)d;
-  BJ_TRY(param_upload(ctx, n_constants ? (const void*)h_constant_cols : (const void*)&null_ptr, sizeof(u64*) * std::max(n_constants, 1u), &d));
-  p.consts = (const u64* const*)d;
+  p.ops = (const PackedOp*)d;
+  {
+    std::vector<const u64*> table;
+    table.reserve((size_t)n_variables + n_witnesses + n_constants + 1);
+    for (uint32_t i = 0; i < n_variables; i++) table.push_back((const u64*)h_variable_cols[i]);
+    for (uint32_t i = 0; i < n_witnesses; i++) table.push_back((const u64*)h_witness_cols[i]);
+    for (uint32_t i = 0; i < n_constants; i++) table.push_back((const u64*)h_constant_cols[i]);
+    for (const u64* c : table)
+      if (!c) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_quotient_gates_general_purpose: NULL column");
+    if (table.empty()) table.push_back(nullptr);
+    BJ_TRY(param_upload(ctx, table.data(), sizeof(u64*) * table.size(), &d));
+    p.cols = (const u64* const*)d;
+    p.consts_base = n_variables + n_witnesses;
+  }
   static const u64 zero2[2] = {0, 0};
   BJ_TRY(param_upload(ctx, alphas.empty() ? (const void*)zero2 : (const void*)alphas.data(), sizeof(u64) * std::max<size_t>(alphas.size(), 2), &d));
   p.alphas = (const u64*)d;
   p.n_rows = n_points;
   p.q_c0 = (u64*)d_q_c0;
   p.q_c1 = (u64*)d_q_c1;
-  gate_eval_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, ctx->stream>>>(p);
+  // K = 4 points per thread once there is enough work to fill the machine with such blocks; slots sized to the live maximum
+  // K = 4 points per thread once there is enough work to fill the machine with such blocks; slots sized to the live maximum
+  int k = ctx->gate_points_per_thread;
+  if (k != 1 && k != 2 && k != 4) k = n_points >= (u64)ctx->sm_count * 4 * 512 ? 4 : n_points >= (u64)ctx->sm_count * 4 * 256 ? 2 : 1;
+  const bool small = max_slots <= 32;
+  if (k == 4) small ? gate_eval_launch<4, 32>(p, ctx->stream) : gate_eval_launch<4, GATE_MAX_TMP>(p, ctx->stream);
+  else if (k == 2) small ? gate_eval_launch<2, 32>(p, ctx->stream) : gate_eval_launch<2, GATE_MAX_TMP>(p, ctx->stream);
+  else small ? gate_eval_launch<1, 32>(p, ctx->stream) : gate_eval_launch<1, GATE_MAX_TMP>(p, ctx->stream);
   BJ_LAUNCH_CHECK(ctx);
   return BJ_OK;
 }

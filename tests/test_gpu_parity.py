@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path, called through the C-ABI (era_boojum_b200 -> libboojum_b200.so), against the CPU
 oracle on the same seeded inputs, against the reference's golden fixture, and - at BASELINE.json sizes - through
 size-independent properties.  Bit-exact: all values are integers mod p compared after canonicalisation."""
+import os
 import numpy as np
 import pytest
 
@@ -592,6 +593,20 @@ def test_gate_programs_of_the_reference_fixture_circuit(bj, ctx, golden_fixture)
                 a0, a1, k = (a0 + term * alphas[k][0]) % P, (a1 + term * alphas[k][1]) % P, k + 1
             w0, w1 = (w0 + sel * a0) % P, (w1 + sel * a1) % P
         assert int(g0[t]) == (int(q0[t]) + w0) % P and int(g1[t]) == (int(q1[t]) + w1) % P, t
+    # the interpreter handles 1, 2 or 4 points per thread (chosen by size; forced here): same result, incl. the ragged tail
+    # (96 rows = not a multiple of the 256- / 512-point blocks)
+    for k in (1, 2, 4):
+        os.environ["BJ_GATE_POINTS_PER_THREAD"] = str(k)
+        try:
+            ck = bj.Context(0)
+        finally:
+            del os.environ["BJ_GATE_POINTS_PER_THREAD"]
+        e0, e1 = bj.to_device(q0), bj.to_device(q1)
+        ck.evaluate_gates_over_general_purpose_columns(gates, [bj.to_device(c) for c in var_cols], [],
+                                                       [bj.to_device(c) for c in const_cols], alphas, e0, e1)
+        ck.synchronize()
+        assert np.array_equal(bj.to_numpy(e0), g0) and np.array_equal(bj.to_numpy(e1), g1), k
+        ck.close()
 
 
 def test_gate_program_limits(bj, ctx):

@@ -17,6 +17,10 @@ for r in rows[2:]:
         if k in hdr:
             i = hdr.index(k)
             print(k, '=', r[i], units[i])
+    for i, h in enumerate(hdr):   # local-memory traffic and cache hit rates (the gate interpreter keeps temporaries in local memory)
+        if ('mem_local' in h and h.endswith('.sum')) or h.endswith('hit_rate.pct') or h.startswith('smsp__inst_executed_op_local'):
+            if r[i] not in ('', '0', 'n/a'):
+                print(h, '=', r[i], units[i])
     stalls = []
     for i, h in enumerate(hdr):
         if 'issue_stalled' in h and h.endswith('per_warp_active.pct') and 'not_issued' not in h:

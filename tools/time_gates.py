@@ -10,7 +10,15 @@ from era_boojum_b200 import gate_library as GL, placement as PL, synthetic
 from oracle import verifier_reference as VR   # circuit layout of the fixture only (tooling, not the product path)
 
 LOG_POINTS = int(os.environ.get("LOG_POINTS", "20"))
-ctx = bj.Context.on_current_stream(0)
+ctx = bj.Context.on_current_stream(0)      # BJ_GATE_POINTS_PER_THREAD (if set) applies to this context
+
+
+def forced_ctx(k):
+    os.environ["BJ_GATE_POINTS_PER_THREAD"] = str(k)
+    try:
+        return bj.Context.on_current_stream(0)
+    finally:
+        del os.environ["BJ_GATE_POINTS_PER_THREAD"]
 fx = json.load(open(os.path.join(ROOT, "tests", "golden", "boojum_proof_fixture.json")))
 fp = fx["vk"]["fixed_parameters"]
 cfg = VR.REFERENCE_FIXTURE_GATES
@@ -48,7 +56,7 @@ for gate_idx, gate in enumerate(cfg["general_purpose"]):
     gp.append((gate.name, GL.placed(gate, reps, PL.output_placement(tree, gate_idx))))
 
 
-def run(gates):
+def run(gates, ctx=ctx):
     n_terms = sum(len(g["writes"]) * g["num_repetitions"] for g in gates)
     alphas = [(3 + i, 5 + 2 * i) for i in range(n_terms)]
     import ctypes
@@ -69,7 +77,23 @@ def run(gates):
 
 
 allg = spec + [g for _, g in gp]
+if os.environ.get("ONLY"):                  # profiling runs: one gate, one warm-up + 3 timed launches
+    res[os.environ["ONLY"]] = run([g for name, g in gp if name == os.environ["ONLY"]])
+    print(json.dumps(res))
+    sys.exit(0)
 res["all_gates"] = run(allg)
+if "BJ_GATE_POINTS_PER_THREAD" not in os.environ:
+    # points per thread 1 / 2 / 4 forced: timing, and the results must be identical
+    outs = {}
+    for k in (1, 2, 4):
+        ck = forced_ctx(k)
+        q0.zero_(); q1.zero_()
+        r = run(allg, ck)
+        res["all_gates_k%d" % k] = r
+        q0.zero_(); q1.zero_()
+        ck.evaluate_gates_over_general_purpose_columns(allg, var_cols, [], const_cols, [(3 + i, 5 + 2 * i) for i in range(r["terms"])], q0, q1)
+        outs[k] = (q0.clone(), q1.clone())
+    res["k_variants_identical"] = all(torch.equal(outs[k][0], outs[1][0]) and torch.equal(outs[k][1], outs[1][1]) for k in (2, 4))
 for name, g in gp:
     res[name] = run([g])
 # the bench circuit's three gates on its own geometry (60 variable columns), same number of points
