@@ -128,8 +128,13 @@ def verification_key(log_n, num_variables, num_constants, gates, quotient_degree
     return {"lookup": lk, "domain_size": 1 << log_n, "num_variables": num_variables, "num_constants": num_constants,
             "quotient_degree": quotient_degree, "fri_lde_factor": config.fri_lde_factor,
             "cap_size": config.merkle_tree_cap_size,
+            # (name, repetitions, selector path, first variable column, first constant column[, recorded program]): the three
+            # bench evaluators are known to the verifier by name; any other gate travels as its SSA program
             "gates": [(g["name"], g["num_repetitions"], list(g["selector_path"]), g.get("variables_initial_offset", 0),
-                       g["constants_placement_offset"]) for g in gates],
+                       g["constants_placement_offset"]) +
+                      (() if g["name"] in ("fma", "reduction4", "constant_allocator") else
+                       ({k: g.get(k, 0) for k in ("relations", "writes", "variables_offset", "witnesses_offset", "constants_offset")},))
+                      for g in gates],
             "public_inputs_locations": [list(p) for p in public_inputs],
             "hasher": config.hasher, "transcript": config.transcript,
             "setup_merkle_tree_cap": _digests(cap, config.hasher)}

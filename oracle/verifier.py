@@ -48,6 +48,52 @@ def _constant_allocator(v, c):
     return [R.e_sub(v[0], c[0])]
 
 
+# Index / Relation numbering of the recorded programs (gpu_synthesizer/mod.rs:115-133; include/boojum_b200.h BJ_IDX_* / BJ_REL_*)
+_IDX_VARIABLE, _IDX_WITNESS, _IDX_CONSTANT_POLY, _IDX_TEMPORARY, _IDX_CONSTANT_VALUE, _IDX_CONSTANT_POLY_SHARED = range(6)
+_REL_ADD, _REL_DOUBLE, _REL_SUB, _REL_NEGATE, _REL_MUL, _REL_SQUARE, _REL_INVERSE = range(7)
+
+
+def _program_terms(prog, var_v, const_v, var_base, const_base):
+    """One repetition of a recorded SSA program (GPUDataCapture) over Fp2 values at z; returns the pushed terms."""
+    tmp = {}
+
+    def fetch(o):
+        kind, val = o
+        if kind == _IDX_VARIABLE:
+            return var_v[var_base + val]
+        if kind == _IDX_CONSTANT_POLY:
+            return const_v[const_base[1] + val]
+        if kind == _IDX_CONSTANT_POLY_SHARED:
+            return const_v[const_base[0] + val]
+        if kind == _IDX_TEMPORARY:
+            return tmp[val]
+        if kind == _IDX_CONSTANT_VALUE:
+            return (int(val) % R.P, 0)
+        raise AssertionError("witness columns are not part of this driver's circuits")
+
+    for op, dst, a, b in prog["relations"]:
+        x = fetch(tuple(a))
+        if op == _REL_ADD:
+            r = R.e_add(x, fetch(tuple(b)))
+        elif op == _REL_DOUBLE:
+            r = R.e_add(x, x)
+        elif op == _REL_SUB:
+            r = R.e_sub(x, fetch(tuple(b)))
+        elif op == _REL_NEGATE:
+            r = R.e_sub((0, 0), x)
+        elif op == _REL_MUL:
+            r = R.e_mul(x, fetch(tuple(b)))
+        elif op == _REL_SQUARE:
+            r = R.e_mul(x, x)
+        elif op == _REL_INVERSE:
+            r = R.e_inv(x)
+        else:
+            raise AssertionError("unknown relation %r" % (op,))
+        assert dst not in tmp, "programs are SSA"
+        tmp[dst] = r
+    return [fetch(tuple(w)) for w in prog["writes"]]
+
+
 GATES = {"fma": (_fma, 4, (4, 0)), "reduction4": (_reduction4, 5, (5, 0)), "constant_allocator": (_constant_allocator, 1, (1, 1))}
 
 
@@ -87,7 +133,8 @@ def verify(vk, proof):
         lookup_gamma = tr.get_ext_challenge()
     tr.witness_merkle_tree_cap(proof["stage_2_oracle_cap"])
     alpha = tr.get_ext_challenge()
-    n_gate_terms = sum(g[1] for g in gates)  # one term per repetition for the three bench gates
+    # one term per repetition for the three bench gates; a gate that carries its recorded program pushes len(writes) per repetition
+    n_gate_terms = sum(g[1] * (len(g[5]["writes"]) if len(g) > 5 else 1) for g in gates)
     total_terms = n_lk_terms + n_gate_terms + 1 + 1 + n_partial
     powers = [(1, 0)]
     for _ in range(1, total_terms):
@@ -147,15 +194,19 @@ def verify(vk, proof):
         name, reps, path = g[0], g[1], g[2]
         var0 = g[3] if len(g) > 3 else 0
         const0 = g[4] if len(g) > 4 else len(path)
-        fn, width, (voff, coff) = GATES[name]
         sel = (1, 0)
         for i, bit in enumerate(path):
             sel = R.e_mul(sel, const_v[i] if bit else R.e_sub((1, 0), const_v[i]))
         acc = (0, 0)
         for rep in range(reps):
-            v = var_v[var0 + rep * voff: var0 + rep * voff + width]
-            c = const_v[const0 + rep * coff:]
-            for term in fn(v, c):
+            if len(g) > 5:      # recorded program: PerChunkOffset per repetition, row-shared constants at the gate's first column
+                prog = g[5]
+                terms = _program_terms(prog, var_v, const_v, var0 + rep * prog["variables_offset"],
+                                       (const0, const0 + rep * prog["constants_offset"]))
+            else:
+                fn, width, (voff, coff) = GATES[name]
+                terms = fn(var_v[var0 + rep * voff: var0 + rep * voff + width], const_v[const0 + rep * coff:])
+            for term in terms:
                 acc = R.e_add(acc, R.e_mul(term, gp_ch[k]))
                 k += 1
         t_acc = R.e_add(t_acc, R.e_mul(acc, sel))

@@ -306,6 +306,42 @@ def test_quotient_degree_above_fri_lde_factor(env, log_n, lde, cap, lookup, hash
     assert got["witness_oracle_cap"] == want
 
 
+@pytest.mark.parametrize("hasher,transcript", [("poseidon2", "poseidon2"), ("blake2s", "blake2s")])
+def test_production_shaped_circuit(env, hasher, transcript):
+    """The geometry of the reference's own vk.json / proof.json fixture (a recursion-layer circuit): 130 general-purpose columns
+    with its 11 evaluators behind the 6-level selector tree (incl. the Poseidon2 flattened gate: ~9.6k relations, 118 terms),
+    8 lookup sub-arguments of width 3, a boolean gate on a specialised column, 4 public inputs, quotient degree 8 with
+    fri_lde_factor 2 and cap 32.  Both drivers give the same proof; the verifier - which evaluates the recorded programs over
+    Fp2 itself - accepts it and rejects tampered openings; a witness that breaks the specialised boolean gate, or an
+    fma row, is refused by the prover."""
+    bj, ctx, prover, synthetic = env
+    c = synthetic.generate_production_shaped(ctx, 11, seed=5)
+    cfg = prover.ProofConfig(fri_lde_factor=2, merkle_tree_cap_size=32, security_level=100, hasher=hasher, transcript=transcript)
+    assert c["variables"].shape[0] == 155 and c["constants"].shape[0] == 8 and len(c["gates"]) == 11
+    assert sum(len(g["writes"]) * g["num_repetitions"] for g in c["gates"]) == 415      # the fixture's number of gate terms
+    nat = ctx.native_setup(c["sigmas"], c["constants"], c["gates"], 8, cfg, lookup=c["lookup"], public_inputs=c["public_inputs"])
+    m = c["lookup"]["multiplicities"]
+    proof = nat.prove(c["variables"], m)
+    vk = nat.vk()
+    assert OV.verify(vk, proof)
+    assert len(proof["public_inputs"]) == 4 and len(proof["values_at_z"]) == 155 + 8 + 155 + 1 + 19 + 1 + 9 + 4 + 8
+    setup = prover.Setup(ctx, c["sigmas"], c["constants"], c["gates"], 8, cfg, lookup=c["lookup"], public_inputs=c["public_inputs"])
+    ref = prover.prove(ctx, setup, c["variables"], multiplicities=m)
+    assert json.dumps(ref, sort_keys=True) == json.dumps(proof, sort_keys=True)
+    bad = json.loads(json.dumps(proof))
+    bad["values_at_z"][40]["coeffs"][1] ^= 1          # a general-purpose variable read by the Poseidon2 gate
+    with pytest.raises(AssertionError):
+        OV.verify(vk, bad)
+    for col, val in ((154, 2), (3, 12345)):           # the specialised boolean column; the output of the first fma repetition
+        w = c["variables"].clone()
+        rows = (c["constants"][1] == 1) & (c["constants"][3] == 1) if col == 3 else None     # fma rows: path bits 0 1 1 1 1
+        row = int(rows.nonzero()[0]) if rows is not None else 9
+        w[col, row] = val
+        with pytest.raises(bj.BoojumError):
+            nat.prove(w, m)
+    nat.close()
+
+
 def test_recursive_mode_poseidon2_type_parameters(env):
     """H = GoldilocksPoseidon2Sponge, TR = GoldilocksPoisedonTranscript (Poseidon v1 sponge): the type parameters of
     run_sha256_prover_recursive_mode_poseidon2 (src/gadgets/sha256/mod.rs:286-293, BASELINE configs[4]).  Both drivers give the
