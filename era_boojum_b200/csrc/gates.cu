@@ -27,16 +27,18 @@ namespace bj {
 constexpr int GATE_MAX_TMP = 128;            // live temporaries per thread after host-side slot allocation
 constexpr u32 GATE_MAX_PROGRAM_TMP = 1u << 20;  // temporaries a recorded program may name (SSA: one per relation)
 constexpr u32 GATE_OP_PUSH = 7;               // internal: fold operand a into the accumulator with alpha power `dst` of the repetition
+constexpr u32 GATE_OP_MADD = 8;               // internal: dst = a * b + c, a product whose only use is the sum that follows (host peephole)
 
 struct DevOperand {
   u32 kind;  // bj_gate_index kinds
   u32 pad;
   u64 value;
 };
-struct DevOp {
+struct DevOp {  // host-side form of one step (the device reads PackedOp)
   u32 op;
   u32 dst;
   DevOperand a, b;
+  DevOperand c;  // GATE_OP_MADD only
 };
 struct DevGate {
   u32 ops_begin, n_ops;
@@ -58,13 +60,15 @@ struct PackedOp {
   u32 code_dst;  // code (8 bits) | destination slot, or term index of a push (24 bits)
   u32 strides;   // per-repetition column stride of operand a (low 16 bits) and b (high 16 bits)
   u64 a, b;      // slot / column index / immediate
-  u64 pad;
+  u64 c;         // GATE_OP_MADD: slot of the addend
 };
 static_assert(sizeof(PackedOp) == 32, "PackedOp is read as two uint4");
 constexpr int KIND_T = 0, KIND_L = 1, KIND_I = 2;
-// dense numbering (a jump table): ADD 0-8, SUB 9-17, MUL 18-26 by (class a, class b); DOUBLE, NEGATE, SQUARE, INVERSE, PUSH 27-41 by class a
+// dense numbering: ADD 0-8, SUB 9-17, MUL 18-26 by (class a, class b); DOUBLE, NEGATE, SQUARE, INVERSE, PUSH 27-41 by class a;
+// MADD 42-47 by (class a in {T, L}, class b), its addend is always a temporary
 __host__ __device__ constexpr u32 gate_code(u32 op, int ka, int kb) {
-  return op == BJ_REL_ADD ? (u32)(ka * 3 + kb)
+  return op == GATE_OP_MADD ? 42u + (u32)(ka * 3 + kb)
+       : op == BJ_REL_ADD ? (u32)(ka * 3 + kb)
        : op == BJ_REL_SUB ? 9u + (u32)(ka * 3 + kb)
        : op == BJ_REL_MUL ? 18u + (u32)(ka * 3 + kb)
        : op == BJ_REL_DOUBLE ? 27u + (u32)ka
@@ -124,9 +128,24 @@ __device__ __forceinline__ void gate_step(const uint4* op, u32 dst, u32 strides,
                                           const u64* const* cols, const u64 (&pt)[K], gl::e2 (&acc)[K], const u64* alpha_rep) {
   u64 a[K], b[K];
   gate_operand<KA, K>(a, a_raw, strides & 0xffffu, rep, tmp, cols, pt);
-  if (OP == BJ_REL_ADD || OP == BJ_REL_SUB || OP == BJ_REL_MUL) {
+  u64 b_raw = 0;
+  if (OP == BJ_REL_ADD || OP == BJ_REL_SUB || OP == BJ_REL_MUL || OP == (int)GATE_OP_MADD) {
     const uint4 wb = __ldg(op + 1);
-    gate_operand<KB, K>(b, ((u64)wb.y << 32) | wb.x, strides >> 16, rep, tmp, cols, pt);
+    b_raw = ((u64)wb.y << 32) | wb.x;
+    gate_operand<KB, K>(b, b_raw, strides >> 16, rep, tmp, cols, pt);
+    if (OP == (int)GATE_OP_MADD) {
+      u64 c[K], r[K];
+      tmp.load(wb.z, c);
+      if (KB == KIND_I && (b_raw >> 32) == 0) {  // 32-bit immediate (uniform test): a * k + c exactly in 96 bits, one reduction
+#pragma unroll
+        for (int k = 0; k < K; k++) r[k] = gl::w96_reduce(gl::w96_add64(gl::mul_u32_wide(a[k], (u32)b_raw), c[k]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) r[k] = gl::fma_lazy(a[k], b[k], c[k]);
+      }
+      tmp.store(dst, r);
+      return;
+    }
   }
   if (OP == (int)GATE_OP_PUSH) {  // push_evaluation_result: the term times its alpha power goes into the gate's accumulator
     const u64 a0 = __ldg(alpha_rep + 2 * dst), a1 = __ldg(alpha_rep + 2 * dst + 1);
@@ -143,7 +162,7 @@ __device__ __forceinline__ void gate_step(const uint4* op, u32 dst, u32 strides,
       else if (OP == BJ_REL_DOUBLE) r[k] = gl::add_lazy(a[k], a[k]);
       else if (OP == BJ_REL_SUB) r[k] = gl::sub_lazy(a[k], b[k]);
       else if (OP == BJ_REL_NEGATE) r[k] = gl::neg(a[k]);
-      else if (OP == BJ_REL_MUL) r[k] = gl::mul_lazy(a[k], b[k]);
+      else if (OP == BJ_REL_MUL) r[k] = (KB == KIND_I && (b_raw >> 32) == 0) ? gl::w96_reduce(gl::mul_u32_wide(a[k], (u32)b_raw)) : gl::mul_lazy(a[k], b[k]);
       else if (OP == BJ_REL_SQUARE) r[k] = gl::mul_lazy(a[k], a[k]);
       else r[k] = gl_inv_chain(gl::canon(a[k]));  // BJ_REL_INVERSE
     }
@@ -196,6 +215,8 @@ __global__ void __launch_bounds__(128) gate_eval_kernel(const GateEvalParams p) 
             GATE_CASES_UNARY(BJ_REL_SQUARE)
             GATE_CASES_UNARY(BJ_REL_INVERSE)
             GATE_CASES_UNARY(GATE_OP_PUSH)
+            GATE_CASE(GATE_OP_MADD, KIND_T, KIND_T) GATE_CASE(GATE_OP_MADD, KIND_T, KIND_L) GATE_CASE(GATE_OP_MADD, KIND_T, KIND_I)
+            GATE_CASE(GATE_OP_MADD, KIND_L, KIND_T) GATE_CASE(GATE_OP_MADD, KIND_L, KIND_L) GATE_CASE(GATE_OP_MADD, KIND_L, KIND_I)
             default: break;
           }
         }
@@ -345,6 +366,67 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     }
     for (uint32_t k : late_pushes)
       if (!emit_push(k)) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: write operand out of range");
+    // 1b. peephole over the recorded program.  Evaluators written against a generic field interface record what they execute:
+    //     the Poseidon2 flattened gate multiplies by the matrix entry 1 3228 times and starts 372 sums at the constant 0
+    //     (9636 relations, 6036 after this pass).  x * 1, x + 0, x - 0 become aliases of x, x * 0 the constant 0; a product
+    //     whose only use is a sum with a temporary becomes one multiply-add step (its 128-bit product takes the addend before
+    //     the single reduction).  Values mod p are unchanged, so the quotient is bit-identical.
+    {
+      const auto is_const = [](const DevOperand& o, u64 v) { return o.kind == BJ_IDX_CONSTANT_VALUE && o.value == v; };
+      std::vector<DevOperand> alias(def_at.size(), DevOperand{0xffffffffu, 0, 0});
+      const auto resolve = [&](DevOperand& o) {
+        while (o.kind == BJ_IDX_TEMPORARY && alias[o.value].kind != 0xffffffffu) o = alias[o.value];
+      };
+      std::vector<DevOp> kept;
+      kept.reserve(prog.size());
+      for (DevOp o : prog) {
+        resolve(o.a);
+        const bool binary = o.op == BJ_REL_ADD || o.op == BJ_REL_SUB || o.op == BJ_REL_MUL;
+        if (binary) resolve(o.b);
+        const DevOperand zero{BJ_IDX_CONSTANT_VALUE, 0, 0};
+        if (!(ctx->gate_peephole & 1)) { kept.push_back(o); continue; }
+        if (o.op == BJ_REL_MUL && (is_const(o.a, 0) || is_const(o.b, 0))) { alias[o.dst] = zero; continue; }
+        if (o.op == BJ_REL_MUL && is_const(o.b, 1)) { alias[o.dst] = o.a; continue; }
+        if (o.op == BJ_REL_MUL && is_const(o.a, 1)) { alias[o.dst] = o.b; continue; }
+        if ((o.op == BJ_REL_ADD || o.op == BJ_REL_SUB) && is_const(o.b, 0)) { alias[o.dst] = o.a; continue; }
+        if (o.op == BJ_REL_ADD && is_const(o.a, 0)) { alias[o.dst] = o.b; continue; }
+        kept.push_back(o);
+      }
+      // multiply-add fusion
+      std::vector<uint32_t> uses(def_at.size(), 0);
+      std::vector<int32_t> def_idx(def_at.size(), -1);
+      for (size_t i = 0; i < kept.size(); i++) {
+        const DevOp& o = kept[i];
+        if (o.a.kind == BJ_IDX_TEMPORARY) uses[o.a.value]++;
+        if ((o.op == BJ_REL_ADD || o.op == BJ_REL_SUB || o.op == BJ_REL_MUL) && o.b.kind == BJ_IDX_TEMPORARY) uses[o.b.value]++;
+        if (o.op != GATE_OP_PUSH) def_idx[o.dst] = (int32_t)i;
+      }
+      std::vector<char> dead(kept.size(), 0);
+      for (size_t j = 0; j < kept.size(); j++) {
+        DevOp& o = kept[j];
+        if (o.op != BJ_REL_ADD || !(ctx->gate_peephole & 2)) continue;
+        for (int side = 0; side < 2; side++) {
+          const DevOperand& prod = side ? o.b : o.a;
+          const DevOperand& other = side ? o.a : o.b;
+          if (prod.kind != BJ_IDX_TEMPORARY || other.kind != BJ_IDX_TEMPORARY || uses[prod.value] != 1) continue;
+          const int32_t i = def_idx[prod.value];
+          if (i < 0 || dead[i] || kept[i].op != BJ_REL_MUL) continue;
+          DevOperand ma = kept[i].a, mb = kept[i].b;
+          if (ma.kind == BJ_IDX_CONSTANT_VALUE) std::swap(ma, mb);  // the immediate goes second
+          if (ma.kind == BJ_IDX_CONSTANT_VALUE) continue;            // constant * constant: left alone
+          const DevOperand addend = other;
+          o.op = GATE_OP_MADD;
+          o.a = ma;
+          o.b = mb;
+          o.c = addend;
+          dead[i] = 1;
+          break;
+        }
+      }
+      prog.clear();
+      for (size_t i = 0; i < kept.size(); i++)
+        if (!dead[i]) prog.push_back(kept[i]);
+    }
     // 2. slot allocation: a temporary lives from its definition to its last use; its slot is then reused (the kernel reads both
     //    operands before it writes the destination, so a destination may take over the slot of an operand that dies there)
     {
@@ -352,6 +434,7 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
       for (size_t i = 0; i < prog.size(); i++) {
         if (prog[i].a.kind == BJ_IDX_TEMPORARY) last_use[prog[i].a.value] = (int32_t)i;
         if (prog[i].op != GATE_OP_PUSH && prog[i].b.kind == BJ_IDX_TEMPORARY) last_use[prog[i].b.value] = (int32_t)i;
+        if (prog[i].op == GATE_OP_MADD) last_use[prog[i].c.value] = (int32_t)i;
       }
       std::vector<uint32_t> free_slots;
       uint32_t next_slot = 0;
@@ -359,10 +442,13 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
         DevOp& o = prog[i];
         const bool is_push = o.op == GATE_OP_PUSH;
         uint64_t ta = o.a.kind == BJ_IDX_TEMPORARY ? o.a.value : ~0ull, tb = (!is_push && o.b.kind == BJ_IDX_TEMPORARY) ? o.b.value : ~0ull;
+        const uint64_t tc = o.op == GATE_OP_MADD ? o.c.value : ~0ull;  // the addend of a multiply-add is always a temporary
         if (ta != ~0ull) o.a.value = (uint64_t)slot[ta];
         if (tb != ~0ull) o.b.value = (uint64_t)slot[tb];
+        if (tc != ~0ull) o.c.value = (uint64_t)slot[tc];
         if (ta != ~0ull && last_use[ta] == (int32_t)i) free_slots.push_back((uint32_t)slot[ta]);
         if (tb != ~0ull && tb != ta && last_use[tb] == (int32_t)i) free_slots.push_back((uint32_t)slot[tb]);
+        if (tc != ~0ull && tc != ta && tc != tb && last_use[tc] == (int32_t)i) free_slots.push_back((uint32_t)slot[tc]);
         if (is_push) continue;
         const uint32_t t_dst = o.dst;
         uint32_t sl;
@@ -403,8 +489,9 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
         PackedOp po{};
         u32 sa = 0, sb = 0;
         const int ka = lower(o.a, &po.a, &sa);
-        const bool binary = o.op == BJ_REL_ADD || o.op == BJ_REL_SUB || o.op == BJ_REL_MUL;
+        const bool binary = o.op == BJ_REL_ADD || o.op == BJ_REL_SUB || o.op == BJ_REL_MUL || o.op == GATE_OP_MADD;
         const int kb = binary ? lower(o.b, &po.b, &sb) : 0;
+        if (o.op == GATE_OP_MADD) po.c = o.c.value;
         po.code_dst = gate_code(o.op, ka, kb) | (o.dst << 8);
         po.strides = sa | (sb << 16);
         ops.push_back(po);

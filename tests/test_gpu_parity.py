@@ -607,6 +607,19 @@ def test_gate_programs_of_the_reference_fixture_circuit(bj, ctx, golden_fixture)
         ck.synchronize()
         assert np.array_equal(bj.to_numpy(e0), g0) and np.array_equal(bj.to_numpy(e1), g1), k
         ck.close()
+    # the host peephole (x * 1, x + 0 aliases; multiply-add fusion) changes the program, not the values: all four settings agree
+    for mode in (0, 1, 2):
+        os.environ["BJ_GATE_PEEPHOLE"] = str(mode)
+        try:
+            ck = bj.Context(0)
+        finally:
+            del os.environ["BJ_GATE_PEEPHOLE"]
+        e0, e1 = bj.to_device(q0), bj.to_device(q1)
+        ck.evaluate_gates_over_general_purpose_columns(gates, [bj.to_device(c) for c in var_cols], [],
+                                                       [bj.to_device(c) for c in const_cols], alphas, e0, e1)
+        ck.synchronize()
+        assert np.array_equal(bj.to_numpy(e0), g0) and np.array_equal(bj.to_numpy(e1), g1), mode
+        ck.close()
 
 
 def test_gate_program_limits(bj, ctx):
