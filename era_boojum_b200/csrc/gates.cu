@@ -19,6 +19,9 @@
 // ConstantValue} and Relation::{Add, Double, Sub, Negate, Mul, Square, Inverse} - so any evaluator the reference can
 // capture runs here unchanged.  One thread owns up to four (coset, row) points and interprets the programs for all of them at
 // once (one decode per step); column loads are coalesced across threads, temporaries live in thread-local memory.
+#include <algorithm>
+#include <cstring>
+#include <functional>
 #include <vector>
 #include "ctx.hpp"
 
@@ -27,6 +30,9 @@ namespace bj {
 constexpr int GATE_MAX_TMP = 128;            // live temporaries per thread after host-side slot allocation
 constexpr u32 GATE_MAX_PROGRAM_TMP = 1u << 20;  // temporaries a recorded program may name (SSA: one per relation)
 constexpr u32 GATE_OP_PUSH = 7;               // internal: fold operand a into the accumulator with alpha power `dst` of the repetition
+constexpr u32 GATE_OP_LINCOMB = 9;            // internal: dst = bias + sum_j k_j * x_j, 2..16 terms, k_j < 2^28 (host peephole: sum trees)
+constexpr u32 GATE_CODE_LINCOMB = 48;         // its opcode (gate_code() numbers the others 0..47)
+constexpr u32 GATE_LINCOMB_MAX_TERMS = 16, GATE_LINCOMB_MAX_COEFF = 1u << 28;  // 16 * 2^64 * 2^28 + 2^64 <= 2^96: one 96-bit sum
 constexpr u32 GATE_OP_MADD = 8;               // internal: dst = a * b + c, a product whose only use is the sum that follows (host peephole)
 
 struct DevOperand {
@@ -38,7 +44,12 @@ struct DevOp {  // host-side form of one step (the device reads PackedOp)
   u32 op;
   u32 dst;
   DevOperand a, b;
-  DevOperand c;  // GATE_OP_MADD only
+  DevOperand c;     // GATE_OP_MADD only
+  int32_t lc = -1;  // GATE_OP_LINCOMB: index of its term list; a.value = the constant term
+};
+struct LcTerm {      // k * x, x a temporary or a variable column
+  DevOperand x;
+  u32 k;
 };
 struct DevGate {
   u32 ops_begin, n_ops;
@@ -61,6 +72,11 @@ struct PackedOp {
   u32 strides;   // per-repetition column stride of operand a (low 16 bits) and b (high 16 bits)
   u64 a, b;      // slot / column index / immediate
   u64 c;         // GATE_OP_MADD: slot of the addend
+};
+// GATE_OP_LINCOMB: the header {code | dst, variables stride, a = number of terms, b = constant term} is followed by
+// ceil(n / 4) records of four (ref, k) pairs; ref = slot, or 0x80000000 | variable column of repetition 0
+struct PackedTerm {
+  u32 ref, k;
 };
 static_assert(sizeof(PackedOp) == 32, "PackedOp is read as two uint4");
 constexpr int KIND_T = 0, KIND_L = 1, KIND_I = 2;
@@ -207,6 +223,30 @@ __global__ void __launch_bounds__(128) gate_eval_kernel(const GateEvalParams p) 
           const u32 dst = w.x >> 8;
           const u64 a_raw = ((u64)w.w << 32) | w.z;
           switch (w.x & 0xffu) {
+            case GATE_CODE_LINCOMB: {
+              const uint4 wb = __ldg(op + 1);
+              const u32 n = w.z;
+              const PackedTerm* terms = reinterpret_cast<const PackedTerm*>(op + 2);
+              gl::w96 sum[K];
+#pragma unroll
+              for (int k = 0; k < K; k++) sum[k] = gl::w96_from(((u64)wb.y << 32) | wb.x);
+              for (u32 t = 0; t < n; t++) {
+                const uint2 tm = __ldg(reinterpret_cast<const uint2*>(terms + t));
+                u64 x[K];
+                if (tm.x >> 31) gate_operand<KIND_L, K>(x, tm.x & 0x7fffffffu, w.y, rep, tmp, p.cols, pt);
+                else tmp.load(tm.x, x);
+#pragma unroll
+                for (int k = 0; k < K; k++) sum[k] = gl::w96_add(sum[k], gl::mul_u32_wide(x[k], tm.y));
+              }
+              u64 r[K];
+#pragma unroll
+              for (int k = 0; k < K; k++) r[k] = gl::w96_reduce(sum[k]);
+              tmp.store(dst, r);
+              const u32 extra = (n + 3) / 4;  // the term records are part of the step
+              op += 2 * (size_t)extra;
+              i += extra;
+              break;
+            }
             GATE_CASES_BINARY(BJ_REL_ADD)
             GATE_CASES_BINARY(BJ_REL_SUB)
             GATE_CASES_BINARY(BJ_REL_MUL)
@@ -316,6 +356,16 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     //    only afterwards), with the pushes of the quotient terms placed right behind the relation that defines them
     //    (push_evaluation_result is called inline by evaluate_once; the alpha power of a term is fixed by its write index)
     std::vector<DevOp> prog;
+    std::vector<std::vector<LcTerm>> lincombs;  // term lists of the GATE_OP_LINCOMB steps (DevOp::lc)
+    // every temporary a step reads (operands a / b, the addend of a multiply-add, the terms of a linear combination)
+    const auto each_temp = [&](DevOp& o, const std::function<void(DevOperand&)>& fn) {
+      if (o.a.kind == BJ_IDX_TEMPORARY) fn(o.a);
+      if ((o.op == BJ_REL_ADD || o.op == BJ_REL_SUB || o.op == BJ_REL_MUL || o.op == GATE_OP_MADD) && o.b.kind == BJ_IDX_TEMPORARY) fn(o.b);
+      if (o.op == GATE_OP_MADD) fn(o.c);
+      if (o.op == GATE_OP_LINCOMB)
+        for (LcTerm& t : lincombs[o.lc])
+          if (t.x.kind == BJ_IDX_TEMPORARY) fn(t.x);
+    };
     prog.reserve(g.n_relations + g.n_writes);
     std::vector<int32_t> def_at;  // program temporary -> index in `prog` of its defining op (-1: undefined)
     auto defined = [&](const bj_gate_index& ix) { return ix.kind != BJ_IDX_TEMPORARY || (ix.value < def_at.size() && def_at[ix.value] >= 0); };
@@ -392,14 +442,103 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
         if (o.op == BJ_REL_ADD && is_const(o.a, 0)) { alias[o.dst] = o.b; continue; }
         kept.push_back(o);
       }
-      // multiply-add fusion
+      // sums of products with small immediates -> ONE step.  A matrix row of the Poseidon2 gate is 12 products by constants and
+      // 11 sums; with the single-use sums merged bottom-up (an inner sum hands its term list to the sum that consumes it) the
+      // row becomes one GATE_OP_LINCOMB: bias + sum_j k_j * x_j, accumulated in 96 bits and reduced once.
+      if (ctx->gate_peephole & 4) {
+        const size_t NT = def_at.size();
+        std::vector<uint32_t> uses(NT, 0);
+        std::vector<int32_t> def_idx(NT, -1), consumer(NT, -1);
+        for (size_t i = 0; i < kept.size(); i++) {
+          each_temp(kept[i], [&](DevOperand& t) {
+            uses[t.value]++;
+            consumer[t.value] = (int32_t)i;
+          });
+          if (kept[i].op != GATE_OP_PUSH) def_idx[kept[i].dst] = (int32_t)i;
+        }
+        struct Pending {
+          std::vector<LcTerm> terms;
+          u64 bias = 0;
+          bool fused = false;  // something was merged into it (a plain a + b of two leaves stays an ADD)
+        };
+        std::vector<int32_t> pending(kept.size(), -1);
+        std::vector<Pending> pend;
+        std::vector<char> dead(kept.size(), 0);
+        const auto leaf = [&](const DevOperand& o, Pending& acc, std::vector<int32_t>& kill) -> bool {
+          if (o.kind == BJ_IDX_CONSTANT_VALUE) {
+            acc.bias = gl::canon(gl::add(acc.bias, o.value));
+            acc.fused = true;
+            return true;
+          }
+          if (o.kind == BJ_IDX_VARIABLE) {
+            acc.terms.push_back({o, 1u});
+            return true;
+          }
+          if (o.kind != BJ_IDX_TEMPORARY) return false;  // witness / constant columns stay with the plain steps
+          const int32_t di = def_idx[o.value];
+          if (uses[o.value] == 1 && di >= 0 && !dead[di]) {
+            const DevOp& d = kept[di];
+            if (d.op == BJ_REL_ADD && pending[di] >= 0 && acc.terms.size() + pend[pending[di]].terms.size() <= GATE_LINCOMB_MAX_TERMS) {
+              const Pending& c = pend[pending[di]];
+              acc.terms.insert(acc.terms.end(), c.terms.begin(), c.terms.end());
+              acc.bias = gl::canon(gl::add(acc.bias, c.bias));
+              acc.fused = true;
+              kill.push_back(di);
+              return true;
+            }
+            if (d.op == BJ_REL_MUL) {
+              const DevOperand *x = &d.a, *k = &d.b;
+              if (x->kind == BJ_IDX_CONSTANT_VALUE) std::swap(x, k);
+              if (k->kind == BJ_IDX_CONSTANT_VALUE && k->value < GATE_LINCOMB_MAX_COEFF &&
+                  (x->kind == BJ_IDX_TEMPORARY || x->kind == BJ_IDX_VARIABLE)) {
+                acc.terms.push_back({*x, (u32)k->value});
+                acc.fused = true;
+                kill.push_back(di);
+                return true;
+              }
+            }
+          }
+          acc.terms.push_back({o, 1u});
+          return true;
+        };
+        const auto finalize = [&](size_t j, const Pending& pd) {
+          if (!pd.fused) return;  // a + b of two plain leaves: unchanged
+          DevOp& o = kept[j];
+          o.op = GATE_OP_LINCOMB;
+          o.a = DevOperand{BJ_IDX_CONSTANT_VALUE, 0, pd.bias};
+          o.b = DevOperand{BJ_IDX_CONSTANT_VALUE, 0, 0};
+          o.lc = (int32_t)lincombs.size();
+          lincombs.push_back(pd.terms);
+        };
+        for (size_t j = 0; j < kept.size(); j++) {
+          if (kept[j].op != BJ_REL_ADD) continue;
+          Pending acc;
+          std::vector<int32_t> kill;
+          if (!leaf(kept[j].a, acc, kill) || !leaf(kept[j].b, acc, kill) || acc.terms.size() > GATE_LINCOMB_MAX_TERMS || acc.terms.empty()) continue;
+          for (int32_t d : kill) dead[d] = 1;
+          const uint32_t t = kept[j].dst;
+          const bool inner = uses[t] == 1 && consumer[t] >= 0 && kept[consumer[t]].op == BJ_REL_ADD;
+          if (inner) {
+            pending[j] = (int32_t)pend.size();
+            pend.push_back(std::move(acc));
+          } else {
+            finalize(j, acc);
+          }
+        }
+        for (size_t j = 0; j < kept.size(); j++)  // inner sums their consumer did not take (size limit, unsupported sibling)
+          if (pending[j] >= 0 && !dead[j]) finalize(j, pend[pending[j]]);
+        std::vector<DevOp> compact;
+        compact.reserve(kept.size());
+        for (size_t i = 0; i < kept.size(); i++)
+          if (!dead[i]) compact.push_back(kept[i]);
+        kept.swap(compact);
+      }
+      // multiply-add fusion (products that are not by a small immediate, or whose sum was not merged above)
       std::vector<uint32_t> uses(def_at.size(), 0);
       std::vector<int32_t> def_idx(def_at.size(), -1);
       for (size_t i = 0; i < kept.size(); i++) {
-        const DevOp& o = kept[i];
-        if (o.a.kind == BJ_IDX_TEMPORARY) uses[o.a.value]++;
-        if ((o.op == BJ_REL_ADD || o.op == BJ_REL_SUB || o.op == BJ_REL_MUL) && o.b.kind == BJ_IDX_TEMPORARY) uses[o.b.value]++;
-        if (o.op != GATE_OP_PUSH) def_idx[o.dst] = (int32_t)i;
+        each_temp(kept[i], [&](DevOperand& t) { uses[t.value]++; });
+        if (kept[i].op != GATE_OP_PUSH) def_idx[kept[i].dst] = (int32_t)i;
       }
       std::vector<char> dead(kept.size(), 0);
       for (size_t j = 0; j < kept.size(); j++) {
@@ -431,24 +570,20 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     //    operands before it writes the destination, so a destination may take over the slot of an operand that dies there)
     {
       std::vector<int32_t> last_use(def_at.size(), -1), slot(def_at.size(), -1);
-      for (size_t i = 0; i < prog.size(); i++) {
-        if (prog[i].a.kind == BJ_IDX_TEMPORARY) last_use[prog[i].a.value] = (int32_t)i;
-        if (prog[i].op != GATE_OP_PUSH && prog[i].b.kind == BJ_IDX_TEMPORARY) last_use[prog[i].b.value] = (int32_t)i;
-        if (prog[i].op == GATE_OP_MADD) last_use[prog[i].c.value] = (int32_t)i;
-      }
+      for (size_t i = 0; i < prog.size(); i++) each_temp(prog[i], [&](DevOperand& t) { last_use[t.value] = (int32_t)i; });
       std::vector<uint32_t> free_slots;
+      std::vector<uint64_t> read;  // program temporaries this step reads (distinct)
       uint32_t next_slot = 0;
       for (size_t i = 0; i < prog.size(); i++) {
         DevOp& o = prog[i];
         const bool is_push = o.op == GATE_OP_PUSH;
-        uint64_t ta = o.a.kind == BJ_IDX_TEMPORARY ? o.a.value : ~0ull, tb = (!is_push && o.b.kind == BJ_IDX_TEMPORARY) ? o.b.value : ~0ull;
-        const uint64_t tc = o.op == GATE_OP_MADD ? o.c.value : ~0ull;  // the addend of a multiply-add is always a temporary
-        if (ta != ~0ull) o.a.value = (uint64_t)slot[ta];
-        if (tb != ~0ull) o.b.value = (uint64_t)slot[tb];
-        if (tc != ~0ull) o.c.value = (uint64_t)slot[tc];
-        if (ta != ~0ull && last_use[ta] == (int32_t)i) free_slots.push_back((uint32_t)slot[ta]);
-        if (tb != ~0ull && tb != ta && last_use[tb] == (int32_t)i) free_slots.push_back((uint32_t)slot[tb]);
-        if (tc != ~0ull && tc != ta && tc != tb && last_use[tc] == (int32_t)i) free_slots.push_back((uint32_t)slot[tc]);
+        read.clear();
+        each_temp(o, [&](DevOperand& t) {
+          if (std::find(read.begin(), read.end(), t.value) == read.end()) read.push_back(t.value);
+          t.value = (uint64_t)slot[t.value];
+        });
+        for (uint64_t t : read)
+          if (last_use[t] == (int32_t)i) free_slots.push_back((uint32_t)slot[t]);
         if (is_push) continue;
         const uint32_t t_dst = o.dst;
         uint32_t sl;
@@ -486,6 +621,28 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
       if (g.variables_offset > 0xffffu || g.witnesses_offset > 0xffffu || g.constants_offset > 0xffffu || g.n_writes >= (1u << 24))
         BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "gate descriptor: per-repetition offset beyond 65535 or more than 2^24 terms");
       for (const DevOp& o : prog) {
+        if (o.op == GATE_OP_LINCOMB) {
+          const std::vector<LcTerm>& terms = lincombs[o.lc];
+          PackedOp head{};
+          head.code_dst = GATE_CODE_LINCOMB | (o.dst << 8);
+          head.strides = g.variables_offset;
+          head.a = terms.size();
+          head.b = o.a.value;
+          ops.push_back(head);
+          for (size_t t0 = 0; t0 < terms.size(); t0 += 4) {
+            PackedTerm rec[4] = {};
+            for (size_t t = t0; t < std::min(terms.size(), t0 + 4); t++) {
+              const LcTerm& lt = terms[t];
+              rec[t - t0].ref = lt.x.kind == BJ_IDX_TEMPORARY ? (u32)lt.x.value : (0x80000000u | (u32)(g.variables_initial_offset + lt.x.value));
+              rec[t - t0].k = lt.k;
+            }
+            PackedOp raw;
+            static_assert(sizeof(rec) == sizeof(PackedOp), "four terms per record");
+            memcpy(&raw, rec, sizeof(raw));
+            ops.push_back(raw);
+          }
+          continue;
+        }
         PackedOp po{};
         u32 sa = 0, sb = 0;
         const int ka = lower(o.a, &po.a, &sa);
@@ -497,7 +654,7 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
         ops.push_back(po);
       }
     }
-    d.n_ops = (u32)prog.size();
+    d.n_ops = (u32)ops.size() - d.ops_begin;  // records, incl. the term records of linear combinations
     total_terms += (uint64_t)g.n_writes * g.num_repetitions;
     gates.push_back(d);
   }
