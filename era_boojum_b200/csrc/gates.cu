@@ -29,11 +29,12 @@ namespace bj {
 
 constexpr int GATE_MAX_TMP = 128;            // live temporaries per thread after host-side slot allocation
 constexpr u32 GATE_MAX_PROGRAM_TMP = 1u << 20;  // temporaries a recorded program may name (SSA: one per relation)
-constexpr u32 GATE_OP_PUSH = 7;               // internal: fold operand a into the accumulator with alpha power `dst` of the repetition
-constexpr u32 GATE_OP_LINCOMB = 9;            // internal: dst = bias + sum_j k_j * x_j, 2..16 terms, k_j < 2^28 (host peephole: sum trees)
+// internal steps next to the seven recorded relation kinds (BJ_REL_* = 0..6)
+constexpr u32 GATE_OP_PUSH = 7;               // fold operand a into the accumulator with alpha power `dst` of the repetition
+constexpr u32 GATE_OP_MADD = 8;               // dst = a * b + c, a product whose only use is the sum that follows (host peephole)
+constexpr u32 GATE_OP_LINCOMB = 9;            // dst = bias + sum_j k_j * x_j, 2..16 terms, k_j < 2^28 (host peephole: sum trees)
 constexpr u32 GATE_CODE_LINCOMB = 48;         // its opcode (gate_code() numbers the others 0..47)
 constexpr u32 GATE_LINCOMB_MAX_TERMS = 16, GATE_LINCOMB_MAX_COEFF = 1u << 28;  // 16 * 2^64 * 2^28 + 2^64 <= 2^96: one 96-bit sum
-constexpr u32 GATE_OP_MADD = 8;               // internal: dst = a * b + c, a product whose only use is the sum that follows (host peephole)
 
 struct DevOperand {
   u32 kind;  // bj_gate_index kinds
@@ -51,13 +52,10 @@ struct LcTerm {      // k * x, x a temporary or a variable column
   DevOperand x;
   u32 k;
 };
-struct DevGate {
-  u32 ops_begin, n_ops;
+struct DevGate {  // placement (PerChunkOffset, specialised-column bases, first constant column) is folded into the steps' operands
+  u32 ops_begin, n_ops;                       // records of the gate's program in GateEvalParams::ops
   u32 n_writes;                               // quotient terms per repetition
   u32 num_repetitions;
-  u32 var_offset, wit_offset, const_offset;  // PerChunkOffset
-  u32 var_base, wit_base;                     // first column of repetition 0 (specialised placement; 0 for general purpose)
-  u32 const_placement;                        // first constant column of the gate (= selector path length)
   u32 path_len;
   u32 path_bits;  // bit i = path[i]
   u32 term_base;  // index of the gate's first alpha power
@@ -341,12 +339,6 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     d.ops_begin = (u32)ops.size();
     d.n_writes = g.n_writes;
     d.num_repetitions = g.num_repetitions;
-    d.var_offset = g.variables_offset;
-    d.wit_offset = g.witnesses_offset;
-    d.var_base = g.variables_initial_offset;
-    d.wit_base = g.witnesses_initial_offset;
-    d.const_offset = g.constants_offset;
-    d.const_placement = g.constants_placement_offset;
     d.path_len = g.selector_path_len;
     d.path_bits = 0;
     d.term_base = (u32)total_terms;
