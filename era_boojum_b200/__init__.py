@@ -23,7 +23,7 @@ import numpy as np
 from . import native
 from .native import BoojumError, P, lib
 
-__all__ = ["Context", "Comm", "MerkleTreeWithCap", "Transcript", "FriOracles", "BoojumError", "P", "to_device", "to_numpy"]
+__all__ = ["Context", "Comm", "compile_gate_programs", "MerkleTreeWithCap", "Transcript", "FriOracles", "BoojumError", "P", "to_device", "to_numpy"]
 
 
 class Transcript:
@@ -110,6 +110,24 @@ class FriOracles:
 
     def __del__(self):
         self.close()
+
+
+def compile_gate_programs(gates, n_variables, n_witnesses, n_constants, peephole=15):
+    """bj_gate_programs_compile: what the gate evaluator will execute for these gate dicts - host code only (no GPU needed).
+    Returns (records [n, 4] uint64 in the step format documented in include/boojum_b200.h, first record of every gate + the
+    end, maximal number of live temporaries)."""
+    keep, descs = Context._gate_descs(gates)
+    n = ctypes.c_uint64()
+    live = ctypes.c_uint32()
+    first = (ctypes.c_uint32 * (len(gates) + 1))()
+    _ok(lib.bj_gate_programs_compile(descs, len(gates), n_variables, n_witnesses, n_constants, peephole, None, 0, ctypes.byref(n),
+                                     first, ctypes.byref(live)), "bj_gate_programs_compile")
+    rec = np.zeros((max(1, n.value), 4), np.uint64)
+    _ok(lib.bj_gate_programs_compile(descs, len(gates), n_variables, n_witnesses, n_constants, peephole,
+                                     rec.ctypes.data_as(ctypes.c_void_p), rec.shape[0], ctypes.byref(n), first, ctypes.byref(live)),
+        "bj_gate_programs_compile")
+    del keep
+    return rec[: n.value], list(first), int(live.value)
 
 
 def to_device(a, device="cuda:0"):

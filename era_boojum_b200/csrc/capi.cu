@@ -124,7 +124,7 @@ int32_t bj_ctx_create(int32_t device, void* stream, bj_ctx** out_ctx) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   ctx->ntt_max_tile_log = env_int("BJ_NTT_MAX_TILE_LOG", 13);
   ctx->gate_points_per_thread = env_int("BJ_GATE_POINTS_PER_THREAD", 0);
-  ctx->gate_peephole = env_int("BJ_GATE_PEEPHOLE", 7);
+  ctx->gate_peephole = env_int("BJ_GATE_PEEPHOLE", 15);
   if (ctx->ntt_max_tile_log < 8) ctx->ntt_max_tile_log = 8;
   if (ctx->ntt_max_tile_log > 14) ctx->ntt_max_tile_log = 14;
   ctx->ntt_pass1_w = env_int("BJ_NTT_PASS1_W", -1);

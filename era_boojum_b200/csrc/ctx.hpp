@@ -80,7 +80,7 @@ struct bj_ctx {
   int ntt_chunk_mb = 0;
   int ntt_full_pow = 1;          // BJ_NTT_FULL_POW=0 keeps the two-level coset power tables only
   uint32_t one = 1;              // a 1 the compiler cannot see (passed as a kernel parameter): additions written as multiply-adds by it issue on the FMA pipe (blake2s.cu)
-  int gate_peephole = 7;           // BJ_GATE_PEEPHOLE: bit 0 = alias x*1 / x+0 / x*0, bit 1 = multiply-add fusion, bit 2 = linear combinations (gates.cu)
+  int gate_peephole = 15;          // BJ_GATE_PEEPHOLE: bit 0 = alias x*1 / x+0 / x*0, 1 = multiply-add fusion, 2 = linear combinations, 3 = pushing steps (gates.cu)
   int gate_points_per_thread = 0;  // BJ_GATE_POINTS_PER_THREAD=1|2|4: force the gate interpreter's points per thread (0: by size)
   int ntt_l2_persist = 1;        // BJ_NTT_L2_PERSIST=0: do not pin the coset-power table in L2 during the scaled pass
   bool l2_limit_set = false;

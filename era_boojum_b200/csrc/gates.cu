@@ -47,6 +47,7 @@ struct DevOp {  // host-side form of one step (the device reads PackedOp)
   DevOperand a, b;
   DevOperand c;     // GATE_OP_MADD only
   int32_t lc = -1;  // GATE_OP_LINCOMB: index of its term list; a.value = the constant term
+  bool push = false;  // the step's value is a quotient term read by nothing else: it is pushed (dst = term index), not stored
 };
 struct LcTerm {      // k * x, x a temporary or a variable column
   DevOperand x;
@@ -66,7 +67,7 @@ struct DevGate {  // placement (PerChunkOffset, specialised-column bases, first 
 // constants] (index of repetition 0 plus a per-repetition stride), I: immediate field element - and the opcode carries the
 // classes, so the interpreter decodes ONE dense switch per step and the step bodies contain no operand dispatch.
 struct PackedOp {
-  u32 code_dst;  // code (8 bits) | destination slot, or term index of a push (24 bits)
+  u32 code_dst;  // code (7 bits) | push flag (bit 7) | destination slot, or the term index when the value is pushed (24 bits)
   u32 strides;   // per-repetition column stride of operand a (low 16 bits) and b (high 16 bits)
   u64 a, b;      // slot / column index / immediate
   u64 c;         // GATE_OP_MADD: slot of the addend
@@ -135,11 +136,12 @@ __device__ __forceinline__ void gate_operand(u64 (&out)[K], u64 raw, u32 stride,
   }
 }
 
-// One step for the K points of the thread.  Values in the slots are LAZY (any u64 congruent to the value): products skip the
-// final canonicalisation, sums canonicalise their second operand only - the term is canonicalised when it is pushed.
+// One step for the K points of the thread: the value it computes is returned in r; the caller stores it in the destination slot
+// or, for a step that carries the push flag, folds it into the gate's accumulator.  Values in the slots are LAZY (any u64
+// congruent to the value): products skip the final canonicalisation, sums canonicalise their second operand only.
 template <int OP, int KA, int KB, int K>
-__device__ __forceinline__ void gate_step(const uint4* op, u32 dst, u32 strides, u64 a_raw, u32 rep, const GateSlots<K>& tmp,
-                                          const u64* const* cols, const u64 (&pt)[K], gl::e2 (&acc)[K], const u64* alpha_rep) {
+__device__ __forceinline__ void gate_step(u64 (&r)[K], const uint4* op, u32 strides, u64 a_raw, u32 rep, const GateSlots<K>& tmp,
+                                          const u64* const* cols, const u64 (&pt)[K]) {
   u64 a[K], b[K];
   gate_operand<KA, K>(a, a_raw, strides & 0xffffu, rep, tmp, cols, pt);
   u64 b_raw = 0;
@@ -148,7 +150,7 @@ __device__ __forceinline__ void gate_step(const uint4* op, u32 dst, u32 strides,
     b_raw = ((u64)wb.y << 32) | wb.x;
     gate_operand<KB, K>(b, b_raw, strides >> 16, rep, tmp, cols, pt);
     if (OP == (int)GATE_OP_MADD) {
-      u64 c[K], r[K];
+      u64 c[K];
       tmp.load(wb.z, c);
       if (KB == KIND_I && (b_raw >> 32) == 0) {  // 32-bit immediate (uniform test): a * k + c exactly in 96 bits, one reduction
 #pragma unroll
@@ -157,35 +159,25 @@ __device__ __forceinline__ void gate_step(const uint4* op, u32 dst, u32 strides,
 #pragma unroll
         for (int k = 0; k < K; k++) r[k] = gl::fma_lazy(a[k], b[k], c[k]);
       }
-      tmp.store(dst, r);
-      return;
     }
   }
-  if (OP == (int)GATE_OP_PUSH) {  // push_evaluation_result: the term times its alpha power goes into the gate's accumulator
-    const u64 a0 = __ldg(alpha_rep + 2 * dst), a1 = __ldg(alpha_rep + 2 * dst + 1);
+  if (OP != (int)GATE_OP_MADD) {
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-      acc[k].c0 = gl::add(acc[k].c0, gl::mul(a[k], a0));
-      acc[k].c1 = gl::add(acc[k].c1, gl::mul(a[k], a1));
-    }
-  } else {
-    u64 r[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      if (OP == BJ_REL_ADD) r[k] = gl::add_lazy(a[k], b[k]);
-      else if (OP == BJ_REL_DOUBLE) r[k] = gl::add_lazy(a[k], a[k]);
-      else if (OP == BJ_REL_SUB) r[k] = gl::sub_lazy(a[k], b[k]);
-      else if (OP == BJ_REL_NEGATE) r[k] = gl::neg(a[k]);
-      else if (OP == BJ_REL_MUL) r[k] = (KB == KIND_I && (b_raw >> 32) == 0) ? gl::w96_reduce(gl::mul_u32_wide(a[k], (u32)b_raw)) : gl::mul_lazy(a[k], b[k]);
-      else if (OP == BJ_REL_SQUARE) r[k] = gl::mul_lazy(a[k], a[k]);
-      else r[k] = gl_inv_chain(gl::canon(a[k]));  // BJ_REL_INVERSE
-    }
-    tmp.store(dst, r);
+  for (int k = 0; k < K; k++) {
+    if (OP == BJ_REL_ADD) r[k] = gl::add_lazy(a[k], b[k]);
+    else if (OP == BJ_REL_DOUBLE) r[k] = gl::add_lazy(a[k], a[k]);
+    else if (OP == BJ_REL_SUB) r[k] = gl::sub_lazy(a[k], b[k]);
+    else if (OP == BJ_REL_NEGATE) r[k] = gl::neg(a[k]);
+    else if (OP == BJ_REL_MUL) r[k] = (KB == KIND_I && (b_raw >> 32) == 0) ? gl::w96_reduce(gl::mul_u32_wide(a[k], (u32)b_raw)) : gl::mul_lazy(a[k], b[k]);
+    else if (OP == BJ_REL_SQUARE) r[k] = gl::mul_lazy(a[k], a[k]);
+    else if (OP == BJ_REL_INVERSE) r[k] = gl_inv_chain(gl::canon(a[k]));
+    else r[k] = a[k];  // GATE_OP_PUSH of a bare operand (column / constant / a temporary that is also read elsewhere)
+  }
   }
 }
 
 #define GATE_CASE(OP, KA, KB) \
-  case gate_code(OP, KA, KB): gate_step<(int)(OP), KA, KB, K>(op, dst, w.y, a_raw, rep, tmp, p.cols, pt, acc, alpha_rep); break;
+  case gate_code(OP, KA, KB): gate_step<(int)(OP), KA, KB, K>(r, op, w.y, a_raw, rep, tmp, p.cols, pt); break;
 #define GATE_CASES_UNARY(OP) GATE_CASE(OP, KIND_T, 0) GATE_CASE(OP, KIND_L, 0) GATE_CASE(OP, KIND_I, 0)
 #define GATE_CASES_BINARY(OP)                                                                     \
   GATE_CASE(OP, KIND_T, KIND_T) GATE_CASE(OP, KIND_T, KIND_L) GATE_CASE(OP, KIND_T, KIND_I)      \
@@ -218,9 +210,10 @@ __global__ void __launch_bounds__(128) gate_eval_kernel(const GateEvalParams p) 
         const uint4* op = reinterpret_cast<const uint4*>(p.ops + gate.ops_begin);
         for (u32 i = 0; i < gate.n_ops; i++, op += 2) {
           const uint4 w = __ldg(op);  // code | dst, strides, operand a; operand b is fetched by the binary steps only
-          const u32 dst = w.x >> 8;
+          const u32 dst = w.x >> 8;   // destination slot, or the term index when the step pushes its value (bit 7 of the code)
           const u64 a_raw = ((u64)w.w << 32) | w.z;
-          switch (w.x & 0xffu) {
+          u64 r[K];
+          switch (w.x & 0x7fu) {
             case GATE_CODE_LINCOMB: {
               const uint4 wb = __ldg(op + 1);
               const u32 n = w.z;
@@ -236,10 +229,8 @@ __global__ void __launch_bounds__(128) gate_eval_kernel(const GateEvalParams p) 
 #pragma unroll
                 for (int k = 0; k < K; k++) sum[k] = gl::w96_add(sum[k], gl::mul_u32_wide(x[k], tm.y));
               }
-              u64 r[K];
 #pragma unroll
               for (int k = 0; k < K; k++) r[k] = gl::w96_reduce(sum[k]);
-              tmp.store(dst, r);
               const u32 extra = (n + 3) / 4;  // the term records are part of the step
               op += 2 * (size_t)extra;
               i += extra;
@@ -255,7 +246,20 @@ __global__ void __launch_bounds__(128) gate_eval_kernel(const GateEvalParams p) 
             GATE_CASES_UNARY(GATE_OP_PUSH)
             GATE_CASE(GATE_OP_MADD, KIND_T, KIND_T) GATE_CASE(GATE_OP_MADD, KIND_T, KIND_L) GATE_CASE(GATE_OP_MADD, KIND_T, KIND_I)
             GATE_CASE(GATE_OP_MADD, KIND_L, KIND_T) GATE_CASE(GATE_OP_MADD, KIND_L, KIND_L) GATE_CASE(GATE_OP_MADD, KIND_L, KIND_I)
-            default: break;
+            default:
+#pragma unroll
+              for (int k = 0; k < K; k++) r[k] = 0;
+              break;
+          }
+          if (w.x & 0x80u) {  // push_evaluation_result: the term times its alpha power goes into the gate's accumulator
+            const u64 a0 = __ldg(alpha_rep + 2 * dst), a1 = __ldg(alpha_rep + 2 * dst + 1);
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+              acc[k].c0 = gl::add(acc[k].c0, gl::mul(r[k], a0));
+              acc[k].c1 = gl::add(acc[k].c1, gl::mul(r[k], a1));
+            }
+          } else {
+            tmp.store(dst, r);
           }
         }
       }
@@ -290,19 +294,37 @@ static void gate_eval_launch(const GateEvalParams& p, cudaStream_t stream) {
 
 using namespace bj;
 
-extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_desc* h_gates, uint32_t n_gates,
-                                                     const uint64_t* const* h_variable_cols, uint32_t n_variables,
-                                                     const uint64_t* const* h_witness_cols, uint32_t n_witnesses,
-                                                     const uint64_t* const* h_constant_cols, uint32_t n_constants,
-                                                     const uint64_t* h_alpha_powers, uint32_t n_alpha_powers,
-                                                     uint64_t n_points, uint64_t* d_q_c0, uint64_t* d_q_c1) {
-  bj::DeviceGuard device_guard(ctx);
-  if (!ctx || !h_gates || n_gates == 0 || !d_q_c0 || !d_q_c1 || n_points == 0 || (!h_alpha_powers && n_alpha_powers))
-    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_quotient_gates_general_purpose: bad argument");
+// Host compiler of the recorded programs: validation, push placement, peephole, slot allocation, lowering.  Pure host code (no
+// device, no context): bj_gate_programs_compile exposes its output, and the CPU test suite runs an emulator of the step format
+// over it for every gate of the library under every peephole setting (tests/test_gate_compiler_cpu.py).
+namespace {
+struct GateCompileError {  // what BJ_FAIL writes to
+  std::string last_error;
+};
+struct CompiledGates {
   std::vector<DevGate> gates;
   std::vector<PackedOp> ops;
   uint32_t max_slots = 0;
   uint64_t total_terms = 0;
+};
+struct GatePeephole {
+  int gate_peephole;
+};
+
+int32_t compile_gates(GateCompileError* err, int peephole, const bj_gate_desc* h_gates, uint32_t n_gates, uint32_t n_variables,
+                      uint32_t n_witnesses, uint32_t n_constants, CompiledGates& compiled) {
+  GateCompileError* const ctx_err = err;
+  const GatePeephole settings{peephole};
+  const GatePeephole* const ctx = &settings;  // the passes below read ctx->gate_peephole
+#define GATE_FAIL(code, msg)               \
+  do {                                     \
+    if (ctx_err) ctx_err->last_error = (msg); \
+    return (code);                         \
+  } while (0)
+  std::vector<DevGate>& gates = compiled.gates;
+  std::vector<PackedOp>& ops = compiled.ops;
+  uint32_t& max_slots = compiled.max_slots;
+  uint64_t& total_terms = compiled.total_terms;
   // operand range checks against the columns the caller passed (all repetitions)
   auto check_index = [&](const bj_gate_index& ix, const bj_gate_desc& g, DevOperand* out) -> bool {
     const uint32_t reps = g.num_repetitions ? g.num_repetitions - 1 : 0;
@@ -334,7 +356,7 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     const bj_gate_desc& g = h_gates[gi];
     if (g.selector_path_len > 32 || g.selector_path_len > n_constants || (g.n_relations && !g.relations) ||
         (g.n_writes && !g.writes))
-      BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate descriptor: bad selector path or NULL program");
+      GATE_FAIL(BJ_ERR_INVALID_ARG, "gate descriptor: bad selector path or NULL program");
     DevGate d{};
     d.ops_begin = (u32)ops.size();
     d.n_writes = g.n_writes;
@@ -366,20 +388,20 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     for (uint32_t i = 0; i < g.n_relations; i++) {
       const bj_gate_relation& r = g.relations[i];
       if (r.op > BJ_REL_INVERSE || r.dst_temporary >= GATE_MAX_PROGRAM_TMP)
-        BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "gate program: unknown relation or temporary index beyond 2^20");
+        GATE_FAIL(BJ_ERR_UNSUPPORTED, "gate program: unknown relation or temporary index beyond 2^20");
       if (r.dst_temporary >= def_at.size()) def_at.resize(r.dst_temporary + 1, -1);
     }
     {
       std::vector<int32_t> def_rel(def_at.size(), -1);
       for (uint32_t i = 0; i < g.n_relations; i++) {
         if (def_rel[g.relations[i].dst_temporary] >= 0)
-          BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: temporary defined twice (programs are SSA)");
+          GATE_FAIL(BJ_ERR_INVALID_ARG, "gate program: temporary defined twice (programs are SSA)");
         def_rel[g.relations[i].dst_temporary] = (int32_t)i;
       }
       for (uint32_t k = 0; k < g.n_writes; k++) {
         const bj_gate_index& w = g.writes[k];
         if (w.kind == BJ_IDX_TEMPORARY) {
-          if (w.value >= def_rel.size() || def_rel[w.value] < 0) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: write of an undefined temporary");
+          if (w.value >= def_rel.size() || def_rel[w.value] < 0) GATE_FAIL(BJ_ERR_INVALID_ARG, "gate program: write of an undefined temporary");
           pushes_of[def_rel[w.value]].push_back(k);
         } else {
           late_pushes.push_back(k);
@@ -400,14 +422,14 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
       const bool binary = r.op == BJ_REL_ADD || r.op == BJ_REL_SUB || r.op == BJ_REL_MUL;
       const bj_gate_index bdummy{BJ_IDX_CONSTANT_VALUE, 0, 0};
       if (!defined(r.a) || (binary && !defined(r.b)) || !check_index(r.a, g, &o.a) || !check_index(binary ? r.b : bdummy, g, &o.b))
-        BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: operand out of range or temporary used before definition");
+        GATE_FAIL(BJ_ERR_INVALID_ARG, "gate program: operand out of range or temporary used before definition");
       def_at[r.dst_temporary] = (int32_t)prog.size();
       prog.push_back(o);
       for (uint32_t k : pushes_of[i])
-        if (!emit_push(k)) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: write operand out of range");
+        if (!emit_push(k)) GATE_FAIL(BJ_ERR_INVALID_ARG, "gate program: write operand out of range");
     }
     for (uint32_t k : late_pushes)
-      if (!emit_push(k)) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "gate program: write operand out of range");
+      if (!emit_push(k)) GATE_FAIL(BJ_ERR_INVALID_ARG, "gate program: write operand out of range");
     // 1b. peephole over the recorded program.  Evaluators written against a generic field interface record what they execute:
     //     the Poseidon2 flattened gate multiplies by the matrix entry 1 3228 times and starts 372 sums at the constant 0
     //     (9636 relations, 6036 after this pass).  x * 1, x + 0, x - 0 become aliases of x, x * 0 the constant 0; a product
@@ -558,6 +580,23 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
       for (size_t i = 0; i < kept.size(); i++)
         if (!dead[i]) prog.push_back(kept[i]);
     }
+    // 1c. a step whose value is read by nothing but the push_evaluation_result that follows it pushes the value itself
+    if (ctx->gate_peephole & 8) {
+      std::vector<uint32_t> uses(def_at.size(), 0);
+      for (DevOp& o : prog) each_temp(o, [&](DevOperand& t) { uses[t.value]++; });
+      std::vector<DevOp> out;
+      out.reserve(prog.size());
+      for (const DevOp& o : prog) {
+        if (o.op == GATE_OP_PUSH && o.a.kind == BJ_IDX_TEMPORARY && !out.empty() && out.back().op != GATE_OP_PUSH && !out.back().push &&
+            out.back().dst == o.a.value && uses[o.a.value] == 1) {
+          out.back().push = true;
+          out.back().dst = o.dst;  // the term index
+          continue;
+        }
+        out.push_back(o);
+      }
+      prog.swap(out);
+    }
     // 2. slot allocation: a temporary lives from its definition to its last use; its slot is then reused (the kernel reads both
     //    operands before it writes the destination, so a destination may take over the slot of an operand that dies there)
     {
@@ -568,7 +607,7 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
       uint32_t next_slot = 0;
       for (size_t i = 0; i < prog.size(); i++) {
         DevOp& o = prog[i];
-        const bool is_push = o.op == GATE_OP_PUSH;
+        const bool is_push = o.op == GATE_OP_PUSH || o.push;
         read.clear();
         each_temp(o, [&](DevOperand& t) {
           if (std::find(read.begin(), read.end(), t.value) == read.end()) read.push_back(t.value);
@@ -586,7 +625,7 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
           sl = next_slot++;
         }
         if (sl >= (uint32_t)GATE_MAX_TMP)
-          BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "gate program: more than 128 temporaries live at once");
+          GATE_FAIL(BJ_ERR_UNSUPPORTED, "gate program: more than 128 temporaries live at once");
         slot[t_dst] = (int32_t)sl;
         o.dst = sl;
         if (last_use[t_dst] < 0) free_slots.push_back(sl);  // defined but never read
@@ -611,12 +650,12 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
         }
       };
       if (g.variables_offset > 0xffffu || g.witnesses_offset > 0xffffu || g.constants_offset > 0xffffu || g.n_writes >= (1u << 24))
-        BJ_FAIL(ctx, BJ_ERR_UNSUPPORTED, "gate descriptor: per-repetition offset beyond 65535 or more than 2^24 terms");
+        GATE_FAIL(BJ_ERR_UNSUPPORTED, "gate descriptor: per-repetition offset beyond 65535 or more than 2^24 terms");
       for (const DevOp& o : prog) {
         if (o.op == GATE_OP_LINCOMB) {
           const std::vector<LcTerm>& terms = lincombs[o.lc];
           PackedOp head{};
-          head.code_dst = GATE_CODE_LINCOMB | (o.dst << 8);
+          head.code_dst = GATE_CODE_LINCOMB | (o.push ? 0x80u : 0u) | (o.dst << 8);
           head.strides = g.variables_offset;
           head.a = terms.size();
           head.b = o.a.value;
@@ -641,7 +680,7 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
         const bool binary = o.op == BJ_REL_ADD || o.op == BJ_REL_SUB || o.op == BJ_REL_MUL || o.op == GATE_OP_MADD;
         const int kb = binary ? lower(o.b, &po.b, &sb) : 0;
         if (o.op == GATE_OP_MADD) po.c = o.c.value;
-        po.code_dst = gate_code(o.op, ka, kb) | (o.dst << 8);
+        po.code_dst = gate_code(o.op, ka, kb) | ((o.op == GATE_OP_PUSH || o.push) ? 0x80u : 0u) | (o.dst << 8);
         po.strides = sa | (sb << 16);
         ops.push_back(po);
       }
@@ -650,6 +689,50 @@ extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_
     total_terms += (uint64_t)g.n_writes * g.num_repetitions;
     gates.push_back(d);
   }
+  return BJ_OK;
+#undef GATE_FAIL
+}
+}  // namespace
+
+extern "C" int32_t bj_gate_programs_compile(const bj_gate_desc* h_gates, uint32_t n_gates, uint32_t n_variables, uint32_t n_witnesses,
+                                            uint32_t n_constants, uint32_t peephole, uint64_t* h_records, uint64_t capacity_records,
+                                            uint64_t* n_records, uint32_t* h_gate_first_record, uint32_t* max_live_temporaries) {
+  if (!h_gates || n_gates == 0 || !n_records) return BJ_ERR_INVALID_ARG;
+  CompiledGates c;
+  const int32_t st = compile_gates(nullptr, (int)peephole, h_gates, n_gates, n_variables, n_witnesses, n_constants, c);
+  if (st != BJ_OK) return st;
+  *n_records = c.ops.size();
+  if (max_live_temporaries) *max_live_temporaries = c.max_slots;
+  if (h_gate_first_record) {
+    for (uint32_t g = 0; g < n_gates; g++) h_gate_first_record[g] = c.gates[g].ops_begin;
+    h_gate_first_record[n_gates] = (uint32_t)c.ops.size();
+  }
+  if (h_records) {
+    if (capacity_records < c.ops.size()) return BJ_ERR_INVALID_ARG;
+    memcpy(h_records, c.ops.data(), sizeof(PackedOp) * c.ops.size());
+  }
+  return BJ_OK;
+}
+
+extern "C" int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_desc* h_gates, uint32_t n_gates,
+                                                     const uint64_t* const* h_variable_cols, uint32_t n_variables,
+                                                     const uint64_t* const* h_witness_cols, uint32_t n_witnesses,
+                                                     const uint64_t* const* h_constant_cols, uint32_t n_constants,
+                                                     const uint64_t* h_alpha_powers, uint32_t n_alpha_powers,
+                                                     uint64_t n_points, uint64_t* d_q_c0, uint64_t* d_q_c1) {
+  bj::DeviceGuard device_guard(ctx);
+  if (!ctx || !h_gates || n_gates == 0 || !d_q_c0 || !d_q_c1 || n_points == 0 || (!h_alpha_powers && n_alpha_powers))
+    BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "bj_quotient_gates_general_purpose: bad argument");
+  CompiledGates compiled;
+  {
+    GateCompileError err;
+    const int32_t st = compile_gates(&err, ctx->gate_peephole, h_gates, n_gates, n_variables, n_witnesses, n_constants, compiled);
+    if (st != BJ_OK) BJ_FAIL(ctx, st, err.last_error);
+  }
+  std::vector<DevGate>& gates = compiled.gates;
+  std::vector<PackedOp>& ops = compiled.ops;
+  const uint32_t max_slots = compiled.max_slots;
+  const uint64_t total_terms = compiled.total_terms;
   if (total_terms > n_alpha_powers) BJ_FAIL(ctx, BJ_ERR_INVALID_ARG, "not enough alpha powers for the gate terms");
   std::vector<u64> alphas(2 * (size_t)total_terms);
   for (size_t i = 0; i < alphas.size(); i++) alphas[i] = gl::canon(h_alpha_powers[i]);

@@ -76,6 +76,7 @@ SIGNATURES = {
     "bj_lookup_polys_specialized": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp]),
     "bj_quotient_lookup_specialized": (_i32, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "bj_quotient_gates_general_purpose": (_i32, [_vp, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _u64, _vp, _vp]),
+    "bj_gate_programs_compile": (_i32, [_vp, _u32, _u32, _u32, _u32, _u32, _vp, _u64, _vp, _vp, _vp]),
     "bj_ntt_natural_to_bitreversed_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
     "bj_intt_natural_to_natural_host": (_i32, [_vp, _vp, _u32, _u32, _u64]),
     "bj_transcript_new": (_vp, []),

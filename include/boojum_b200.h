@@ -271,6 +271,24 @@ BJ_API int32_t bj_quotient_gates_general_purpose(bj_ctx* ctx, const bj_gate_desc
                                           const uint64_t* const* h_constant_cols, uint32_t n_constants,
                                           const uint64_t* h_alpha_powers, uint32_t n_alpha_powers,
                                           uint64_t n_points, uint64_t* d_q_c0, uint64_t* d_q_c1);
+/* What the evaluator will execute for these gates - pure host code, no device needed.  The recorded programs are validated
+ * (SSA, operand ranges against n_variables / n_witnesses / n_constants), rewritten (peephole bits: 1 = x*1, x+0, x*0 become
+ * aliases; 2 = a product whose only use is a sum becomes a multiply-add; 4 = trees of single-use sums over products with
+ * immediates < 2^28 become one linear combination; 8 = a value read only by push_evaluation_result is pushed by the step that
+ * computes it; 15 = what bj_quotient_gates_general_purpose uses) and lowered to 32-byte records = 4 little-endian u64:
+ *   word 0: code (bits 0-6) | pushes-its-value flag (bit 7) | destination slot or term index (bits 8-31) |
+ *           per-repetition column stride of operand a (bits 32-47) and b (bits 48-63);  word 1: operand a;  word 2: operand b;
+ *   word 3: addend slot of a multiply-add.  Operand classes T (slot), L (index into [variables | witnesses | constants] at
+ *   repetition 0), I (immediate).  Codes: ADD 0-8, SUB 9-17, MUL 18-26 = base + 3 * class(a) + class(b) with T, L, I = 0, 1, 2;
+ *   DOUBLE 27-29, NEGATE 30-32, SQUARE 33-35, INVERSE 36-38, MOVE 39-41 = base + class(a); multiply-add a * b + slot 42-47 =
+ *   42 + 3 * class(a) + class(b), class(a) in {T, L}; 48 = linear combination: word 0 stride = variables stride, word 1 = number
+ *   of terms n, word 2 = constant term, followed by ceil(n / 4) records of four (u32 ref, u32 k) pairs, ref = slot or
+ *   0x80000000 | variable column.
+ * h_records may be NULL (sizes only); h_gate_first_record has n_gates + 1 entries.  Used by the CPU test suite, which runs an
+ * emulator of this format against the gate evaluators (tests/test_gate_compiler_cpu.py). */
+BJ_API int32_t bj_gate_programs_compile(const bj_gate_desc* h_gates, uint32_t n_gates, uint32_t n_variables, uint32_t n_witnesses,
+                                 uint32_t n_constants, uint32_t peephole, uint64_t* h_records, uint64_t capacity_records,
+                                 uint64_t* n_records, uint32_t* h_gate_first_record, uint32_t* max_live_temporaries);
 
 /* ---- quotient: copy-permutation relations + the z(1) = 1 term (src/cs/implementations/copy_permutation.rs:1000-1249,
  *      src/cs/implementations/prover.rs:1189-1227) over the first 2^log_quotient_degree cosets of the LDE ----

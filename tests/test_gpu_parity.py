@@ -607,8 +607,8 @@ def test_gate_programs_of_the_reference_fixture_circuit(bj, ctx, golden_fixture)
         ck.synchronize()
         assert np.array_equal(bj.to_numpy(e0), g0) and np.array_equal(bj.to_numpy(e1), g1), k
         ck.close()
-    # the host peephole (x * 1, x + 0 aliases; multiply-add fusion) changes the program, not the values: all settings agree (7 = default: aliases, multiply-add fusion, linear combinations)
-    for mode in (0, 1, 3, 5):
+    # the host peephole (x * 1, x + 0 aliases; multiply-add fusion) changes the program, not the values: all settings agree (15 = default: aliases, multiply-add fusion, linear combinations, pushing steps)
+    for mode in (0, 1, 3, 7, 13):
         os.environ["BJ_GATE_PEEPHOLE"] = str(mode)
         try:
             ck = bj.Context(0)
