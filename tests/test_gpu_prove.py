@@ -342,6 +342,34 @@ def test_production_shaped_circuit(env, hasher, transcript):
     nat.close()
 
 
+@pytest.mark.parametrize("log_n,V,L,cap,lookup,pis", [(5, 20, 8, 16, False, ()), (6, 20, 4, 8, True, ((1, 3), (5, 3), (0, 9))),
+                                                        (6, 20, 2, 8, True, ()), (7, 40, 8, 16, True, ((2, 100),)), (9, 60, 8, 16, True, ((0, 1), (59, 511)))])
+def test_proof_equals_the_cpu_oracle_prover(env, log_n, V, L, cap, lookup, pis):
+    """bj_prove returns, bit for bit, the proof of the oracle's own CPU prover (oracle/prover.py: prove_cpu_basic restated end
+    to end - quotient point by point in Python integers, openings by Horner from the monomial forms, C restatement of NTT /
+    Merkle / FRI) on a circuit generated on the CPU (oracle/circuits.py): transcript order, challenges, caps, openings, the FRI
+    chain, query indices and every Merkle path agree - incl. lookups, public inputs and an LDE factor below the quotient degree."""
+    bj, ctx, prover, synthetic = env
+    from oracle import circuits, prover as OP
+    c = circuits.sha_shaped(log_n, V, seed=100 + log_n, lookup=lookup)
+    want, want_setup_cap = OP.prove(c["variables"], c["sigmas"], c["constants"], c["gates"], c["quotient_degree"], L, cap,
+                                    lookup=c["lookup"], public_inputs=pis)
+    gates = synthetic.sha_shaped_gates(V)
+    assert [(g["name"], g["num_repetitions"], g["selector_path"]) for g in gates] == [tuple(g) for g in c["gates"]]
+    lk = None
+    if lookup:
+        lk = dict(c["lookup"], tables=bj.to_device(c["lookup"]["tables"]), multiplicities=bj.to_device(c["lookup"]["multiplicities"]))
+    cfg = prover.ProofConfig(fri_lde_factor=L, merkle_tree_cap_size=cap, security_level=100)
+    nat = ctx.native_setup(bj.to_device(c["sigmas"]), bj.to_device(c["constants"]), gates, c["quotient_degree"], cfg, lookup=lk,
+                           public_inputs=list(pis))
+    assert np.array_equal(nat.get_cap(), want_setup_cap)
+    got = nat.prove(bj.to_device(c["variables"]), lk["multiplicities"] if lk else None)
+    nat.close()
+    for key in want:                      # field by field first (a readable failure), then the whole document
+        assert got[key] == want[key], key
+    assert json.dumps(got, sort_keys=True) == json.dumps(want, sort_keys=True)
+
+
 def test_recursive_mode_poseidon2_type_parameters(env):
     """H = GoldilocksPoseidon2Sponge, TR = GoldilocksPoisedonTranscript (Poseidon v1 sponge): the type parameters of
     run_sha256_prover_recursive_mode_poseidon2 (src/gadgets/sha256/mod.rs:286-293, BASELINE configs[4]).  Both drivers give the

@@ -1,0 +1,40 @@
+"""The oracle's own CPU prover (oracle/prover.py: prove_cpu_basic restated end to end on the oracle primitives, openings by
+Horner from monomials, quotient point by point) and the oracle verifier agree - the pair the GPU library's proofs are compared
+with bit for bit in tests/test_gpu_prove.py::test_proof_equals_the_cpu_oracle_prover."""
+import json
+
+import pytest
+
+from oracle import circuits, prover as OP, verifier as OV
+
+
+def vk_of(c, L, cap, setup_cap, public_inputs=()):
+    lk = c["lookup"]
+    return {"domain_size": c["variables"].shape[1], "num_variables": c["variables"].shape[0], "num_constants": c["constants"].shape[0],
+            "quotient_degree": c["quotient_degree"], "fri_lde_factor": L, "cap_size": cap,
+            "gates": [(name, reps, path, 0, len(path)) for name, reps, path in c["gates"]],
+            "lookup": {k: lk[k] for k in ("width", "num_repetitions", "variables_offset", "table_id_column")} if lk else None,
+            "public_inputs_locations": [list(p) for p in public_inputs], "hasher": "poseidon2", "transcript": "poseidon2",
+            "setup_merkle_tree_cap": setup_cap.tolist()}
+
+
+@pytest.mark.parametrize("log_n,V,L,cap,lookup,pis", [(5, 20, 8, 16, False, ()), (6, 20, 4, 8, True, ((1, 3), (5, 3), (0, 9))),
+                                                        (6, 20, 2, 8, True, ())])
+def test_cpu_prover_and_verifier_agree(log_n, V, L, cap, lookup, pis):
+    c = circuits.sha_shaped(log_n, V, seed=log_n, lookup=lookup)
+    proof, setup_cap = OP.prove(c["variables"], c["sigmas"], c["constants"], c["gates"], c["quotient_degree"], L, cap,
+                                lookup=c["lookup"], public_inputs=pis)
+    vk = vk_of(c, L, cap, setup_cap, pis)
+    assert OV.verify(vk, proof)
+    bad = json.loads(json.dumps(proof))
+    bad["values_at_z"][2]["coeffs"][0] ^= 1
+    with pytest.raises(AssertionError):
+        OV.verify(vk, bad)
+
+
+def test_cpu_prover_refuses_an_unsatisfied_witness():
+    c = circuits.sha_shaped(5, 20, seed=1)
+    w = c["variables"].copy()
+    w[7, 11] ^= 1
+    with pytest.raises((ValueError, AssertionError)):
+        OP.prove(w, c["sigmas"], c["constants"], c["gates"], c["quotient_degree"], 8, 16)
