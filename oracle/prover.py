@@ -3,7 +3,8 @@ an independent CPU prover for SMALL circuits, so that the proof of the GPU libra
 
 Follows src/cs/implementations/prover.rs:153-2269 round by round (the line ranges are quoted at each step) for circuits made of
 the three bench gates (oracle/gates.py), optionally with the lookup argument over specialised columns with the table id in a
-constant column and with public inputs; tree hasher Poseidon2, transcript GoldilocksPoisedon2Transcript; no proof of work.
+constant column and with public inputs; every tree hasher (Poseidon2 / Blake2s256 / Keccak256) and transcript (Poseidon2,
+Poseidon, Blake2s, Keccak256) of the reference - the bench's two type-parameter pairs included; no proof of work.
 Where the GPU library evaluates on the LDE domain with kernels, this file loops over the points in Python with the point-wise
 restatements of oracle/stage2.py, oracle/lookup.py and oracle/gates.py; NTT / LDE / Merkle / FRI folds / DEEP come from the C
 restatement (oracle/oracle.c).  Openings are evaluated from the MONOMIAL forms by Horner's rule (the library uses barycentric
@@ -41,8 +42,20 @@ def _ext_columns(vals):
     return (np.array([v[0] for v in vals], dtype=np.uint64), np.array([v[1] for v in vals], dtype=np.uint64))
 
 
+TRANSCRIPTS = {"poseidon2": R.Poseidon2Transcript, "poseidon": R.PoseidonTranscript, "blake2s": R.Blake2sTranscript,
+               "keccak256": R.Keccak256Transcript}
+
+
+def _serde(digests, hasher):
+    """TreeHasher::Output values (4 u64 words each) in serde form: [u64; 4] for Poseidon2, [u8; 32] for Blake2s256 / Keccak256"""
+    a = np.ascontiguousarray(np.asarray(digests, dtype=np.uint64).reshape(-1, 4))
+    if hasher == "poseidon2":
+        return a.tolist()
+    return a.astype("<u8").view(np.uint8).reshape(-1, 32).tolist()
+
+
 def prove(variables, sigmas, constants, gates, quotient_degree, fri_lde_factor, cap_size, security_level=100, lookup=None,
-          public_inputs=()):
+          public_inputs=(), hasher="poseidon2", transcript=None):
     """variables / sigmas: [V, n], constants: [C, n] uint64 arrays in natural row order; gates: [(name, repetitions, selector
     path)] of oracle/gates.py in registration order; lookup: None or dict(width, num_repetitions, variables_offset,
     table_id_column, tables [width + 1, n], multiplicities [n]); public_inputs: [(column, row)]."""
@@ -58,7 +71,8 @@ def prove(variables, sigmas, constants, gates, quotient_degree, fri_lde_factor, 
     tables = np.asarray(lk["tables"], dtype=np.uint64) if lk else np.zeros((0, n), np.uint64)
     mult = np.asarray(lk["multiplicities"], dtype=np.uint64) if lk else None
     T = tables.shape[0]
-    commit = lambda cols: O.merkle_tree([c[:ncm] for c in cols], cap_size)
+    tree = lambda cols: R.merkle_tree_with_hasher(cols, cap_size, 1, hasher)
+    commit = lambda cols: tree([c[:ncm] for c in cols])
 
     # ---- setup oracle: sigmas | constants | lookup tables (setup.rs:1093-1255) ----
     setup_lde = O.lde(np.concatenate([sigmas, constants, tables]), log_d)
@@ -66,7 +80,7 @@ def prove(variables, sigmas, constants, gates, quotient_degree, fri_lde_factor, 
     sigma_cols, const_cols, table_cols = setup_cols[:V], setup_cols[V:V + C], setup_cols[V + C:]
     setup_lh, setup_lv, setup_cap = commit(setup_cols)
 
-    tr = R.Poseidon2Transcript()
+    tr = TRANSCRIPTS[transcript or hasher]()
     tr.witness_merkle_tree_cap(setup_cap.tolist())                       # prover.rs:211
     public_values = [int(variables[c, r]) for c, r in public_inputs]
     for v in public_values:                                              # prover.rs:264-266
@@ -137,7 +151,7 @@ def prove(variables, sigmas, constants, gates, quotient_degree, fri_lde_factor, 
     chunks = np.stack([mono_q[k][j * n:(j + 1) * n] for j in range(Q) for k in (0, 1)])   # c0, c1 of chunk 0, chunk 1, ...
     qt_lde = O.lde(chunks, log_l, from_monomials=True)
     qt_cols = [_flat(qt_lde, c) for c in range(2 * Q)]
-    qt_lh, qt_lv, qt_cap = O.merkle_tree(qt_cols, cap_size)
+    qt_lh, qt_lv, qt_cap = tree(qt_cols)
     tr.witness_merkle_tree_cap(qt_cap.tolist())
 
     # ---- round 4: openings from the monomial forms (prover.rs:1501-1802) ----
@@ -200,12 +214,12 @@ def prove(variables, sigmas, constants, gates, quotient_degree, fri_lde_factor, 
         off += len(members)
     new_pow, num_queries, schedule, final_degree = R.compute_fri_schedule(security_level, cap_size, 0, log_l, log_n)
     assert new_pow == 0, "the oracle prover does not grind"
-    fri = R.do_fri_oracle(d0, d1, tr, schedule, log_l, cap_size)
+    fri = R.do_fri_oracle(d0, d1, tr, schedule, log_l, cap_size, hasher)
 
     # ---- queries (prover.rs:2161-2266) ----
     max_bits = log_n + log_l
     bools = R.BoolsBuffer(max_bits)
-    answer = lambda cols, lh, lv, idx: {"leaf_elements": [int(col[idx]) for col in cols], "proof": O.merkle_path(lh, lv, idx).tolist()}
+    answer = lambda cols, lh, lv, idx: {"leaf_elements": [int(col[idx]) for col in cols], "proof": _serde(O.merkle_path(lh, lv, idx), hasher)}
     queries = []
     for _ in range(num_queries):
         bits = bools.get_bits(tr, max_bits)
@@ -218,7 +232,7 @@ def prove(variables, sigmas, constants, gates, quotient_degree, fri_lde_factor, 
             lh, lv = fri["trees"][lvl]
             leaf, deg = sub >> k, 1 << k
             le = [int(x) for x in c0_l[leaf * deg:(leaf + 1) * deg]] + [int(x) for x in c1_l[leaf * deg:(leaf + 1) * deg]]
-            fqs.append({"leaf_elements": le, "proof": O.merkle_path(lh, lv, leaf).tolist()})
+            fqs.append({"leaf_elements": le, "proof": _serde(O.merkle_path(lh, lv, leaf), hasher)})
             sub >>= k
         q["fri_queries"] = fqs
         queries.append(q)
@@ -226,11 +240,11 @@ def prove(variables, sigmas, constants, gates, quotient_degree, fri_lde_factor, 
         "proof_config": {"fri_lde_factor": L, "merkle_tree_cap_size": cap_size, "fri_folding_schedule": None,
                          "security_level": security_level, "pow_bits": 0},
         "public_inputs": public_values,
-        "witness_oracle_cap": w_cap.tolist(), "stage_2_oracle_cap": s2_cap.tolist(), "quotient_oracle_cap": qt_cap.tolist(),
+        "witness_oracle_cap": _serde(w_cap, hasher), "stage_2_oracle_cap": _serde(s2_cap, hasher), "quotient_oracle_cap": _serde(qt_cap, hasher),
         "final_fri_monomials": [fri["monomials"][0].tolist(), fri["monomials"][1].tolist()],
         "values_at_z": [_ext_dict(v) for v in values_at_z], "values_at_z_omega": [_ext_dict(v) for v in values_at_z_omega],
         "values_at_0": [_ext_dict(v) for v in values_at_0],
-        "fri_base_oracle_cap": fri["caps"][0].tolist(), "fri_intermediate_oracles_caps": [cp.tolist() for cp in fri["caps"][1:]],
+        "fri_base_oracle_cap": _serde(fri["caps"][0], hasher), "fri_intermediate_oracles_caps": [_serde(cp, hasher) for cp in fri["caps"][1:]],
         "queries_per_fri_repetition": queries, "pow_challenge": 0, "_marker": None,
     }
     return proof, setup_cap

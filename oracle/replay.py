@@ -582,7 +582,25 @@ def replay_proof(fixture, num_variable_polys=None):
 
 
 # ------------------------------------------------------------------ prover-side FRI commit phase (oracle) ----------
-def do_fri_oracle(c0, c1, transcript, schedule, log_lde, cap_size):
+def merkle_tree_with_hasher(sources, cap_size, elems_per_leaf=1, hasher="poseidon2"):
+    """MerkleTreeWithCap::construct* for any TreeHasher -> (leaf hashes [n, 4], levels bottom-up, cap), digests as 4 u64 words.
+    Poseidon2 goes through the C restatement; Blake2s256 / Keccak256 are hashed here (hashlib / oracle/keccak.py), leaf preimage =
+    the leaf's elements source by source (src/cs/oracle/merkle_tree.rs:78-449)."""
+    if hasher == "poseidon2":
+        return O.merkle_tree(sources, cap_size, elems_per_leaf)
+    leaf_fn, node_fn = {"blake2s": (blake2s_leaf_hash, blake2s_node_hash), "keccak256": (keccak_leaf_hash, keccak_node_hash)}[hasher]
+    srcs = [np.asarray(x, dtype=np.uint64).reshape(-1) for x in sources]
+    n_leaves = srcs[0].shape[0] // elems_per_leaf
+    lh = np.array([leaf_fn([int(v) for x in srcs for v in x[t * elems_per_leaf:(t + 1) * elems_per_leaf]]) for t in range(n_leaves)],
+                  dtype=np.uint64).reshape(n_leaves, 4)
+    levels, cur = [], lh
+    while cur.shape[0] > cap_size:
+        cur = np.array([node_fn(cur[2 * i], cur[2 * i + 1]) for i in range(cur.shape[0] // 2)], dtype=np.uint64).reshape(-1, 4)
+        levels.append(cur)
+    return lh, levels, (levels[-1] if levels else lh)
+
+
+def do_fri_oracle(c0, c1, transcript, schedule, log_lde, cap_size, hasher="poseidon2"):
     """do_fri restated on the oracle primitives (src/cs/implementations/fri/mod.rs:49-357).
     c0, c1: flat LDE codeword (numpy uint64).  Returns dict(caps, challenges, levels=[(c0,c1)], monomials=(m0,m1))."""
     log_full = len(c0).bit_length() - 1
@@ -592,7 +610,7 @@ def do_fri_oracle(c0, c1, transcript, schedule, log_lde, cap_size):
     cur0, cur1 = np.array(c0, dtype=np.uint64), np.array(c1, dtype=np.uint64)
     for k in schedule:
         levels.append((cur0, cur1))
-        lh, lv, cap = O.merkle_tree([cur0, cur1], cap_size, elems_per_leaf=1 << k)
+        lh, lv, cap = merkle_tree_with_hasher([cur0, cur1], cap_size, 1 << k, hasher)
         trees.append((lh, lv))
         caps.append(cap)
         transcript.witness_merkle_tree_cap(cap.tolist())

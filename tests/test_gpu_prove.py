@@ -342,9 +342,13 @@ def test_production_shaped_circuit(env, hasher, transcript):
     nat.close()
 
 
-@pytest.mark.parametrize("log_n,V,L,cap,lookup,pis", [(5, 20, 8, 16, False, ()), (6, 20, 4, 8, True, ((1, 3), (5, 3), (0, 9))),
-                                                        (6, 20, 2, 8, True, ()), (7, 40, 8, 16, True, ((2, 100),)), (9, 60, 8, 16, True, ((0, 1), (59, 511)))])
-def test_proof_equals_the_cpu_oracle_prover(env, log_n, V, L, cap, lookup, pis):
+@pytest.mark.parametrize("log_n,V,L,cap,lookup,pis,hasher,transcript", [
+    (5, 20, 8, 16, False, (), "poseidon2", "poseidon2"), (6, 20, 4, 8, True, ((1, 3), (5, 3), (0, 9)), "poseidon2", "poseidon2"),
+    (6, 20, 2, 8, True, (), "poseidon2", "poseidon2"), (7, 40, 8, 16, True, ((2, 100),), "poseidon2", "poseidon2"),
+    (9, 60, 8, 16, True, ((0, 1), (59, 511)), "poseidon2", "poseidon2"),
+    (6, 20, 8, 16, True, ((3, 5),), "blake2s", "blake2s"), (6, 20, 8, 16, True, ((3, 5),), "poseidon2", "poseidon"),
+    (5, 20, 4, 8, True, (), "keccak256", "keccak256")])
+def test_proof_equals_the_cpu_oracle_prover(env, log_n, V, L, cap, lookup, pis, hasher, transcript):
     """bj_prove returns, bit for bit, the proof of the oracle's own CPU prover (oracle/prover.py: prove_cpu_basic restated end
     to end - quotient point by point in Python integers, openings by Horner from the monomial forms, C restatement of NTT /
     Merkle / FRI) on a circuit generated on the CPU (oracle/circuits.py): transcript order, challenges, caps, openings, the FRI
@@ -353,13 +357,13 @@ def test_proof_equals_the_cpu_oracle_prover(env, log_n, V, L, cap, lookup, pis):
     from oracle import circuits, prover as OP
     c = circuits.sha_shaped(log_n, V, seed=100 + log_n, lookup=lookup)
     want, want_setup_cap = OP.prove(c["variables"], c["sigmas"], c["constants"], c["gates"], c["quotient_degree"], L, cap,
-                                    lookup=c["lookup"], public_inputs=pis)
+                                    lookup=c["lookup"], public_inputs=pis, hasher=hasher, transcript=transcript)
     gates = synthetic.sha_shaped_gates(V)
     assert [(g["name"], g["num_repetitions"], g["selector_path"]) for g in gates] == [tuple(g) for g in c["gates"]]
     lk = None
     if lookup:
         lk = dict(c["lookup"], tables=bj.to_device(c["lookup"]["tables"]), multiplicities=bj.to_device(c["lookup"]["multiplicities"]))
-    cfg = prover.ProofConfig(fri_lde_factor=L, merkle_tree_cap_size=cap, security_level=100)
+    cfg = prover.ProofConfig(fri_lde_factor=L, merkle_tree_cap_size=cap, security_level=100, hasher=hasher, transcript=transcript)
     nat = ctx.native_setup(bj.to_device(c["sigmas"]), bj.to_device(c["constants"]), gates, c["quotient_degree"], cfg, lookup=lk,
                            public_inputs=list(pis))
     assert np.array_equal(nat.get_cap(), want_setup_cap)

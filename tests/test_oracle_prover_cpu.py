@@ -8,13 +8,13 @@ import pytest
 from oracle import circuits, prover as OP, verifier as OV
 
 
-def vk_of(c, L, cap, setup_cap, public_inputs=()):
+def vk_of(c, L, cap, setup_cap, public_inputs=(), hasher="poseidon2", transcript="poseidon2"):
     lk = c["lookup"]
     return {"domain_size": c["variables"].shape[1], "num_variables": c["variables"].shape[0], "num_constants": c["constants"].shape[0],
             "quotient_degree": c["quotient_degree"], "fri_lde_factor": L, "cap_size": cap,
             "gates": [(name, reps, path, 0, len(path)) for name, reps, path in c["gates"]],
             "lookup": {k: lk[k] for k in ("width", "num_repetitions", "variables_offset", "table_id_column")} if lk else None,
-            "public_inputs_locations": [list(p) for p in public_inputs], "hasher": "poseidon2", "transcript": "poseidon2",
+            "public_inputs_locations": [list(p) for p in public_inputs], "hasher": hasher, "transcript": transcript,
             "setup_merkle_tree_cap": setup_cap.tolist()}
 
 
@@ -28,6 +28,24 @@ def test_cpu_prover_and_verifier_agree(log_n, V, L, cap, lookup, pis):
     assert OV.verify(vk, proof)
     bad = json.loads(json.dumps(proof))
     bad["values_at_z"][2]["coeffs"][0] ^= 1
+    with pytest.raises(AssertionError):
+        OV.verify(vk, bad)
+
+
+@pytest.mark.parametrize("hasher,transcript", [("blake2s", "blake2s"), ("poseidon2", "poseidon"), ("keccak256", "keccak256")])
+def test_cpu_prover_other_type_parameters(hasher, transcript):
+    """the bench's second pair (Blake2s256 tree + Blake2sTranscript, sha256/mod.rs:264-271), the recursive-mode pair (Poseidon2
+    tree + Poseidon transcript, :286-293) and Keccak256"""
+    c = circuits.sha_shaped(5, 20, seed=3, lookup=True)
+    pis = ((0, 2),)
+    proof, setup_cap = OP.prove(c["variables"], c["sigmas"], c["constants"], c["gates"], c["quotient_degree"], 4, 8, lookup=c["lookup"],
+                                public_inputs=pis, hasher=hasher, transcript=transcript)
+    vk = vk_of(c, 4, 8, setup_cap, pis, hasher, transcript)
+    assert OV.verify(vk, proof)
+    if hasher != "poseidon2":
+        assert len(proof["witness_oracle_cap"][0]) == 32          # [u8; 32] digests
+    bad = json.loads(json.dumps(proof))
+    bad["queries_per_fri_repetition"][0]["witness_query"]["leaf_elements"][0] ^= 1
     with pytest.raises(AssertionError):
         OV.verify(vk, bad)
 
