@@ -40,18 +40,68 @@ def selector(path, const_row):
     return s
 
 
+# Index / Relation numbering of recorded programs (gpu_synthesizer/mod.rs:115-133; include/boojum_b200.h BJ_IDX_* / BJ_REL_*)
+_VAR, _WIT, _CONST, _TMP, _IMM, _SHARED = range(6)
+
+
+def program_terms(prog, var_row, const_row, var_base, shared_base, const_base):
+    """one repetition of a recorded SSA program (GPUDataCapture: dict(relations, writes)) over base-field values of one point"""
+    tmp = {}
+
+    def fetch(o):
+        kind, val = o
+        if kind == _VAR:
+            return var_row[var_base + val]
+        if kind == _CONST:
+            return const_row[const_base + val]
+        if kind == _SHARED:
+            return const_row[shared_base + val]
+        if kind == _TMP:
+            return tmp[val]
+        assert kind == _IMM, "witness columns are not used by these circuits"
+        return int(val) % P
+
+    for op, dst, a, b in prog["relations"]:
+        x = fetch(a)
+        if op == 0:
+            r = x + fetch(b)
+        elif op == 1:
+            r = 2 * x
+        elif op == 2:
+            r = x - fetch(b)
+        elif op == 3:
+            r = -x
+        elif op == 4:
+            r = x * fetch(b)
+        elif op == 5:
+            r = x * x
+        else:
+            assert op == 6
+            r = pow(x, P - 2, P)
+        tmp[dst] = r % P
+    return [fetch(w) for w in prog["writes"]]
+
+
 def quotient_gates_row(gates, var_row, const_row, alphas):
-    """gates: list of (name, num_repetitions, selector_path).  Returns the (c0, c1) contribution of one point."""
+    """gates: list of (name, num_repetitions, selector_path[, first variable column, first constant column[, program]]) - the
+    three bench gates by name, any other gate as its recorded program (specialised-column gates have an empty path and their own
+    first columns).  Returns the (c0, c1) contribution of one point."""
     q0 = q1 = 0
     k = 0
-    for name, reps, path in gates:
-        fn, width, _, (voff, coff) = GATES[name]
-        place = len(path)
+    for g in gates:
+        name, reps, path = g[0], g[1], g[2]
+        var0 = g[3] if len(g) > 3 else 0
+        place = g[4] if len(g) > 4 else len(path)
         a0 = a1 = 0
         for rep in range(reps):
-            v = var_row[rep * voff: rep * voff + width]
-            c = const_row[place + rep * coff:]
-            for term in fn(v, c):
+            if len(g) > 5:
+                prog = g[5]
+                terms = program_terms(prog, var_row, const_row, var0 + rep * prog["variables_offset"], place,
+                                      place + rep * prog["constants_offset"])
+            else:
+                fn, width, _, (voff, coff) = GATES[name]
+                terms = fn(var_row[var0 + rep * voff: var0 + rep * voff + width], const_row[place + rep * coff:])
+            for term in terms:
                 a0 = (a0 + term * alphas[k][0]) % P
                 a1 = (a1 + term * alphas[k][1]) % P
                 k += 1

@@ -57,7 +57,8 @@ def _serde(digests, hasher):
 def prove(variables, sigmas, constants, gates, quotient_degree, fri_lde_factor, cap_size, security_level=100, lookup=None,
           public_inputs=(), hasher="poseidon2", transcript=None):
     """variables / sigmas: [V, n], constants: [C, n] uint64 arrays in natural row order; gates: [(name, repetitions, selector
-    path)] of oracle/gates.py in registration order; lookup: None or dict(width, num_repetitions, variables_offset,
+    path[, first variable column, first constant column[, recorded program]])] as oracle/gates.py::quotient_gates_row takes them,
+    in the order of their quotient terms (specialised-column gates first); lookup: None or dict(width, num_repetitions, variables_offset,
     table_id_column, tables [width + 1, n], multiplicities [n]); public_inputs: [(column, row)]."""
     variables, sigmas, constants = (np.asarray(a, dtype=np.uint64) % np.uint64(P) for a in (variables, sigmas, constants))
     V, n = variables.shape
@@ -121,7 +122,8 @@ def prove(variables, sigmas, constants, gates, quotient_degree, fri_lde_factor, 
 
     # ---- round 3: quotient (prover.rs:560-1495), point by point over the first Q cosets of the LDE domain ----
     alpha = tr.get_ext_challenge()
-    n_gate_terms = sum(reps for _, reps, _ in gates)                     # one term per repetition for the three bench gates
+    # one term per repetition for the three bench gates; a gate given as a recorded program pushes len(writes) per repetition
+    n_gate_terms = sum(g[1] * (len(g[5]["writes"]) if len(g) > 5 else 1) for g in gates)
     n_lk_terms = nsub + 1 if lk else 0                                   # lookup terms come first (prover.rs:608-625)
     total_terms = n_lk_terms + n_gate_terms + 1 + 1 + n_partial
     powers = R.ext_powers(alpha, total_terms)

@@ -374,6 +374,31 @@ def test_proof_equals_the_cpu_oracle_prover(env, log_n, V, L, cap, lookup, pis, 
     assert json.dumps(got, sort_keys=True) == json.dumps(want, sort_keys=True)
 
 
+@pytest.mark.parametrize("log_n,cap,hasher", [(5, 4, "poseidon2"), (4, 4, "blake2s")])
+def test_production_shaped_proof_equals_the_cpu_oracle_prover(env, log_n, cap, hasher):
+    """the production shape at proof level: the geometry of the reference's vk.json - 11 gates as recorded programs (the Poseidon2
+    flattened gate, the boolean gate on a specialised column, ...), 8 lookups of width 3, quotient degree 8 over fri_lde_factor 2,
+    public inputs - generated on the CPU; bj_prove (device interpreter with all peephole passes) returns bit for bit the proof of
+    the oracle's CPU prover, which evaluates the recorded programs relation by relation in Python integers."""
+    bj, ctx, prover, synthetic = env
+    from oracle import circuits, prover as OP
+    from tests.test_oracle_prover_cpu import production_gates
+    c = circuits.production_shaped(log_n, seed=40 + log_n)
+    dicts, tuples = production_gates()
+    pis = ((0, 3), (1, 3), (2, 7))
+    want, want_setup_cap = OP.prove(c["variables"], c["sigmas"], c["constants"], tuples, 8, 2, cap, lookup=c["lookup"], public_inputs=pis,
+                                    hasher=hasher)
+    lk = dict(c["lookup"], tables=bj.to_device(c["lookup"]["tables"]), multiplicities=bj.to_device(c["lookup"]["multiplicities"]))
+    cfg = prover.ProofConfig(fri_lde_factor=2, merkle_tree_cap_size=cap, security_level=100, hasher=hasher, transcript=hasher)
+    nat = ctx.native_setup(bj.to_device(c["sigmas"]), bj.to_device(c["constants"]), dicts, 8, cfg, lookup=lk, public_inputs=list(pis))
+    assert np.array_equal(nat.get_cap(), want_setup_cap)
+    got = nat.prove(bj.to_device(c["variables"]), lk["multiplicities"])
+    nat.close()
+    for key in want:
+        assert got[key] == want[key], key
+    assert json.dumps(got, sort_keys=True) == json.dumps(want, sort_keys=True)
+
+
 def test_recursive_mode_poseidon2_type_parameters(env):
     """H = GoldilocksPoseidon2Sponge, TR = GoldilocksPoisedonTranscript (Poseidon v1 sponge): the type parameters of
     run_sha256_prover_recursive_mode_poseidon2 (src/gadgets/sha256/mod.rs:286-293, BASELINE configs[4]).  Both drivers give the

@@ -56,3 +56,34 @@ def test_cpu_prover_refuses_an_unsatisfied_witness():
     w[7, 11] ^= 1
     with pytest.raises((ValueError, AssertionError)):
         OP.prove(w, c["sigmas"], c["constants"], c["gates"], c["quotient_degree"], 8, 16)
+
+
+def production_gates():
+    """the 11 gates of the reference's vk.json as placed recorded programs: (GPU-side dicts, oracle-side tuples)"""
+    from era_boojum_b200 import gate_library as GL
+    gp = [GL.CONSTANT_ALLOCATOR, GL.U8X4_FMA, GL.poseidon2_flattened_gate(130, 0), GL.DOT_PRODUCT4, GL.ZERO_CHECK, GL.FMA, GL.UINTX_ADD,
+          GL.SELECTION, GL.PARALLEL_SELECTION4, GL.NOP, GL.REDUCTION4]
+    dicts = [GL.placed(GL.BOOLEAN, 1, [], constants_placement_offset=8, variables_initial_offset=154)]
+    for gate, path in zip(gp, circuits.PRODUCTION_PATHS):
+        if gate.terms:
+            dicts.append(GL.placed(gate, gate.num_repetitions_in_geometry(130, 0, 4), path))
+    tuples = [(g["name"], g["num_repetitions"], g["selector_path"], g["variables_initial_offset"], g["constants_placement_offset"], g)
+              for g in dicts]
+    return dicts, tuples
+
+
+def test_cpu_prover_production_shaped_circuit():
+    """the geometry of the reference's vk.json (11 gates as recorded programs incl. the Poseidon2 flattened gate and the
+    specialised boolean gate, lookups of width 3, quotient degree 8 over LDE factor 2) through the CPU prover and the verifier"""
+    c = circuits.production_shaped(4, seed=2)
+    dicts, tuples = production_gates()
+    assert sum(len(g["writes"]) * g["num_repetitions"] for g in dicts) == 415
+    pis = ((0, 3), (1, 3))
+    proof, setup_cap = OP.prove(c["variables"], c["sigmas"], c["constants"], tuples, 8, 2, 4, lookup=c["lookup"], public_inputs=pis)
+    vk = vk_of(dict(c, gates=[]), 2, 4, setup_cap, pis)
+    vk["gates"] = [t[:5] + ({k: t[5][k] for k in ("relations", "writes", "variables_offset", "constants_offset")},) for t in tuples]
+    assert OV.verify(vk, proof)
+    w = c["variables"].copy()
+    w[154, 5] = 2                                    # breaks the boolean gate on its specialised column
+    with pytest.raises((ValueError, AssertionError)):
+        OP.prove(w, c["sigmas"], c["constants"], tuples, 8, 2, 4, lookup=c["lookup"])
