@@ -124,7 +124,7 @@ def _prove_sharded_threads(bj, prover, synthetic, world, log_n, V, lde, cap, see
 
 
 @pytest.mark.parametrize("world,log_n,V,lde,cap,lookup", [(2, 9, 20, 8, 16, False), (4, 8, 60, 8, 16, True), (8, 8, 20, 8, 16, False),
-                                                          (2, 10, 60, 4, 8, True)])
+                                                          (2, 10, 60, 4, 8, True), (2, 10, 60, 2, 16, True)])   # last: LDE factor 2 < quotient degree 4
 def test_coset_sharded_prover_equals_single_gpu(env, world, log_n, V, lde, cap, lookup):
     """the multi-GPU decomposition (every rank holds the cosets j = rank mod world; caps, quotient cosets, openings, the
     last FRI codeword and the query answers are exchanged) yields the SAME proof as the single-context prover."""
