@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(128) gate_eval_kernel(const GateEvalParams p) 
             const u64 a0 = __ldg(alpha_rep + 2 * dst), a1 = __ldg(alpha_rep + 2 * dst + 1);
 #pragma unroll
             for (int k = 0; k < K; k++) {
-              acc[k].c0 = gl::add(acc[k].c0, gl::mul(r[k], a0));
-              acc[k].c1 = gl::add(acc[k].c1, gl::mul(r[k], a1));
+              acc[k].c0 = gl::fma_lazy(r[k], a0, acc[k].c0);  // the running sum enters the 128-bit product before its one reduction
+              acc[k].c1 = gl::fma_lazy(r[k], a1, acc[k].c1);
             }
           } else {
             tmp.store(dst, r);
