@@ -114,3 +114,76 @@ def test_compiler_rejects_bad_programs():
     for g in bad_programs:
         with pytest.raises(bj.BoojumError):
             bj.compile_gate_programs([g], 4, 0, 1)
+
+
+def _random_program(rnd, n_rel, n_vars, n_consts_per_rep, n_shared):
+    """a random SSA program in the recorded form: operands favour recent temporaries (single-use chains, the shapes the peephole
+    passes rewrite), immediates include 0, 1, small and full-width values, some terms are bare columns / constants"""
+    N = bj.native
+    V, C, CS, T, K = N.IDX_VARIABLE, N.IDX_CONSTANT_POLY, N.IDX_CONSTANT_POLY_SHARED, N.IDX_TEMPORARY, N.IDX_CONSTANT_VALUE
+    imms = [0, 1, 1, 2, 3, 7, 1 << 20, (1 << 28) - 1, 1 << 28, (1 << 32) - 1, 1 << 32, P - 1, rnd.randrange(P)]
+    rel = []
+
+    def operand(i):
+        x = rnd.random()
+        if i and x < 0.55:
+            return (T, i - 1 - min(i - 1, int(rnd.expovariate(0.7))))
+        if x < 0.70:
+            return (V, rnd.randrange(n_vars))
+        if x < 0.78 and n_consts_per_rep:
+            return (C, rnd.randrange(n_consts_per_rep))
+        if x < 0.84 and n_shared:
+            return (CS, rnd.randrange(n_shared))
+        return (K, rnd.choice(imms))
+    for i in range(n_rel):
+        op = rnd.choices([N.REL_ADD, N.REL_SUB, N.REL_MUL, N.REL_DOUBLE, N.REL_NEGATE, N.REL_SQUARE, N.REL_INVERSE],
+                         weights=[34, 10, 34, 6, 5, 9, 2])[0]
+        binary = op in (N.REL_ADD, N.REL_SUB, N.REL_MUL)
+        rel.append((op, i, operand(i), operand(i) if binary else None))
+    n_writes = rnd.randrange(1, 6)
+    writes = [(T, rnd.randrange(n_rel)) if rnd.random() < 0.85 else rnd.choice([(V, rnd.randrange(n_vars)), (K, rnd.randrange(P))])
+              for _ in range(n_writes)]
+    if rnd.random() < 0.5:
+        writes[-1] = (T, n_rel - 1)
+    return rel, writes
+
+
+def _interpret(rel, writes, var_v, const_v, var_base, shared_base, const_base):
+    N = bj.native
+    tmp = {}
+
+    def fetch(o):
+        kind, val = o
+        return {N.IDX_VARIABLE: lambda: var_v[var_base + val], N.IDX_CONSTANT_POLY: lambda: const_v[const_base + val],
+                N.IDX_CONSTANT_POLY_SHARED: lambda: const_v[shared_base + val], N.IDX_TEMPORARY: lambda: tmp[val],
+                N.IDX_CONSTANT_VALUE: lambda: val % P}[kind]()
+    for op, dst, a, b in rel:
+        x = fetch(a)
+        y = fetch(b) if b is not None else None
+        tmp[dst] = {N.REL_ADD: lambda: x + y, N.REL_SUB: lambda: x - y, N.REL_MUL: lambda: x * y, N.REL_DOUBLE: lambda: 2 * x,
+                    N.REL_NEGATE: lambda: -x, N.REL_SQUARE: lambda: x * x, N.REL_INVERSE: lambda: pow(x, P - 2, P)}[op]() % P
+    return [fetch(w) % P for w in writes]
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_compiler_on_random_programs(seed):
+    """the peephole passes, the push placement and the slot allocation on programs nobody wrote by hand: for random SSA programs
+    the compiled steps (every combination of passes) compute what a direct interpretation of the recorded program computes"""
+    rnd = random.Random(1000 + seed)
+    n_vars_rep, n_consts_rep, n_shared, reps = rnd.randrange(2, 7), rnd.randrange(0, 3), rnd.randrange(0, 3), rnd.randrange(1, 4)
+    rel, writes = _random_program(rnd, rnd.randrange(3, 160), n_vars_rep, n_consts_rep, n_shared)
+    var0, place = rnd.randrange(0, 3), rnd.randrange(0, 3)
+    gate = dict(name="random", relations=rel, writes=writes, num_repetitions=reps, variables_offset=n_vars_rep,
+                constants_offset=n_consts_rep, constants_placement_offset=place, selector_path=[True] * place,
+                variables_initial_offset=var0)
+    n_vars = var0 + n_vars_rep * reps
+    n_consts = place + max(n_shared, n_consts_rep * reps, 1)
+    var_v = [rnd.randrange(P) for _ in range(n_vars)]
+    const_v = [rnd.randrange(P) for _ in range(n_consts)]
+    want = []
+    for rep in range(reps):
+        want += _interpret(rel, writes, var_v, const_v, var0 + rep * n_vars_rep, place, place + rep * n_consts_rep)
+    for peephole in (0, 1, 2, 3, 4, 5, 7, 8, 9, 11, 13, 15):
+        records, first, live = bj.compile_gate_programs([gate], n_vars, 0, n_consts, peephole)
+        got = emulate(records, first[0], first[1], var_v + const_v, reps, len(writes))
+        assert got == want, (seed, peephole)
