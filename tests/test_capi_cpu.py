@@ -73,3 +73,13 @@ def test_no_cpu_fallback(native):
     import era_boojum_b200 as bj
     with pytest.raises(bj.BoojumError):
         bj.Context(0)
+
+
+@pytest.mark.parametrize("log_n,cols", [(4, 1), (10, 60), (16, 93), (20, 155), (22, 93)])
+def test_non_residues_for_copy_permutation_host(native, log_n, cols):
+    """bj_non_residues_for_copy_permutation (host code; make_non_residues, src/cs/implementations/utils.rs:636-688) against the
+    Python-int restatement: k_0 = 1, then the smallest quadratic non-residues whose n-th powers are pairwise distinct and != 1"""
+    from oracle.stage2 import non_residues_for_copy_permutation
+    out = (ctypes.c_uint64 * cols)()
+    assert native.lib.bj_non_residues_for_copy_permutation(1 << log_n, cols, out) == 0
+    assert list(out) == non_residues_for_copy_permutation(1 << log_n, cols)
